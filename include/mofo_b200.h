@@ -1,0 +1,173 @@
+/* libmofo_sm100.so — C ABI of the B200-native MOFO pretraining hot path.
+ *
+ * The reference (Moohnai/MOFO) has no FFI layer: the hot path is plain PyTorch reached through the Python
+ * modules masking_generator / modeling_pretrain / engine_for_pretraining.  Every entry point
+ * below names the reference code (file:line under the MOFO tree) whose device work it replaces; the Python
+ * look-alike modules in mofo_b200/ bind them with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; all pointers are DEVICE pointers unless stated otherwise.
+ *   - every call returns 0 on success or a negative mofo status; mofo_last_error() returns a thread-local message.
+ *   - every call takes the CUDA stream it launches on (cudaStream_t passed as void*); no call synchronises,
+ *     allocates device memory or takes ownership of anything.  Outputs and workspaces are caller-allocated.
+ *   - bf16 tensors are passed as mofo_bf16* (raw 16-bit storage); "rows" are tokens, row-major, leading
+ *     dimension given in elements.
+ *   - token n of a clip = t*(H'*W') + h*W' + w; feature orders are stated per call.
+ */
+#ifndef MOFO_B200_H_
+#define MOFO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOFO_B200_VERSION 100
+
+typedef uint16_t mofo_bf16;
+
+/* status codes */
+#define MOFO_STATUS_OK 0
+#define MOFO_STATUS_INVALID (-1)
+#define MOFO_STATUS_CUDA (-2)
+#define MOFO_STATUS_UNSUPPORTED (-3)
+
+int mofo_version(void);
+const char* mofo_last_error(void);
+int mofo_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (1) Tube masking with the motion-box constraint.
+ * Replaces TubeMaskingGenerator_BB.__call__ (masking_generator.py:43-85) for a batch of clips, bit-exact given the
+ * same random draw.  bb_first[b] = the FIRST frame's box (x1,y1,x2,y2) (the reference reads bb[0] only, :46,55).
+ * rng_words[b, 0..W) = the raw 32-bit MT19937 outputs numpy's legacy shuffle would consume for clip b.
+ * Outputs: mask[b, T*H*Wd] (1 = masked), vis_idx[b, T*(H*Wd-n_mask)] / msk_idx[b, T*n_mask] = ascending token ids
+ * (what x[~mask] / x[mask] enumerate, modeling_pretrain.py:90,261-262), words_used[b] (-1 if W was too small).
+ * mofo_tube_mask_plain is the non-BB generator (masking_generator.py:17-24).
+ */
+int mofo_tube_mask_bb(const double* bb_first, const uint32_t* rng_words, int B, int W, int T, int H, int Wd,
+                      int n_mask_per_frame, double ratio_bb, uint8_t* mask, int32_t* vis_idx, int32_t* msk_idx,
+                      int32_t* words_used, void* stream);
+int mofo_tube_mask_plain(const uint32_t* rng_words, int B, int W, int T, int H, int Wd, int n_mask_per_frame,
+                         uint8_t* mask, int32_t* vis_idx, int32_t* msk_idx, int32_t* words_used, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (2) Tubelet gather for the patch embedding.
+ * Replaces the input side of PatchEmbed.forward (Conv3d k=s=(2,16,16), modeling_finetune.py:238-248) followed by
+ * x[~mask] (modeling_pretrain.py:90): only the visible tubes are read.  Writes the im2col matrix
+ * A[b*n_idx + j, c*512 + p0*256 + p1*16 + p2] = video[b, c, 2t+p0, 16h+p1, 16w+p2] in bf16, where (t,h,w) is token
+ * idx[b, j].  Feature order (c,p0,p1,p2) = the flattened Conv3d weight order, so the embedding is A · W^T.
+ * video: f32 [B,3,frames,size,size] contiguous (NCTHW).  tubelet 2, patch 16 are fixed (modeling_pretrain.py:112).
+ */
+int mofo_gather_tubes(const float* video, const int32_t* idx, int B, int n_idx, int frames, int size,
+                      mofo_bf16* A, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (3) Dense layers on tcgen05 tensor cores (bf16 x bf16 -> f32 accumulate in TMEM).
+ * mofo_gemm_tn:  C[M,N] = epilogue( A[M,K] · B[N,K]^T ), A and B row-major bf16 (both K-contiguous).
+ *   Replaces F.linear / nn.Linear forward (modeling_finetune.py:45-50,82-85,96; modeling_pretrain.py:156,256) and,
+ *   with B = W^T (bf16 copy kept by the caller), the input-gradient GEMMs of their backward.
+ * Epilogues (aux pointers may be NULL when unused):
+ *   BIAS_BF16       out0 bf16 = acc + bias[n]
+ *   BIAS_GELU_BF16  out0 bf16 = acc + bias[n] (pre-activation, kept for backward); out1 bf16 = gelu_erf(out0)
+ *                   (Mlp.forward fc1 + nn.GELU, modeling_finetune.py:45-46)
+ *   BIAS_RESID_F32  out0 f32 = acc + bias[n] + resid[m,n]  (residual add of Block.forward, :218-219)
+ *   PLAIN_BF16      out0 bf16 = acc
+ *   GELU_BWD_BF16   out0 bf16 = acc * gelu_erf'(aux_bf16[m,n])   (backward through nn.GELU)
+ *   BIAS_POS_F32    out0 f32 [row' , n] = acc + bias[n] + pos[row_idx[m], n]; row' = (m / group_rows) *
+ *                   out_group_rows + m % group_rows.  With bias = patch-embed bias this is "+ pos_embed" then the
+ *                   visible gather (modeling_pretrain.py:85-90); with bias = NULL, group_rows = N_vis,
+ *                   out_group_rows = N it is encoder_to_decoder + pos_emd_vis written in place of the
+ *                   torch.cat of :260-263.
+ * bias/pos/resid are f32.  ld* in elements.  Requirements: K % 8 == 0, N % 8 == 0, 16-byte aligned bases.
+ */
+enum {
+  MOFO_EPI_BIAS_BF16 = 0,
+  MOFO_EPI_BIAS_GELU_BF16 = 1,
+  MOFO_EPI_BIAS_RESID_F32 = 2,
+  MOFO_EPI_PLAIN_BF16 = 3,
+  MOFO_EPI_GELU_BWD_BF16 = 4,
+  MOFO_EPI_BIAS_POS_F32 = 5
+};
+int mofo_gemm_tn(const mofo_bf16* A, int lda, const mofo_bf16* B, int ldb, int M, int N, int K, int epilogue,
+                 const float* bias, const float* resid, int ldr, const mofo_bf16* aux_bf16, int ldaux,
+                 const float* pos, const int32_t* row_idx, int group_rows, int out_group_rows, void* out0, int ldo0,
+                 void* out1, int ldo1, void* stream);
+
+/* mofo_gemm_wgrad: dW[N,K] += dY[M,N]^T · X[M,K]   (f32 accumulate into dW with red.global.add; dW must hold the
+ * running sum, e.g. a zeroed slice of the gradient arena).  Replaces the weight-gradient GEMM of every nn.Linear /
+ * the Conv3d patch embedding in autograd's backward (utils.py:354 scale(loss).backward()).
+ * dY, X row-major bf16; reduction runs over rows, split across CTAs.  N % 8 == 0, K % 8 == 0. */
+int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, int M, int N, int K, float* dW,
+                    int ldw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (4) Fused multi-head attention, head_dim 64 (every registry model, modeling_pretrain.py:268-338).
+ * Replaces Attention.forward lines modeling_finetune.py:85-95 (split heads, q*scale, softmax(q k^T), attn @ v,
+ * merge heads) and their backward.  qkv: bf16 [B*S, 3*H*64] = output of the QKV linear (q | k | v, each H*64 wide);
+ * out: bf16 [B*S, H*64]; lse: f32 [B,H,S] (log2-domain log-sum-exp kept for backward).
+ * Backward: dqkv bf16 [B*S, 3*H*64]; delta: f32 workspace [B,H,S].
+ */
+int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_bf16* out, float* lse, void* stream);
+int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* dout, const float* lse, int B, int S,
+                  int H, float scale, mofo_bf16* dqkv, float* delta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (5) LayerNorm (eps 1e-6; nn.LayerNorm at modeling_finetune.py:200,206, modeling_pretrain.py:51,123).
+ * Row selection: logical row m reads x row (m / group_rows) * in_group_rows + in_row_offset + m % group_rows
+ * (group_rows = M, in_group_rows = M, offset 0 for a plain call; decoder.norm on x[:, -N_mask:] uses
+ * group_rows = N_mask, in_group_rows = N, offset = N - N_mask; modeling_pretrain.py:156).
+ * fwd: y bf16 [M,D] (dense), mean/rstd f32 [M].
+ * bwd: dx = LN'(dy) (+ dres[row] if dres != NULL) written to dx_f32 / dx_bf16 at the mapped x rows (either may be
+ *      NULL); dgamma/dbeta f32 [D] are accumulated with atomics (caller zeroes them).
+ */
+int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int D, float eps,
+                       int group_rows, int in_group_rows, int in_row_offset, mofo_bf16* y, float* mean, float* rstd,
+                       void* stream);
+int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       const float* dres, int M, int D, int group_rows, int in_group_rows, int in_row_offset,
+                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (6) Decoder input assembly, masked rows (modeling_pretrain.py:260-263): for each clip b and masked slot j,
+ * x_full[b, n_vis + j, :] = mask_token + pos[msk_idx[b,j], :]  (f32).  The visible rows are written by the
+ * encoder_to_decoder GEMM (BIAS_POS_F32 epilogue).  bwd: dmask_token[Dd] += sum over b,j of dx_full[b, n_vis+j, :],
+ * and dvis bf16 [B*n_vis, Dd] = dx_full[b, j<n_vis, :] (the gradient entering encoder_to_decoder).
+ */
+int mofo_decoder_assemble_fwd(const float* mask_token, const float* pos, const int32_t* msk_idx, int B, int n_vis,
+                              int n_msk, int Dd, float* x_full, void* stream);
+int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk, int Dd, float* dmask_token,
+                              mofo_bf16* dvis, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (7) Target + loss (engine_for_pretraining.py:258-304): un-normalise with ImageNet mean/std (:260-265), patchify
+ * 'b c (t p0) (h p1) (w p2) -> b (t h w) (p0 p1 p2) c' (:268), per-(tube,channel) mean / unbiased std + 1e-6
+ * (:269-270), flatten to feature f = p*3 + c (:276), gather the masked tubes (:285-286), MSE mean (:301-304).
+ * One CTA per masked tube; the labels are never materialised.
+ *   pred bf16 [B*n_msk, 1536] (model output), msk_idx [B, n_msk];
+ *   loss_partials f32 [B*n_msk] = per-tube sum of squared errors; loss f32[1] = mean (second tiny kernel);
+ *   dpred bf16 [B*n_msk, 1536] = dloss/dpred * grad_scale = 2 (pred - label) / (B*n_msk*1536) * grad_scale
+ *   (NULL to skip); labels_out f32 [B*n_msk,1536] optional debug/test output (NULL in production).
+ * normalize_target = 0 selects the reference's un-normalised branch (:280).
+ */
+int mofo_target_mse(const float* video, const int32_t* msk_idx, const mofo_bf16* pred, int B, int n_msk, int frames,
+                    int size, int normalize_target, float grad_scale, float* loss_partials, float* loss,
+                    mofo_bf16* dpred, float* labels_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (8) Small dense helpers used by the step.
+ * mofo_cast_weight: f32 master weight W[R,C] -> bf16 W (row-major, may be NULL) and bf16 W^T [C,R] (may be NULL).
+ * mofo_pack_qkv_bias: out f32[3*D] = [q_bias, 0, v_bias]   (modeling_finetune.py:82-84).
+ * mofo_colsum_bf16: out f32[N] += column sums of a bf16 [M,N] matrix (bias gradients; caller zeroes out).
+ * mofo_sq_norm_f32: out f32[1] += sum(x^2) over n elements (gradient-norm of the arena, utils.py:376-388).
+ */
+int mofo_cast_weight(const float* W, int R, int C, mofo_bf16* W_bf16, mofo_bf16* Wt_bf16, void* stream);
+int mofo_pack_qkv_bias(const float* q_bias, const float* v_bias, int D, float* out, void* stream);
+int mofo_colsum_bf16(const mofo_bf16* X, int ldx, int M, int N, float* out, void* stream);
+int mofo_sq_norm_f32(const float* x, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOFO_B200_H_ */

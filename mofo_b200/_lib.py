@@ -1,0 +1,211 @@
+"""ctypes binding of libmofo_sm100.so (the C ABI declared in include/mofo_b200.h).
+
+The library is the only compute path: there is no CPU or PyTorch fallback.  Loading fails loudly if
+the shared object is missing (run ``python -m mofo_b200.build``), and every call raises ``MofoError``
+with the library's message on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmofo_sm100.so")
+
+EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PLAIN_BF16, EPI_GELU_BWD_BF16, EPI_BIAS_POS_F32 = range(6)
+
+# symbol -> argtypes ; must list every function declared in include/mofo_b200.h
+_P, _I, _F, _D, _L = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64
+SIGNATURES = {
+    "mofo_version": ([], C.c_int),
+    "mofo_last_error": ([], C.c_char_p),
+    "mofo_sm_count": ([], C.c_int),
+    "mofo_tube_mask_bb": ([_P, _P, _I, _I, _I, _I, _I, _I, _D, _P, _P, _P, _P, _P], C.c_int),
+    "mofo_tube_mask_plain": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
+    "mofo_gather_tubes": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
+    "mofo_gemm_tn": ([_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P, _I, _P], C.c_int),
+    "mofo_gemm_wgrad": ([_P, _I, _P, _I, _I, _I, _I, _P, _I, _P], C.c_int),
+    "mofo_attn_fwd": ([_P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
+    "mofo_attn_bwd": ([_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
+    "mofo_layernorm_fwd": ([_P, _P, _P, _I, _I, _F, _I, _I, _I, _P, _P, _P, _P], C.c_int),
+    "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
+    "mofo_decoder_assemble_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
+    "mofo_decoder_assemble_bwd": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
+    "mofo_target_mse": ([_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P], C.c_int),
+    "mofo_cast_weight": ([_P, _I, _I, _P, _P, _P], C.c_int),
+    "mofo_pack_qkv_bias": ([_P, _P, _I, _P, _P], C.c_int),
+    "mofo_colsum_bf16": ([_P, _I, _I, _I, _P, _P], C.c_int),
+    "mofo_sq_norm_f32": ([_P, _L, _P, _P], C.c_int),
+}
+
+
+class MofoError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library and bind every declared symbol (raises if any is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MofoError(f"{LIB_PATH} not found: build it with `python -m mofo_b200.build` "
+                        "(there is no CPU/PyTorch fallback for the MOFO hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().mofo_last_error()
+        raise MofoError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "mofo_b200 kernels take CUDA tensors only"
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------------------------
+# thin tensor-level wrappers (shape bookkeeping only; all arithmetic happens in the library)
+# ------------------------------------------------------------------------------------------------
+def tube_mask_bb(bb_first, rng_words, grid, n_mask_per_frame, ratio_bb):
+    """bb_first f64 [B,4], rng_words u32-as-int32/uint32 [B,W] (CUDA) -> mask u8 [B,N], vis_idx, msk_idx, words_used."""
+    T, H, Wd = grid
+    B, W = rng_words.shape
+    npf = H * Wd
+    dev = rng_words.device
+    mask = torch.empty(B, T * npf, dtype=torch.uint8, device=dev)
+    vis = torch.empty(B, T * (npf - n_mask_per_frame), dtype=torch.int32, device=dev)
+    msk = torch.empty(B, T * n_mask_per_frame, dtype=torch.int32, device=dev)
+    used = torch.empty(B, dtype=torch.int32, device=dev)
+    if bb_first is None:
+        _check(load().mofo_tube_mask_plain(_ptr(rng_words), B, W, T, H, Wd, n_mask_per_frame, _ptr(mask), _ptr(vis),
+                                           _ptr(msk), _ptr(used), _stream()), "mofo_tube_mask_plain")
+    else:
+        assert bb_first.dtype == torch.float64 and bb_first.shape == (B, 4) and bb_first.is_contiguous()
+        _check(load().mofo_tube_mask_bb(_ptr(bb_first), _ptr(rng_words), B, W, T, H, Wd, n_mask_per_frame,
+                                        float(ratio_bb), _ptr(mask), _ptr(vis), _ptr(msk), _ptr(used), _stream()),
+               "mofo_tube_mask_bb")
+    return mask, vis, msk, used
+
+
+def gather_tubes(video, idx, out=None):
+    B, Cc, frames, size, _ = video.shape
+    assert Cc == 3 and video.dtype == torch.float32 and video.is_contiguous() and idx.dtype == torch.int32
+    n = idx.shape[1]
+    if out is None:
+        out = torch.empty(B * n, 1536, dtype=torch.bfloat16, device=video.device)
+    _check(load().mofo_gather_tubes(_ptr(video), _ptr(idx), B, n, frames, size, _ptr(out), _stream()), "mofo_gather_tubes")
+    return out
+
+
+def gemm_tn(A, Bm, epilogue, out0, out1=None, bias=None, resid=None, aux=None, pos=None, row_idx=None,
+            group_rows=0, out_group_rows=0, M=None):
+    """out0 = epi(A[M,K] @ Bm[N,K]^T).  A/Bm bf16 row-major (last dim contiguous)."""
+    M = A.shape[0] if M is None else M
+    K = A.shape[1]
+    N = Bm.shape[0]
+    assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16 and Bm.shape[1] == K
+    assert A.stride(1) == 1 and Bm.stride(1) == 1 and out0.stride(-1) == 1
+    _check(load().mofo_gemm_tn(_ptr(A), A.stride(0), _ptr(Bm), Bm.stride(0), M, N, K, epilogue, _ptr(bias), _ptr(resid),
+                               resid.stride(0) if resid is not None else 0, _ptr(aux),
+                               aux.stride(0) if aux is not None else 0, _ptr(pos), _ptr(row_idx), group_rows,
+                               out_group_rows, _ptr(out0), out0.stride(0), _ptr(out1),
+                               out1.stride(0) if out1 is not None else 0, _stream()), "mofo_gemm_tn")
+    return out0
+
+
+def gemm_wgrad(dY, X, dW, M=None):
+    """dW[N,K] += dY[M,N]^T @ X[M,K]  (dW f32, accumulated)."""
+    M = dY.shape[0] if M is None else M
+    N, K = dY.shape[1], X.shape[1]
+    assert dY.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dW.dtype == torch.float32
+    assert dY.stride(1) == 1 and X.stride(1) == 1 and dW.stride(-1) == 1 and dW.numel() == N * K
+    _check(load().mofo_gemm_wgrad(_ptr(dY), dY.stride(0), _ptr(X), X.stride(0), M, N, K, _ptr(dW), K, _stream()),
+           "mofo_gemm_wgrad")
+    return dW
+
+
+def attn_fwd(qkv, B, S, H, scale, out, lse):
+    _check(load().mofo_attn_fwd(_ptr(qkv), B, S, H, float(scale), _ptr(out), _ptr(lse), _stream()), "mofo_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, B, S, H, scale, dqkv, delta):
+    _check(load().mofo_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), B, S, H, float(scale), _ptr(dqkv),
+                                _ptr(delta), _stream()), "mofo_attn_bwd")
+    return dqkv
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, M, D, eps=1e-6, group_rows=0, in_group_rows=0, in_row_offset=0):
+    g = group_rows if group_rows > 0 else M
+    ig = in_group_rows if in_group_rows > 0 else M
+    _check(load().mofo_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), M, D, eps, g, ig, in_row_offset, _ptr(y),
+                                     _ptr(mean), _ptr(rstd), _stream()), "mofo_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres, M, D, dx_f32, dx_bf16, dgamma, dbeta, group_rows=0,
+                  in_group_rows=0, in_row_offset=0):
+    g = group_rows if group_rows > 0 else M
+    ig = in_group_rows if in_group_rows > 0 else M
+    _check(load().mofo_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), M, D, g, ig,
+                                     in_row_offset, _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _stream()),
+           "mofo_layernorm_bwd")
+
+
+def decoder_assemble_fwd(mask_token, pos, msk_idx, B, n_vis, n_msk, Dd, x_full):
+    _check(load().mofo_decoder_assemble_fwd(_ptr(mask_token), _ptr(pos), _ptr(msk_idx), B, n_vis, n_msk, Dd,
+                                            _ptr(x_full), _stream()), "mofo_decoder_assemble_fwd")
+
+
+def decoder_assemble_bwd(dx_full, B, n_vis, n_msk, Dd, dmask_token, dvis):
+    _check(load().mofo_decoder_assemble_bwd(_ptr(dx_full), B, n_vis, n_msk, Dd, _ptr(dmask_token), _ptr(dvis),
+                                            _stream()), "mofo_decoder_assemble_bwd")
+
+
+def target_mse(video, msk_idx, pred, loss_partials, loss, dpred, normalize_target=True, grad_scale=1.0,
+               labels_out=None):
+    B, _, frames, size, _ = video.shape
+    n_msk = msk_idx.shape[1]
+    _check(load().mofo_target_mse(_ptr(video), _ptr(msk_idx), _ptr(pred), B, n_msk, frames, size,
+                                  1 if normalize_target else 0, float(grad_scale), _ptr(loss_partials), _ptr(loss),
+                                  _ptr(dpred), _ptr(labels_out), _stream()), "mofo_target_mse")
+
+
+def cast_weight(W, W_bf16=None, Wt_bf16=None):
+    R = W.shape[0]
+    Cc = W.numel() // R
+    assert W.dtype == torch.float32 and W.is_contiguous()
+    _check(load().mofo_cast_weight(_ptr(W), R, Cc, _ptr(W_bf16), _ptr(Wt_bf16), _stream()), "mofo_cast_weight")
+
+
+def pack_qkv_bias(q_bias, v_bias, out):
+    _check(load().mofo_pack_qkv_bias(_ptr(q_bias), _ptr(v_bias), q_bias.numel(), _ptr(out), _stream()), "mofo_pack_qkv_bias")
+
+
+def colsum_bf16(X, M, N, out):
+    """out[N] += column sums of X[:M, :N] (X may be a column slice view; stride(0) is the leading dimension)."""
+    assert X.dtype == torch.bfloat16 and X.stride(1) == 1 and out.dtype == torch.float32
+    _check(load().mofo_colsum_bf16(_ptr(X), X.stride(0), M, N, _ptr(out), _stream()), "mofo_colsum_bf16")
+
+
+def sq_norm_f32(x, out):
+    _check(load().mofo_sq_norm_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "mofo_sq_norm_f32")

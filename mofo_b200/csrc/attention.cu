@@ -1,0 +1,537 @@
+// Fused multi-head attention (head_dim 64) on tcgen05 tensor cores, forward and backward.
+// Replaces modeling_finetune.py:85-95 (Attention.forward between the qkv and proj linears).
+//
+// Layout: qkv bf16 [B*S, 3*H*64] (q | k | v), out / dout bf16 [B*S, H*64], lse / delta f32 [B,H,S].
+// All three kernels use 128 threads: thread r owns TMEM lane r = one row of the 128-row tile, so the
+// softmax needs no cross-thread reduction.  Thread 0 additionally issues TMA loads and tcgen05.mma.
+//   S = Q K^T and friends:  both operands K-major SW128 tiles [128 rows x 64 d] straight from TMA.
+//   P V / dS K / P^T dO ...: A = bf16 tile written by the threads into a K-major SW128 layout,
+//                            B = the same TMA tile re-read as an MN-major operand (rows = reduction index).
+// Everything is kept in the log2 domain: t = s * scale * log2(e), p = exp2(t - lse2).
+#include "../../include/mofo_b200.h"
+#include "common.cuh"
+
+namespace mofo {
+
+constexpr int AT = 128;                       // tile rows (q or kv)
+constexpr int TILE_BYTES = AT * 64 * 2;       // 16 KB: [128 x 64] bf16
+constexpr int PTILE_BYTES = 2 * TILE_BYTES;   // 32 KB: [128 x 128] bf16 as two 64-wide K panels
+
+__device__ __forceinline__ void check_align(uint32_t base) {
+  if (base & 1023u) {
+    if (threadIdx.x == 0) printf("mofo: dynamic shared memory base not 1024-B aligned (0x%x)\n", base);
+    __trap();
+  }
+}
+
+// write 32 consecutive columns [c0, c0+32) of row `row` of a [128 x 128] bf16 K-major SW128 tile pair
+__device__ __forceinline__ void store_p_chunk(uint32_t tile_base, int row, int c0, const float (&v)[32]) {
+  const uint32_t panel = tile_base + (c0 >> 6) * TILE_BYTES;
+  const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t addr = panel + sw128_offset(row, chunk0 + g);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(v[g * 8 + 0], v[g * 8 + 1])),
+                 "r"(pack_bf16(v[g * 8 + 2], v[g * 8 + 3])), "r"(pack_bf16(v[g * 8 + 4], v[g * 8 + 5])),
+                 "r"(pack_bf16(v[g * 8 + 6], v[g * 8 + 7]))
+                 : "memory");
+  }
+}
+
+// issue the 4 K-steps of a [128 x 64] · [128 x 64]^T product (both K-major) into d_tmem (N = 128)
+__device__ __forceinline__ void mma_qk(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(d_tmem, umma_desc_kmajor(a_tile + k * 32), umma_desc_kmajor(b_tile + k * 32), idesc, k != 0);
+}
+// D[128 x 64] (+)= P[128 x 128] (K-major pair) · T[128 x 64] (MN-major: rows = reduction index)
+__device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t p_tile, uint32_t t_tile, bool accumulate) {
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    umma_bf16(d_tmem, umma_desc_kmajor(p_tile + (k >> 2) * TILE_BYTES + (k & 3) * 32),
+              umma_desc_mnmajor(t_tile + k * 2048, 8192), idesc, (accumulate || k != 0) ? 1u : 0u);
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+constexpr int FWD_SMEM = 7 * TILE_BYTES + 64;   // Q, K0, V0, K1, V1, P(2)  + barriers
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float c /*scale*log2e*/,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  check_align(base);
+  const uint32_t sQ = base, sP = base + 5 * TILE_BYTES;
+  auto sK = [&](int b) { return base + (1 + 2 * b) * TILE_BYTES; };
+  auto sV = [&](int b) { return base + (2 + 2 * b) * TILE_BYTES; };
+  const uint32_t bars = base + 7 * TILE_BYTES;
+  const uint32_t bar_q = bars, bar_s = bars + 8, bar_o = bars + 16, tmem_slot = bars + 40;
+  auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = b * S;
+  const int n_kv = (S + AT - 1) / AT;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_kv(0), 1); mbar_init(bar_kv(1), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_qkv);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, TILE_BYTES);
+    tma_load_2d(sQ, &tm_qkv, bar_q, h * 64, row0 + q0);
+    mbar_expect_tx(bar_kv(0), 2 * TILE_BYTES);
+    tma_load_2d(sK(0), &tm_qkv, bar_kv(0), (H + h) * 64, row0);
+    tma_load_2d(sV(0), &tm_qkv, bar_kv(0), (2 * H + h) * 64, row0);
+  }
+
+  float o_acc[64];
+#pragma unroll
+  for (int e = 0; e < 64; ++e) o_acc[e] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int buf = j & 1;
+    if (tid == 0) {
+      if (j + 1 < n_kv) {   // prefetch next K/V tile (its buffer was released by bar_o of iteration j-1)
+        mbar_expect_tx(bar_kv(buf ^ 1), 2 * TILE_BYTES);
+        tma_load_2d(sK(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * AT);
+        tma_load_2d(sV(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * AT);
+      }
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv(buf), (j >> 1) & 1);
+      tc_fence_after();
+      mma_qk(tS, sQ, sK(buf));
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, j & 1);
+    tc_fence_after();
+    const int kv_valid = S - j * AT;   // columns >= kv_valid are padding
+    // pass 1: row max
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < AT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_off + c0, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (c0 + e < kv_valid) mx = fmaxf(mx, __uint_as_float(r[e]));
+    }
+    const float m_new = fmaxf(m_run, mx * c);
+    const float alpha = exp2f(m_run - m_new);
+    // pass 2: p = exp2(t - m), row sum, bf16 P tile
+    float rs = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < AT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_off + c0, r);
+      tc_wait_ld();
+      float p[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        p[e] = (c0 + e < kv_valid) ? exp2f(__uint_as_float(r[e]) * c - m_new) : 0.f;
+        rs += p[e];
+      }
+      store_p_chunk(sP, tid, c0, p);
+    }
+    l_run = l_run * alpha + rs;
+    m_run = m_new;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mma_pv(tO, sP, sV(buf), false);
+      tc_commit(bar_o);
+    }
+    mbar_wait(bar_o, j & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_off + c0, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o_acc[c0 + e] = o_acc[c0 + e] * alpha + __uint_as_float(r[e]);
+    }
+    tc_fence_before();
+  }
+
+  const int q = q0 + tid;
+  if (q < S) {
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* dst = out + (static_cast<size_t>(row0 + q) * H + h) * 64;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint4 o;
+      o.x = pack_bf16(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
+      o.y = pack_bf16(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
+      o.z = pack_bf16(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
+      o.w = pack_bf16(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
+      reinterpret_cast<uint4*>(dst)[g] = o;
+    }
+    lse[(static_cast<size_t>(b) * H + h) * S + q] = m_run + log2f(l_run);
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// =================================================================================================
+// backward, part 0: delta[b,h,q] = sum_d dO * O
+// =================================================================================================
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int rows,
+                                  int S, int H, float* __restrict__ delta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (row, head), head fastest
+  if (i >= rows * H) return;
+  const int row = i / H, h = i % H;
+  const uint4* o = reinterpret_cast<const uint4*>(out + static_cast<size_t>(i) * 64);
+  const uint4* d = reinterpret_cast<const uint4*>(dout + static_cast<size_t>(i) * 64);
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    uint4 a = __ldg(o + g), bq = __ldg(d + g);
+    s += bf16_lo(a.x) * bf16_lo(bq.x) + bf16_hi(a.x) * bf16_hi(bq.x) + bf16_lo(a.y) * bf16_lo(bq.y) + bf16_hi(a.y) * bf16_hi(bq.y) +
+         bf16_lo(a.z) * bf16_lo(bq.z) + bf16_hi(a.z) * bf16_hi(bq.z) + bf16_lo(a.w) * bf16_lo(bq.w) + bf16_hi(a.w) * bf16_hi(bq.w);
+  }
+  const int b = row / S, q = row % S;
+  delta[(static_cast<size_t>(b) * H + h) * S + q] = s;
+}
+
+// =================================================================================================
+// backward, part 1: dQ   (CTA per (q tile, head, clip); loops over kv tiles)
+// =================================================================================================
+constexpr int DQ_SMEM = 8 * TILE_BYTES + 64;   // Q, dO, K0, V0, K1, V1, dS(2)
+
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, int S, int H,
+                   float c, float scale, const float* __restrict__ lse, const float* __restrict__ delta,
+                   __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  check_align(base);
+  const uint32_t sQ = base, sdO = base + TILE_BYTES, sdS = base + 6 * TILE_BYTES;
+  auto sK = [&](int b) { return base + (2 + 2 * b) * TILE_BYTES; };
+  auto sV = [&](int b) { return base + (3 + 2 * b) * TILE_BYTES; };
+  const uint32_t bars = base + 8 * TILE_BYTES;
+  const uint32_t bar_q = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
+  auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = b * S;
+  const int n_kv = (S + AT - 1) / AT;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1); mbar_init(bar_kv(0), 1); mbar_init(bar_kv(1), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdQ = tmem_base + 256;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+
+  const int q = q0 + tid;
+  const bool q_ok = q < S;
+  const float my_lse = q_ok ? lse[(static_cast<size_t>(b) * H + h) * S + q] : 0.f;
+  const float my_delta = q_ok ? delta[(static_cast<size_t>(b) * H + h) * S + q] : 0.f;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, 2 * TILE_BYTES);
+    tma_load_2d(sQ, &tm_qkv, bar_q, h * 64, row0 + q0);
+    tma_load_2d(sdO, &tm_do, bar_q, h * 64, row0 + q0);
+    mbar_expect_tx(bar_kv(0), 2 * TILE_BYTES);
+    tma_load_2d(sK(0), &tm_qkv, bar_kv(0), (H + h) * 64, row0);
+    tma_load_2d(sV(0), &tm_qkv, bar_kv(0), (2 * H + h) * 64, row0);
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_kv(0), 0);
+    tc_fence_after();
+    mma_qk(tS, sQ, sK(0));      // S  = Q K^T
+    mma_qk(tdP, sdO, sV(0));    // dP = dO V^T
+    tc_commit(bar_12);
+  }
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int buf = j & 1;
+    mbar_wait(bar_12, j & 1);   // also covers MMA3 of iteration j-1 (tensor pipe is in-order)
+    tc_fence_after();
+    if (tid == 0 && j + 1 < n_kv) {
+      mbar_expect_tx(bar_kv(buf ^ 1), 2 * TILE_BYTES);
+      tma_load_2d(sK(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * AT);
+      tma_load_2d(sV(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * AT);
+    }
+    const int kv_valid = S - j * AT;
+#pragma unroll 1
+    for (int c0 = 0; c0 < AT; c0 += 32) {
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tS + lane_off + c0, rs);
+      tmem_ld32(tdP + lane_off + c0, rp);
+      tc_wait_ld();
+      float ds[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const bool ok = q_ok && (c0 + e < kv_valid);
+        const float p = ok ? exp2f(__uint_as_float(rs[e]) * c - my_lse) : 0.f;
+        ds[e] = ok ? p * (__uint_as_float(rp[e]) - my_delta) : 0.f;
+      }
+      store_p_chunk(sdS, tid, c0, ds);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mma_pv(tdQ, sdS, sK(buf), j != 0);          // dQ += dS K
+      if (j + 1 < n_kv) {
+        mbar_wait(bar_kv(buf ^ 1), ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        mma_qk(tS, sQ, sK(buf ^ 1));
+        mma_qk(tdP, sdO, sV(buf ^ 1));
+        tc_commit(bar_12);
+      } else {
+        tc_commit(bar_fin);
+      }
+    }
+  }
+  mbar_wait(bar_fin, 0);
+  tc_fence_after();
+  if (true) {
+    __nv_bfloat16* dst = dqkv + static_cast<size_t>(row0 + q) * (3 * H * 64) + h * 64;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tdQ + lane_off + c0, r);
+      tc_wait_ld();
+      if (q_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[g * 8 + 0]) * scale, __uint_as_float(r[g * 8 + 1]) * scale);
+          o.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * scale, __uint_as_float(r[g * 8 + 3]) * scale);
+          o.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * scale, __uint_as_float(r[g * 8 + 5]) * scale);
+          o.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * scale, __uint_as_float(r[g * 8 + 7]) * scale);
+          reinterpret_cast<uint4*>(dst + c0)[g] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// =================================================================================================
+// backward, part 2: dK, dV   (CTA per (kv tile, head, clip); loops over q tiles)
+// =================================================================================================
+constexpr int DKV_SMEM = 10 * TILE_BYTES + 2048 + 64;   // K, V, Q0, dO0, Q1, dO1, P^T(2), dS^T(2), lse/delta x2
+
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, int S, int H,
+                    float c, float scale, const float* __restrict__ lse, const float* __restrict__ delta,
+                    __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  check_align(base);
+  const uint32_t sK = base, sV = base + TILE_BYTES, sP = base + 6 * TILE_BYTES, sdS = base + 8 * TILE_BYTES;
+  auto sQ = [&](int b) { return base + (2 + 2 * b) * TILE_BYTES; };
+  auto sdO = [&](int b) { return base + (3 + 2 * b) * TILE_BYTES; };
+  float* vec = reinterpret_cast<float*>(smem_raw + 10 * TILE_BYTES);   // [2 buffers][lse 128 | delta 128]
+  const uint32_t bars = base + 10 * TILE_BYTES + 2048;
+  const uint32_t bar_kv = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
+  auto bar_q = [&](int b) { return bars + 24 + 8 * b; };
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int kv0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
+  const int row0 = b * S;
+  const int n_q = (S + AT - 1) / AT;
+
+  if (tid == 0) {
+    mbar_init(bar_kv, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1); mbar_init(bar_q(0), 1); mbar_init(bar_q(1), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+
+  const int kv = kv0 + tid;
+  const bool kv_ok = kv < S;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_kv, 2 * TILE_BYTES);
+    tma_load_2d(sK, &tm_qkv, bar_kv, (H + h) * 64, row0 + kv0);
+    tma_load_2d(sV, &tm_qkv, bar_kv, (2 * H + h) * 64, row0 + kv0);
+    mbar_expect_tx(bar_q(0), 2 * TILE_BYTES);
+    tma_load_2d(sQ(0), &tm_qkv, bar_q(0), h * 64, row0);
+    tma_load_2d(sdO(0), &tm_do, bar_q(0), h * 64, row0);
+    mbar_wait(bar_kv, 0);
+    mbar_wait(bar_q(0), 0);
+    tc_fence_after();
+    mma_qk(tS, sK, sQ(0));       // S^T  = K Q^T
+    mma_qk(tdP, sV, sdO(0));     // dP^T = V dO^T
+    tc_commit(bar_12);
+  }
+
+  for (int i = 0; i < n_q; ++i) {
+    const int buf = i & 1;
+    {   // per-column (q) statistics of this q tile
+      const int qq = i * AT + tid;
+      const bool ok = qq < S;
+      vec[buf * 256 + tid] = ok ? lse[(static_cast<size_t>(b) * H + h) * S + qq] : 0.f;
+      vec[buf * 256 + 128 + tid] = ok ? delta[(static_cast<size_t>(b) * H + h) * S + qq] : 0.f;
+    }
+    mbar_wait(bar_12, i & 1);    // also covers MMA3/4 of iteration i-1
+    tc_fence_after();
+    __syncthreads();             // vec[] visible
+    if (tid == 0 && i + 1 < n_q) {
+      mbar_expect_tx(bar_q(buf ^ 1), 2 * TILE_BYTES);
+      tma_load_2d(sQ(buf ^ 1), &tm_qkv, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * AT);
+      tma_load_2d(sdO(buf ^ 1), &tm_do, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * AT);
+    }
+    const int q_valid = S - i * AT;
+    const float* lse_s = vec + buf * 256;
+    const float* del_s = lse_s + 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < AT; c0 += 32) {
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tS + lane_off + c0, rs);
+      tmem_ld32(tdP + lane_off + c0, rp);
+      tc_wait_ld();
+      float p[32], ds[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const bool ok = kv_ok && (c0 + e < q_valid);
+        p[e] = ok ? exp2f(__uint_as_float(rs[e]) * c - lse_s[c0 + e]) : 0.f;
+        ds[e] = ok ? p[e] * (__uint_as_float(rp[e]) - del_s[c0 + e]) : 0.f;
+      }
+      store_p_chunk(sP, tid, c0, p);
+      store_p_chunk(sdS, tid, c0, ds);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mma_pv(tdV, sP, sdO(buf), i != 0);       // dV += P^T dO
+      mma_pv(tdK, sdS, sQ(buf), i != 0);       // dK += dS^T Q
+      if (i + 1 < n_q) {
+        mbar_wait(bar_q(buf ^ 1), ((i + 1) >> 1) & 1);
+        tc_fence_after();
+        mma_qk(tS, sK, sQ(buf ^ 1));
+        mma_qk(tdP, sV, sdO(buf ^ 1));
+        tc_commit(bar_12);
+      } else {
+        tc_commit(bar_fin);
+      }
+    }
+  }
+  mbar_wait(bar_fin, 0);
+  tc_fence_after();
+  {
+    __nv_bfloat16* dk = dqkv + static_cast<size_t>(row0 + kv) * (3 * H * 64) + (H + h) * 64;
+    __nv_bfloat16* dv = dqkv + static_cast<size_t>(row0 + kv) * (3 * H * 64) + (2 * H + h) * 64;
+#pragma unroll
+    for (int half = 0; half < 4; ++half) {   // 0,1: dV cols 0-31/32-63 ; 2,3: dK
+      uint32_t r[32];
+      tmem_ld32((half < 2 ? tdV : tdK) + lane_off + (half & 1) * 32, r);
+      tc_wait_ld();
+      if (kv_ok) {
+        const float sc = half < 2 ? 1.0f : scale;
+        __nv_bfloat16* dst = (half < 2 ? dv : dk) + (half & 1) * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[g * 8 + 0]) * sc, __uint_as_float(r[g * 8 + 1]) * sc);
+          o.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * sc, __uint_as_float(r[g * 8 + 3]) * sc);
+          o.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * sc, __uint_as_float(r[g * 8 + 5]) * sc);
+          o.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * sc, __uint_as_float(r[g * 8 + 7]) * sc);
+          reinterpret_cast<uint4*>(dst)[g] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+int get_tmap(CUtensorMap* out, const void* p, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);  // gemm.cu
+
+}  // namespace mofo
+
+using namespace mofo;
+
+extern "C" {
+
+int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_bf16* out, float* lse, void* stream) {
+  MOFO_CHECK_ARG(qkv && out && lse, "attn_fwd: null pointer");
+  MOFO_CHECK_ARG(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
+  CUtensorMap tm;
+  int rc = get_tmap(&tm, qkv, static_cast<uint64_t>(B) * S, 3ull * H * 64, 3ull * H * 64, AT);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MOFO_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((S + AT - 1) / AT, H, B);
+  attn_fwd_kernel<<<grid, 128, FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, S, H, scale * 1.4426950408889634f,
+                                                                            reinterpret_cast<__nv_bfloat16*>(out), lse);
+  MOFO_LAUNCH_CHECK("attn_fwd_kernel");
+  return MOFO_OK;
+}
+
+int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* dout, const float* lse, int B, int S,
+                  int H, float scale, mofo_bf16* dqkv, float* delta, void* stream) {
+  MOFO_CHECK_ARG(qkv && out && dout && lse && dqkv && delta, "attn_bwd: null pointer");
+  MOFO_CHECK_ARG(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attn_bwd: bad shape B=%d S=%d H=%d", B, S, H);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap tq, td;
+  int rc = get_tmap(&tq, qkv, static_cast<uint64_t>(B) * S, 3ull * H * 64, 3ull * H * 64, AT);
+  if (rc) return rc;
+  rc = get_tmap(&td, dout, static_cast<uint64_t>(B) * S, 1ull * H * 64, 1ull * H * 64, AT);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MOFO_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    MOFO_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    attr_set = true;
+  }
+  const int rows = B * S;
+  attn_delta_kernel<<<(rows * H + 127) / 128, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                                           reinterpret_cast<const __nv_bfloat16*>(dout), rows, S, H, delta);
+  MOFO_LAUNCH_CHECK("attn_delta_kernel");
+  dim3 grid((S + AT - 1) / AT, H, B);
+  const float c = scale * 1.4426950408889634f;
+  attn_bwd_dq_kernel<<<grid, 128, DQ_SMEM, s>>>(tq, td, S, H, c, scale, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv));
+  MOFO_LAUNCH_CHECK("attn_bwd_dq_kernel");
+  attn_bwd_dkv_kernel<<<grid, 128, DKV_SMEM, s>>>(tq, td, S, H, c, scale, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv));
+  MOFO_LAUNCH_CHECK("attn_bwd_dkv_kernel");
+  return MOFO_OK;
+}
+
+}  // extern "C"

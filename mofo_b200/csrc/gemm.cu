@@ -1,0 +1,488 @@
+// tcgen05 / TMEM / TMA GEMM kernels for the dense layers of the MOFO pretraining step.
+//
+//   gemm_tn_kernel    C[M,N] = epi(A[M,K] · B[N,K]^T)   persistent, warp-specialised:
+//                       warp 4 = TMA producer, warp 5 = tcgen05.mma issuer (+TMEM owner),
+//                       warps 0-3 = epilogue (TMEM -> registers -> fused epilogue -> global).
+//                     128 x BN output tiles (BN = 128/192/256), BLOCK_K = 64 (one 128-byte swizzle row),
+//                     multi-stage smem ring, two TMEM accumulators so the epilogue of tile i overlaps the
+//                     main loop of tile i+1.
+//   gemm_wgrad_kernel dW[N,K] += dY[M,N]^T · X[M,K]     both operands MN-major (reduction over rows),
+//                     split over M across CTAs, fp32 red.add into the gradient arena.
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "../../include/mofo_b200.h"
+#include "common.cuh"
+
+namespace mofo {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+
+struct EpiParams {
+  const float* bias;
+  const float* resid;
+  int ldr;
+  const __nv_bfloat16* aux;
+  int ldaux;
+  const float* pos;
+  const int32_t* row_idx;
+  int group_rows, out_group_rows;
+  void* out0;
+  int ldo0;
+  void* out1;
+  int ldo1;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 o;
+  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+// One thread owns row `row`, 32 consecutive columns starting at n0 (accumulators in r[]).
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int M, int n0, int N, const uint32_t (&r)[32]) {
+  if (row >= M) return;
+  size_t orow = row;
+  const float* posrow = nullptr;
+  if (EPI == MOFO_EPI_BIAS_POS_F32) {
+    orow = static_cast<size_t>(row / ep.group_rows) * ep.out_group_rows + (row % ep.group_rows);
+    posrow = ep.pos + static_cast<size_t>(ep.row_idx[row]) * N;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = n0 + g * 8;
+    if (n >= N) break;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]);
+    if (EPI == MOFO_EPI_BIAS_BF16 || EPI == MOFO_EPI_BIAS_GELU_BF16 || EPI == MOFO_EPI_BIAS_RESID_F32 ||
+        EPI == MOFO_EPI_BIAS_POS_F32) {
+      if (ep.bias) {
+        float b[8];
+        load8(ep.bias + n, b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += b[e];
+      }
+    }
+    if (EPI == MOFO_EPI_BIAS_BF16 || EPI == MOFO_EPI_PLAIN_BF16) {
+      store8_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out0) + orow * ep.ldo0 + n, v);
+    } else if (EPI == MOFO_EPI_BIAS_GELU_BF16) {
+      // the pre-activation is rounded to bf16 first (it is what F.linear returns under autocast), GELU acts on that
+      float u[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+      store8_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out0) + orow * ep.ldo0 + n, u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) u[e] = gelu_erf(u[e]);
+      store8_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out1) + orow * ep.ldo1 + n, u);
+    } else if (EPI == MOFO_EPI_BIAS_RESID_F32) {
+      float q[8];
+      load8(ep.resid + orow * ep.ldr + n, q);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += q[e];
+      store8_f32(reinterpret_cast<float*>(ep.out0) + orow * ep.ldo0 + n, v);
+    } else if (EPI == MOFO_EPI_GELU_BWD_BF16) {
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(ep.aux + orow * ep.ldaux + n));
+      float u[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y), bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= gelu_erf_grad(u[e]);
+      store8_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out0) + orow * ep.ldo0 + n, v);
+    } else if (EPI == MOFO_EPI_BIAS_POS_F32) {
+      float q[8];
+      load8(posrow + n, q);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += q[e];
+      store8_f32(reinterpret_cast<float*>(ep.out0) + orow * ep.ldo0 + n, v);
+    }
+  }
+}
+
+template <int BN>
+struct TnCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = BN == 128 ? 6 : (BN == 192 ? 5 : 4);
+  static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+               EpiParams ep) {
+  using Cfg = TnCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_n = (N + BN - 1) / BN, num_m = (M + BM - 1) / BM;
+  const int tiles = num_m * num_n;
+  const int kblocks = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          tma_load_2d(smem_a(stage), &tmA, full_bar(stage), kb * BK, m_blk * BM);
+          tma_load_2d(smem_b(stage), &tmB, full_bar(stage), kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = umma_desc_kmajor(smem_a(stage) + k * 32);
+            const uint64_t bdesc = umma_desc_kmajor(smem_b(stage) + k * 32);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {  // ===== epilogue warps 0..3 (TMEM lanes 32*warp .. +31) =====
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tc_wait_ld();
+        epilogue_store<EPI>(ep, row, M, n_blk * BN + c0, N, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// wgrad: dW[n, k] += sum_m dY[m, n] * X[m, k]
+// ---------------------------------------------------------------------------------------------------
+template <int BNW>
+struct WgCfg {
+  static constexpr int A_BYTES = 2 * 64 * 128;            // two 64-wide n panels x 64 m rows
+  static constexpr int B_BYTES = (BNW / 64) * 64 * 128;   // BNW/64 panels
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BNW == 256 ? 4 : (BNW == 192 ? 5 : 6);
+  static constexpr int TMEM_COLS = BNW == 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BNW>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
+                  float* __restrict__ dW, int ldw, int kb_per_split) {
+  using Cfg = WgCfg<BNW>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  auto smem_a = [&](int s) { return base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = (K + BNW - 1) / BNW;
+  const int n_blk = blockIdx.x / num_k, k_blk = blockIdx.x % num_k;
+  const int kblocks_total = (M + BK - 1) / BK;
+  const int kb0 = blockIdx.y * kb_per_split;
+  const int kb1 = min(kblocks_total, kb0 + kb_per_split);
+  const int nkb = kb1 - kb0;   // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmX); }
+  if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        const int m0 = (kb0 + i) * BK;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) tma_load_2d(smem_a(stage) + p * 8192, &tmY, full_bar(stage), n_blk * 128 + p * 64, m0);
+#pragma unroll
+        for (int p = 0; p < BNW / 64; ++p) tma_load_2d(smem_b(stage) + p * 8192, &tmX, full_bar(stage), k_blk * BNW + p * 64, m0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t adesc = umma_desc_mnmajor(smem_a(stage) + k * 2048, 8192);
+          const uint64_t bdesc = umma_desc_mnmajor(smem_b(stage) + k * 2048, 8192);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(tfull_bar);
+    }
+  } else {
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int n = n_blk * 128 + warp * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BNW; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tc_wait_ld();
+      if (n < N) {
+        float* dst = dW + static_cast<size_t>(n) * ldw + k_blk * BNW + c0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (k_blk * BNW + c0 + e < K) atomicAdd(dst + e, __uint_as_float(r[e]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct TmapKey {
+  const void* p; uint64_t rows, cols, ld; uint32_t box_rows;
+  bool operator<(const TmapKey& o) const {
+    return std::tie(p, rows, cols, ld, box_rows) < std::tie(o.p, o.rows, o.cols, o.ld, o.box_rows);
+  }
+};
+static std::map<TmapKey, CUtensorMap> g_tmaps;
+static std::mutex g_tmap_mu;
+
+int get_tmap(CUtensorMap* out, const void* p, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  TmapKey k{p, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    auto it = g_tmaps.find(k);
+    if (it != g_tmaps.end()) { *out = it->second; return MOFO_OK; }
+  }
+  int rc = make_tmap_bf16_2d(out, p, rows, cols, ld, box_rows);
+  if (rc != MOFO_OK) return rc;
+  std::lock_guard<std::mutex> g(g_tmap_mu);
+  if (g_tmaps.size() > 4096) g_tmaps.clear();
+  g_tmaps[k] = *out;
+  return MOFO_OK;
+}
+
+template <int BN, int EPI>
+static int launch_tn(const CUtensorMap& tA, const CUtensorMap& tB, int M, int N, int K, const EpiParams& ep, cudaStream_t s) {
+  using Cfg = TnCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MOFO_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tA, tB, M, N, K, ep);
+  MOFO_LAUNCH_CHECK("gemm_tn_kernel");
+  return MOFO_OK;
+}
+
+static int pick_bn(int M, int N) {
+  const int sms = sm_count();
+  const int num_m = (M + BM - 1) / BM;
+  int best = 128;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 128 && N < bn) continue;
+    const int tiles = num_m * ((N + bn - 1) / bn);
+    const int waves = (tiles + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) * (bn + 24);   // +24: per-tile fixed overhead in "columns"
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int EPI>
+static int dispatch_bn(int bn, const CUtensorMap& tA, const CUtensorMap& tB, int M, int N, int K, const EpiParams& ep, cudaStream_t s) {
+  switch (bn) {
+    case 256: return launch_tn<256, EPI>(tA, tB, M, N, K, ep, s);
+    case 192: return launch_tn<192, EPI>(tA, tB, M, N, K, ep, s);
+    default:  return launch_tn<128, EPI>(tA, tB, M, N, K, ep, s);
+  }
+}
+
+template <int BNW>
+static int launch_wgrad(const CUtensorMap& tY, const CUtensorMap& tX, int M, int N, int K, float* dW, int ldw, cudaStream_t s) {
+  using Cfg = WgCfg<BNW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MOFO_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((N + 127) / 128) * ((K + BNW - 1) / BNW);
+  const int kblocks = (M + BK - 1) / BK;
+  int splits = sm_count() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > kblocks) splits = kblocks;
+  const int kb_per_split = (kblocks + splits - 1) / splits;
+  splits = (kblocks + kb_per_split - 1) / kb_per_split;
+  dim3 grid(tiles, splits);
+  gemm_wgrad_kernel<BNW><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tY, tX, M, N, K, dW, ldw, kb_per_split);
+  MOFO_LAUNCH_CHECK("gemm_wgrad_kernel");
+  return MOFO_OK;
+}
+
+}  // namespace mofo
+
+using namespace mofo;
+
+extern "C" {
+
+int mofo_gemm_tn(const mofo_bf16* A, int lda, const mofo_bf16* B, int ldb, int M, int N, int K, int epilogue,
+                 const float* bias, const float* resid, int ldr, const mofo_bf16* aux_bf16, int ldaux, const float* pos,
+                 const int32_t* row_idx, int group_rows, int out_group_rows, void* out0, int ldo0, void* out1, int ldo1,
+                 void* stream) {
+  MOFO_CHECK_ARG(A && B && out0, "gemm_tn: null pointer");
+  MOFO_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0, "gemm_tn: M=%d N=%d K=%d (need K%%8==0, N%%8==0)", M, N, K);
+  MOFO_CHECK_ARG(lda >= K && ldb >= K && lda % 8 == 0 && ldb % 8 == 0, "gemm_tn: bad leading dimensions lda=%d ldb=%d", lda, ldb);
+  MOFO_CHECK_ARG(ldo0 % 8 == 0 && (reinterpret_cast<uintptr_t>(out0) & 15) == 0, "gemm_tn: out0 must be 16-B aligned with ld%%8==0");
+  EpiParams ep{bias, resid, ldr, reinterpret_cast<const __nv_bfloat16*>(aux_bf16), ldaux, pos, row_idx,
+               group_rows > 0 ? group_rows : M, out_group_rows > 0 ? out_group_rows : M, out0, ldo0, out1, ldo1};
+  switch (epilogue) {
+    case MOFO_EPI_BIAS_GELU_BF16:
+      MOFO_CHECK_ARG(out1 && ldo1 % 8 == 0, "gemm_tn: BIAS_GELU needs out1"); break;
+    case MOFO_EPI_BIAS_RESID_F32:
+      MOFO_CHECK_ARG(resid && ldr % 4 == 0, "gemm_tn: BIAS_RESID needs resid"); break;
+    case MOFO_EPI_GELU_BWD_BF16:
+      MOFO_CHECK_ARG(aux_bf16 && ldaux % 8 == 0, "gemm_tn: GELU_BWD needs aux_bf16"); break;
+    case MOFO_EPI_BIAS_POS_F32:
+      MOFO_CHECK_ARG(pos && row_idx, "gemm_tn: BIAS_POS needs pos and row_idx"); break;
+    case MOFO_EPI_BIAS_BF16: case MOFO_EPI_PLAIN_BF16: break;
+    default: MOFO_CHECK_ARG(false, "gemm_tn: unknown epilogue %d", epilogue);
+  }
+  const int bn = pick_bn(M, N);
+  CUtensorMap tA, tB;
+  int rc = get_tmap(&tA, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = get_tmap(&tB, B, N, K, ldb, bn);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (epilogue) {
+    case MOFO_EPI_BIAS_BF16:      return dispatch_bn<MOFO_EPI_BIAS_BF16>(bn, tA, tB, M, N, K, ep, s);
+    case MOFO_EPI_BIAS_GELU_BF16: return dispatch_bn<MOFO_EPI_BIAS_GELU_BF16>(bn, tA, tB, M, N, K, ep, s);
+    case MOFO_EPI_BIAS_RESID_F32: return dispatch_bn<MOFO_EPI_BIAS_RESID_F32>(bn, tA, tB, M, N, K, ep, s);
+    case MOFO_EPI_PLAIN_BF16:     return dispatch_bn<MOFO_EPI_PLAIN_BF16>(bn, tA, tB, M, N, K, ep, s);
+    case MOFO_EPI_GELU_BWD_BF16:  return dispatch_bn<MOFO_EPI_GELU_BWD_BF16>(bn, tA, tB, M, N, K, ep, s);
+    default:                      return dispatch_bn<MOFO_EPI_BIAS_POS_F32>(bn, tA, tB, M, N, K, ep, s);
+  }
+}
+
+int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, int M, int N, int K, float* dW, int ldw,
+                    void* stream) {
+  MOFO_CHECK_ARG(dY && X && dW, "gemm_wgrad: null pointer");
+  MOFO_CHECK_ARG(M > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, "gemm_wgrad: M=%d N=%d K=%d (need N%%8==0, K%%8==0)", M, N, K);
+  MOFO_CHECK_ARG(ldy >= N && ldx >= K && ldy % 8 == 0 && ldx % 8 == 0 && ldw >= K, "gemm_wgrad: bad leading dimensions");
+  CUtensorMap tY, tX;
+  int rc = get_tmap(&tY, dY, M, N, ldy, 64);
+  if (rc) return rc;
+  rc = get_tmap(&tX, X, M, K, ldx, 64);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (K % 256 == 0) return launch_wgrad<256>(tY, tX, M, N, K, dW, ldw, s);
+  if (K % 192 == 0) return launch_wgrad<192>(tY, tX, M, N, K, dW, ldw, s);
+  return launch_wgrad<128>(tY, tX, M, N, K, dW, ldw, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,655 @@
+// HBM-/latency-bound kernels of the MOFO pretraining step: tube masking, tubelet gather, LayerNorm fwd/bwd,
+// decoder-input assembly, target + MSE, weight casts, bias-gradient column sums, gradient norm.
+// All of them are integer/byte/elementwise work: coalesced 16-byte accesses, no tensor cores.
+#include "../../include/mofo_b200.h"
+#include "common.cuh"
+
+namespace mofo {
+
+// =================================================================================================
+// (1) tube masking  — masking_generator.py:17-24, 43-85
+// =================================================================================================
+struct WordStream {
+  const uint32_t* w;
+  int n;
+  int pos;
+  bool ok;
+  // numpy legacy random_interval (masked rejection on 32-bit MT19937 outputs)
+  __device__ int interval(int mx) {
+    if (mx == 0) return 0;
+    uint32_t mask = static_cast<uint32_t>(mx);
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    while (true) {
+      if (pos >= n) { ok = false; return 0; }
+      uint32_t v = w[pos++] & mask;
+      if (v <= static_cast<uint32_t>(mx)) return static_cast<int>(v);
+    }
+  }
+};
+
+template <typename T>
+__device__ void legacy_shuffle(T* x, int n, WordStream& ws) {
+  for (int i = n - 1; i > 0; --i) {
+    int j = ws.interval(i);
+    T tmp = x[i]; x[i] = x[j]; x[j] = tmp;
+  }
+}
+
+// one warp per clip; lane 0 runs the (inherently sequential) Fisher-Yates passes in shared memory,
+// the whole warp does the predicate, the compactions and the writes.
+template <bool BB>
+__global__ void tube_mask_kernel(const double* __restrict__ bb_first, const uint32_t* __restrict__ rng_words, int B,
+                                 int W, int T, int H, int Wd, int nmask, double ratio_bb,
+                                 uint8_t* __restrict__ mask, int32_t* __restrict__ vis_idx,
+                                 int32_t* __restrict__ msk_idx, int32_t* __restrict__ words_used) {
+  extern __shared__ int16_t sm[];
+  const int npf = H * Wd;
+  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * warps + wid;
+  int16_t* index = sm + wid * (3 * npf);     // in-box ids, later shuffled
+  int16_t* remaining = index + npf;          // candidates 0..nmask-1 not selected
+  int16_t* f = remaining + npf;              // per-frame mask (0/1)
+  if (b >= B) return;
+  WordStream ws{rng_words + static_cast<size_t>(b) * W, W, 0, true};
+
+  for (int i = lane; i < npf; i += 32) f[i] = 0;
+  __syncwarp();
+  if (BB) {
+    const double b0 = bb_first[b * 4 + 0], b1 = bb_first[b * 4 + 1], b2 = bb_first[b * 4 + 2], b3 = bb_first[b * 4 + 3];
+    int n_in = 0;
+    for (int base = 0; base < npf; base += 32) {
+      int id = base + lane;
+      bool in = false;
+      if (id < npf) {
+        int j = id / Wd, k = id % Wd;
+        double x1t = j * 16, x2t = j * 16 + 16, y1t = k * 16, y2t = k * 16 + 16;
+        in = !((b0 > x2t || b2 < x1t) && (b1 > y2t || b3 < y1t));       // :55  (cross predicate, x vs row j)
+      }
+      unsigned bal = __ballot_sync(0xffffffffu, in);
+      if (in) index[n_in + __popc(bal & ((1u << lane) - 1))] = static_cast<int16_t>(id);
+      n_in += __popc(bal);
+    }
+    __syncwarp();
+    int cap = 0;
+    if (lane == 0) {
+      legacy_shuffle(index, n_in, ws);                                   // :62
+      cap = static_cast<int>(static_cast<double>(n_in) * ratio_bb);     // int(len(index)*ratio)  :64
+      cap = cap < nmask ? cap : nmask;
+      for (int i = 0; i < cap; ++i) f[index[i]] = 1;                     // :67-68
+    }
+    cap = __shfl_sync(0xffffffffu, cap, 0);
+    __syncwarp();
+    int n_rem = 0;                                                       // setdiff1d(arange(nmask), selected)  :72
+    for (int base = 0; base < nmask; base += 32) {
+      int id = base + lane;
+      bool keep = id < nmask && f[id] == 0;
+      unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) remaining[n_rem + __popc(bal & ((1u << lane) - 1))] = static_cast<int16_t>(id);
+      n_rem += __popc(bal);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      legacy_shuffle(remaining, n_rem, ws);                              // :75
+      int need = nmask - cap;                                            // :71
+      for (int i = 0; i < need; ++i) f[remaining[i]] = 1;                // :76-77
+    }
+  } else {
+    for (int i = lane; i < npf; i += 32) f[i] = (i >= npf - nmask) ? 1 : 0;   // hstack([zeros, ones])  :18-21
+    __syncwarp();
+    if (lane == 0) legacy_shuffle(f, npf, ws);                                // :22
+  }
+  __syncwarp();
+  if (lane == 0) words_used[b] = ws.ok ? ws.pos : -1;
+
+  // tile over T slabs (:84) + ascending index lists
+  const int nvis = npf - nmask;
+  int cv = 0, cm = 0;
+  for (int base = 0; base < npf; base += 32) {
+    int id = base + lane;
+    bool valid = id < npf;
+    bool m = valid && f[id] != 0;
+    unsigned balm = __ballot_sync(0xffffffffu, m);
+    unsigned balv = __ballot_sync(0xffffffffu, valid && !m);
+    int pm = cm + __popc(balm & ((1u << lane) - 1));
+    int pv = cv + __popc(balv & ((1u << lane) - 1));
+    if (valid) {
+      for (int t = 0; t < T; ++t) {
+        mask[(static_cast<size_t>(b) * T + t) * npf + id] = m ? 1 : 0;
+        if (m) msk_idx[(static_cast<size_t>(b) * T + t) * nmask + pm] = t * npf + id;
+        else   vis_idx[(static_cast<size_t>(b) * T + t) * nvis + pv] = t * npf + id;
+      }
+    }
+    cm += __popc(balm);
+    cv += __popc(balv);
+  }
+}
+
+// =================================================================================================
+// (2) tubelet gather (im2col of the visible tubes)  — modeling_finetune.py:238-248 + modeling_pretrain.py:90
+// =================================================================================================
+// 192 threads per tube: thread -> (segment = (c,p0,p1) row of 16 px, half of 8 px).
+__global__ void __launch_bounds__(192) gather_tubes_kernel(const float* __restrict__ video,
+                                                           const int32_t* __restrict__ idx, int n_idx, int frames,
+                                                           int size, __nv_bfloat16* __restrict__ A) {
+  const int row = blockIdx.x;
+  const int b = row / n_idx;
+  const int hw = size >> 4;
+  const int tok = idx[row];
+  const int t = tok / (hw * hw), h = (tok / hw) % hw, w = tok % hw;
+  const int seg = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int c = seg >> 5, p0 = (seg >> 4) & 1, p1 = seg & 15;
+  const float* src = video + ((static_cast<size_t>(b) * 3 + c) * frames + 2 * t + p0) * size * size +
+                     static_cast<size_t>(16 * h + p1) * size + 16 * w + half * 8;
+  float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+  float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  uint4 o;
+  o.x = pack_bf16(v0.x, v0.y); o.y = pack_bf16(v0.z, v0.w);
+  o.z = pack_bf16(v1.x, v1.y); o.w = pack_bf16(v1.z, v1.w);
+  *reinterpret_cast<uint4*>(A + static_cast<size_t>(row) * 1536 + seg * 16 + half * 8) = o;
+}
+
+// =================================================================================================
+// (5) LayerNorm
+// =================================================================================================
+constexpr int LN_MAX_CHUNKS = 8;  // D <= 1024 (float4 chunk per lane per iteration)
+
+__device__ __forceinline__ size_t map_row(int m, int group_rows, int in_group_rows, int in_row_offset) {
+  return static_cast<size_t>(m / group_rows) * in_group_rows + in_row_offset + (m % group_rows);
+}
+
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int M, int D, float eps,
+                                                            int group_rows, int in_group_rows, int in_row_offset,
+                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+                                                            float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int nch = D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + map_row(m, group_rows, in_group_rows, in_row_offset) * D);
+  float4 v[LN_MAX_CHUNKS];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    int ch = lane + i * 32;
+    if (ch < nch) { v[i] = xr[ch]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+  }
+  const float mu = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    int ch = lane + i * 32;
+    if (ch < nch) {
+      float a = v[i].x - mu, b2 = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+      q += (a * a + b2 * b2) + (c * c + d * d);
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / D + eps);
+  if (lane == 0) { mean[m] = mu; rstd[m] = rs; }
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(m) * D);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    int ch = lane + i * 32;
+    if (ch < nch) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
+      float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + ch);
+      uint2 o;
+      o.x = pack_bf16((v[i].x - mu) * rs * g.x + bt.x, (v[i].y - mu) * rs * g.y + bt.y);
+      o.y = pack_bf16((v[i].z - mu) * rs * g.z + bt.z, (v[i].w - mu) * rs * g.w + bt.w);
+      yr[ch] = o;
+    }
+  }
+}
+
+// warp per row, grid-stride over rows; per-lane register partials of dgamma/dbeta, reduced through shared
+// memory per CTA and accumulated with one atomicAdd per column per CTA.
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres, int M, int D,
+    int group_rows, int in_group_rows, int in_row_offset, float* __restrict__ dx_f32,
+    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float red[];  // [warps][2*D]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int nch = D >> 2;
+  float4 dg[LN_MAX_CHUNKS], db[LN_MAX_CHUNKS];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
+
+  for (int m = blockIdx.x * warps + wid; m < M; m += gridDim.x * warps) {
+    const size_t xrow = map_row(m, group_rows, in_group_rows, in_row_offset);
+    const float4* xr = reinterpret_cast<const float4*>(x + xrow * D);
+    const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(m) * D);
+    const float mu = mean[m], rs = rstd[m];
+    float4 xh[LN_MAX_CHUNKS], g[LN_MAX_CHUNKS];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      int ch = lane + i * 32;
+      if (ch < nch) {
+        float4 xv = xr[ch];
+        uint2 d2 = dyr[ch];
+        float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
+        float4 d = make_float4(bf16_lo(d2.x), bf16_hi(d2.x), bf16_lo(d2.y), bf16_hi(d2.y));
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+      int ch = lane + i * 32;
+      if (ch < nch) {
+        float4 o = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
+                               rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
+        if (dres) {
+          float4 r = reinterpret_cast<const float4*>(dres + xrow * D)[ch];
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (dx_f32) reinterpret_cast<float4*>(dx_f32 + xrow * D)[ch] = o;
+        if (dx_bf16) {
+          uint2 p; p.x = pack_bf16(o.x, o.y); p.y = pack_bf16(o.z, o.w);
+          reinterpret_cast<uint2*>(dx_bf16 + xrow * D)[ch] = p;
+        }
+      }
+    }
+  }
+  // CTA reduction of the parameter-gradient partials
+  float* mine = red + static_cast<size_t>(wid) * 2 * D;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    int ch = lane + i * 32;
+    if (ch < nch) {
+      reinterpret_cast<float4*>(mine)[ch] = dg[i];
+      reinterpret_cast<float4*>(mine + D)[ch] = db[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    float s = 0.f;
+    for (int w2 = 0; w2 < warps; ++w2) s += red[static_cast<size_t>(w2) * 2 * D + c];
+    if (c < D) atomicAdd(dgamma + c, s);
+    else atomicAdd(dbeta + (c - D), s);
+  }
+}
+
+// =================================================================================================
+// (6) decoder input assembly  — modeling_pretrain.py:260-263
+// =================================================================================================
+__global__ void assemble_fwd_kernel(const float* __restrict__ mask_token, const float* __restrict__ pos,
+                                    const int32_t* __restrict__ msk_idx, int n_vis, int n_msk, int Dd,
+                                    float* __restrict__ x_full) {
+  const int r = blockIdx.x;                 // b*n_msk + j
+  const int b = r / n_msk, j = r % n_msk;
+  const float4* p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(msk_idx[r]) * Dd);
+  const float4* mt = reinterpret_cast<const float4*>(mask_token);
+  float4* o = reinterpret_cast<float4*>(x_full + (static_cast<size_t>(b) * (n_vis + n_msk) + n_vis + j) * Dd);
+  for (int c = threadIdx.x; c < (Dd >> 2); c += blockDim.x) {
+    float4 a = __ldg(mt + c), q = __ldg(p + c);
+    o[c] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+
+// grid = (row chunks, B).  Threads own float4 column chunks; rows of the chunk are streamed.
+__global__ void assemble_bwd_kernel(const float* __restrict__ dx_full, int n_vis, int n_msk, int Dd, int rows_per_cta,
+                                    float* __restrict__ dmask_token, __nv_bfloat16* __restrict__ dvis) {
+  const int b = blockIdx.y;
+  const int N = n_vis + n_msk;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < (Dd >> 2); c += blockDim.x) {
+    float4 acc = make_float4(0, 0, 0, 0);
+    bool any = false;
+    for (int r = r0; r < r1; ++r) {
+      float4 v = reinterpret_cast<const float4*>(dx_full + (static_cast<size_t>(b) * N + r) * Dd)[c];
+      if (r < n_vis) {
+        uint2 p; p.x = pack_bf16(v.x, v.y); p.y = pack_bf16(v.z, v.w);
+        reinterpret_cast<uint2*>(dvis + (static_cast<size_t>(b) * n_vis + r) * Dd)[c] = p;
+      } else {
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; any = true;
+      }
+    }
+    if (any) {
+      atomicAdd(dmask_token + 4 * c + 0, acc.x); atomicAdd(dmask_token + 4 * c + 1, acc.y);
+      atomicAdd(dmask_token + 4 * c + 2, acc.z); atomicAdd(dmask_token + 4 * c + 3, acc.w);
+    }
+  }
+}
+
+// =================================================================================================
+// (7) target + MSE  — engine_for_pretraining.py:258-304
+// =================================================================================================
+__device__ __forceinline__ float block_sum_128(float v, float* sh) {  // 128 threads; result broadcast
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+
+// one CTA (128 threads) per masked tube.  thread -> (p0, p1, quad of 4 px) for each of the 3 channels.
+__global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict__ video,
+                                                         const int32_t* __restrict__ msk_idx,
+                                                         const __nv_bfloat16* __restrict__ pred, int n_msk, int frames,
+                                                         int size, int normalize_target, float gscale,
+                                                         float* __restrict__ loss_partials,
+                                                         __nv_bfloat16* __restrict__ dpred,
+                                                         float* __restrict__ labels_out) {
+  __shared__ __align__(16) float lab[1536];
+  __shared__ float sh[4];
+  const int row = blockIdx.x;
+  const int b = row / n_msk;
+  const int hw = size >> 4;
+  const int tok = msk_idx[row];
+  const int t = tok / (hw * hw), h = (tok / hw) % hw, w = tok % hw;
+  const int tid = threadIdx.x;
+  const int p0 = tid >> 6, p1 = (tid >> 2) & 15, q = tid & 3;
+  const float mean_c[3] = {0.485f, 0.456f, 0.406f};     // IMAGENET_DEFAULT_MEAN  (:260)
+  const float std_c[3] = {0.229f, 0.224f, 0.225f};      // IMAGENET_DEFAULT_STD   (:261)
+  float xv[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* src = video + ((static_cast<size_t>(b) * 3 + c) * frames + 2 * t + p0) * size * size +
+                       static_cast<size_t>(16 * h + p1) * size + 16 * w + 4 * q;
+    float4 v = __ldg(reinterpret_cast<const float4*>(src));
+    // videos * std + mean: two separately rounded fp32 ops as in torch (:265)
+    xv[c][0] = __fadd_rn(__fmul_rn(v.x, std_c[c]), mean_c[c]);
+    xv[c][1] = __fadd_rn(__fmul_rn(v.y, std_c[c]), mean_c[c]);
+    xv[c][2] = __fadd_rn(__fmul_rn(v.z, std_c[c]), mean_c[c]);
+    xv[c][3] = __fadd_rn(__fmul_rn(v.w, std_c[c]), mean_c[c]);
+  }
+  const int pbase = p0 * 256 + p1 * 16 + q * 4;         // pixel index p = p0*256 + p1*16 + p2  (:268)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float mu = 0.f, sd = 1.f;
+    if (normalize_target) {
+      float s = (xv[c][0] + xv[c][1]) + (xv[c][2] + xv[c][3]);
+      mu = block_sum_128(s, sh) * (1.0f / 512.0f);                       // mean over the 512 pixels  (:269)
+      float d0 = xv[c][0] - mu, d1 = xv[c][1] - mu, d2 = xv[c][2] - mu, d3 = xv[c][3] - mu;
+      float qs = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      float var = block_sum_128(qs, sh) * (1.0f / 511.0f);               // unbiased  (:270)
+      sd = sqrtf(var) + 1e-6f;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = normalize_target ? __fdiv_rn(xv[c][e] - mu, sd) : xv[c][e];
+      lab[(pbase + e) * 3 + c] = v;                                      // feature f = p*3 + c  (:276)
+    }
+  }
+  __syncthreads();
+  float acc = 0.f;
+  for (int v = tid; v < 192; v += 128) {
+    const size_t off = static_cast<size_t>(row) * 1536 + v * 8;
+    float l[8];
+    *reinterpret_cast<float4*>(l) = *reinterpret_cast<const float4*>(lab + v * 8);
+    *reinterpret_cast<float4*>(l + 4) = *reinterpret_cast<const float4*>(lab + v * 8 + 4);
+    if (labels_out) {
+      *reinterpret_cast<float4*>(labels_out + off) = *reinterpret_cast<float4*>(l);
+      *reinterpret_cast<float4*>(labels_out + off + 4) = *reinterpret_cast<float4*>(l + 4);
+    }
+    if (pred) {
+      uint4 pv = __ldg(reinterpret_cast<const uint4*>(pred + off));
+      float p[8] = {bf16_lo(pv.x), bf16_hi(pv.x), bf16_lo(pv.y), bf16_hi(pv.y),
+                    bf16_lo(pv.z), bf16_hi(pv.z), bf16_lo(pv.w), bf16_hi(pv.w)};
+      float d[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { d[e] = p[e] - l[e]; acc += d[e] * d[e]; }
+      if (dpred) {
+        uint4 o;
+        o.x = pack_bf16(d[0] * gscale, d[1] * gscale); o.y = pack_bf16(d[2] * gscale, d[3] * gscale);
+        o.z = pack_bf16(d[4] * gscale, d[5] * gscale); o.w = pack_bf16(d[6] * gscale, d[7] * gscale);
+        *reinterpret_cast<uint4*>(dpred + off) = o;
+      }
+    }
+  }
+  float tot = block_sum_128(acc, sh);
+  if (tid == 0 && loss_partials) loss_partials[row] = tot;
+}
+
+__global__ void __launch_bounds__(1024) loss_finish_kernel(const float* __restrict__ partials, int n, double inv_count,
+                                                           float* __restrict__ loss) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += static_cast<double>(partials[i]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = sh[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *loss = static_cast<float>(s * inv_count);
+  }
+}
+
+// =================================================================================================
+// (8) helpers
+// =================================================================================================
+// 32x32 tile transpose through shared memory; block (32,8)
+__global__ void cast_weight_kernel(const float* __restrict__ W, int R, int C, __nv_bfloat16* __restrict__ Wb,
+                                   __nv_bfloat16* __restrict__ Wt) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    float v = (r < R && c < C) ? W[static_cast<size_t>(r) * C + c] : 0.f;
+    tile[i][threadIdx.x] = v;
+    if (Wb && r < R && c < C) Wb[static_cast<size_t>(r) * C + c] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  if (Wt) {
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < R && c < C) Wt[static_cast<size_t>(c) * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+__global__ void pack_qkv_bias_kernel(const float* __restrict__ qb, const float* __restrict__ vb, int D,
+                                     float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * D) out[i] = i < D ? qb[i] : (i < 2 * D ? 0.f : vb[i - 2 * D]);
+}
+
+// grid (ceil(N/256), row chunks); 256 threads = 8 warps; lane owns 8 consecutive columns.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int M, int N,
+                                                          int rows_per_cta, float* __restrict__ out) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (int r = r0 + wid; r < r1; r += 8) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(X + static_cast<size_t>(r) * ldx + col));
+      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[wid][lane * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) s += red[w2][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) sq_norm_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { float v = x[n4 * 4 + threadIdx.x]; s += v * v; }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < 8 ? sh[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+}  // namespace mofo
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace mofo;
+
+static int mask_common(bool bb, const double* bb_first, const uint32_t* rng_words, int B, int W, int T, int H, int Wd,
+                       int nmask, double ratio_bb, uint8_t* mask, int32_t* vis_idx, int32_t* msk_idx,
+                       int32_t* words_used, void* stream) {
+  MOFO_CHECK_ARG(B > 0 && W > 0 && T > 0 && H > 0 && Wd > 0, "tube_mask: non-positive size");
+  MOFO_CHECK_ARG(H * Wd <= 4096 && nmask >= 0 && nmask <= H * Wd, "tube_mask: grid %dx%d / n_mask %d unsupported", H, Wd, nmask);
+  MOFO_CHECK_ARG(rng_words && mask && vis_idx && msk_idx && words_used && (!bb || bb_first), "tube_mask: null pointer");
+  const int warps = 4;
+  size_t smem = static_cast<size_t>(warps) * 3 * H * Wd * sizeof(int16_t);
+  dim3 grid((B + warps - 1) / warps), block(warps * 32);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bb) {
+    if (smem > 48 * 1024) MOFO_CUDA(cudaFuncSetAttribute(tube_mask_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tube_mask_kernel<true><<<grid, block, smem, s>>>(bb_first, rng_words, B, W, T, H, Wd, nmask, ratio_bb, mask, vis_idx, msk_idx, words_used);
+  } else {
+    if (smem > 48 * 1024) MOFO_CUDA(cudaFuncSetAttribute(tube_mask_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tube_mask_kernel<false><<<grid, block, smem, s>>>(nullptr, rng_words, B, W, T, H, Wd, nmask, 0.0, mask, vis_idx, msk_idx, words_used);
+  }
+  MOFO_LAUNCH_CHECK("tube_mask_kernel");
+  return MOFO_OK;
+}
+
+extern "C" {
+
+int mofo_tube_mask_bb(const double* bb_first, const uint32_t* rng_words, int B, int W, int T, int H, int Wd,
+                      int n_mask_per_frame, double ratio_bb, uint8_t* mask, int32_t* vis_idx, int32_t* msk_idx,
+                      int32_t* words_used, void* stream) {
+  return mask_common(true, bb_first, rng_words, B, W, T, H, Wd, n_mask_per_frame, ratio_bb, mask, vis_idx, msk_idx, words_used, stream);
+}
+
+int mofo_tube_mask_plain(const uint32_t* rng_words, int B, int W, int T, int H, int Wd, int n_mask_per_frame,
+                         uint8_t* mask, int32_t* vis_idx, int32_t* msk_idx, int32_t* words_used, void* stream) {
+  return mask_common(false, nullptr, rng_words, B, W, T, H, Wd, n_mask_per_frame, 0.0, mask, vis_idx, msk_idx, words_used, stream);
+}
+
+int mofo_gather_tubes(const float* video, const int32_t* idx, int B, int n_idx, int frames, int size, mofo_bf16* A,
+                      void* stream) {
+  MOFO_CHECK_ARG(video && idx && A, "gather_tubes: null pointer");
+  MOFO_CHECK_ARG(B > 0 && n_idx > 0 && frames % 2 == 0 && size % 16 == 0, "gather_tubes: bad shape B=%d n=%d frames=%d size=%d", B, n_idx, frames, size);
+  gather_tubes_kernel<<<B * n_idx, 192, 0, static_cast<cudaStream_t>(stream)>>>(video, idx, n_idx, frames, size, reinterpret_cast<__nv_bfloat16*>(A));
+  MOFO_LAUNCH_CHECK("gather_tubes_kernel");
+  return MOFO_OK;
+}
+
+int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int D, float eps, int group_rows,
+                       int in_group_rows, int in_row_offset, mofo_bf16* y, float* mean, float* rstd, void* stream) {
+  MOFO_CHECK_ARG(x && gamma && beta && y && mean && rstd, "layernorm_fwd: null pointer");
+  MOFO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_CHUNKS && group_rows > 0, "layernorm_fwd: unsupported M=%d D=%d", M, D);
+  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, gamma, beta, M, D, eps, group_rows, in_group_rows, in_row_offset, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd);
+  MOFO_LAUNCH_CHECK("layernorm_fwd_kernel");
+  return MOFO_OK;
+}
+
+int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       const float* dres, int M, int D, int group_rows, int in_group_rows, int in_row_offset,
+                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, void* stream) {
+  MOFO_CHECK_ARG(dy && x && gamma && mean && rstd && dgamma && dbeta, "layernorm_bwd: null pointer");
+  MOFO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_CHUNKS && group_rows > 0, "layernorm_bwd: unsupported M=%d D=%d", M, D);
+  const int warps = 8;
+  int grid = (M + warps - 1) / warps;
+  int cap = sm_count() * 4;
+  if (grid > cap) grid = cap;
+  size_t smem = static_cast<size_t>(warps) * 2 * D * sizeof(float);
+  if (smem > 48 * 1024) MOFO_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  layernorm_bwd_kernel<<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, M, D, group_rows, in_group_rows, in_row_offset,
+      dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta);
+  MOFO_LAUNCH_CHECK("layernorm_bwd_kernel");
+  return MOFO_OK;
+}
+
+int mofo_decoder_assemble_fwd(const float* mask_token, const float* pos, const int32_t* msk_idx, int B, int n_vis,
+                              int n_msk, int Dd, float* x_full, void* stream) {
+  MOFO_CHECK_ARG(mask_token && pos && msk_idx && x_full, "decoder_assemble_fwd: null pointer");
+  MOFO_CHECK_ARG(B > 0 && n_vis >= 0 && n_msk > 0 && Dd % 4 == 0, "decoder_assemble_fwd: bad shape");
+  assemble_fwd_kernel<<<B * n_msk, 128, 0, static_cast<cudaStream_t>(stream)>>>(mask_token, pos, msk_idx, n_vis, n_msk, Dd, x_full);
+  MOFO_LAUNCH_CHECK("assemble_fwd_kernel");
+  return MOFO_OK;
+}
+
+int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk, int Dd, float* dmask_token,
+                              mofo_bf16* dvis, void* stream) {
+  MOFO_CHECK_ARG(dx_full && dmask_token && dvis, "decoder_assemble_bwd: null pointer");
+  MOFO_CHECK_ARG(B > 0 && n_vis >= 0 && n_msk > 0 && Dd % 4 == 0, "decoder_assemble_bwd: bad shape");
+  const int rows_per_cta = 16;
+  dim3 grid((n_vis + n_msk + rows_per_cta - 1) / rows_per_cta, B);
+  assemble_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(dx_full, n_vis, n_msk, Dd, rows_per_cta, dmask_token,
+                                                                       reinterpret_cast<__nv_bfloat16*>(dvis));
+  MOFO_LAUNCH_CHECK("assemble_bwd_kernel");
+  return MOFO_OK;
+}
+
+int mofo_target_mse(const float* video, const int32_t* msk_idx, const mofo_bf16* pred, int B, int n_msk, int frames,
+                    int size, int normalize_target, float grad_scale, float* loss_partials, float* loss,
+                    mofo_bf16* dpred, float* labels_out, void* stream) {
+  MOFO_CHECK_ARG(video && msk_idx, "target_mse: null pointer");
+  MOFO_CHECK_ARG(B > 0 && n_msk > 0 && frames % 2 == 0 && size % 16 == 0, "target_mse: bad shape");
+  MOFO_CHECK_ARG(!loss || (loss_partials && pred), "target_mse: loss needs pred and loss_partials");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const double count = static_cast<double>(B) * n_msk * 1536.0;
+  const float gscale = static_cast<float>(2.0 / count) * grad_scale;
+  target_mse_kernel<<<B * n_msk, 128, 0, s>>>(video, msk_idx, reinterpret_cast<const __nv_bfloat16*>(pred), n_msk, frames, size,
+                                              normalize_target, gscale, loss_partials, reinterpret_cast<__nv_bfloat16*>(dpred), labels_out);
+  MOFO_LAUNCH_CHECK("target_mse_kernel");
+  if (loss) {
+    loss_finish_kernel<<<1, 1024, 0, s>>>(loss_partials, B * n_msk, 1.0 / count, loss);
+    MOFO_LAUNCH_CHECK("loss_finish_kernel");
+  }
+  return MOFO_OK;
+}
+
+int mofo_cast_weight(const float* W, int R, int C, mofo_bf16* W_bf16, mofo_bf16* Wt_bf16, void* stream) {
+  MOFO_CHECK_ARG(W && (W_bf16 || Wt_bf16) && R > 0 && C > 0, "cast_weight: bad argument");
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  cast_weight_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(W, R, C, reinterpret_cast<__nv_bfloat16*>(W_bf16),
+                                                                          reinterpret_cast<__nv_bfloat16*>(Wt_bf16));
+  MOFO_LAUNCH_CHECK("cast_weight_kernel");
+  return MOFO_OK;
+}
+
+int mofo_pack_qkv_bias(const float* q_bias, const float* v_bias, int D, float* out, void* stream) {
+  MOFO_CHECK_ARG(q_bias && v_bias && out && D > 0, "pack_qkv_bias: bad argument");
+  pack_qkv_bias_kernel<<<(3 * D + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(q_bias, v_bias, D, out);
+  MOFO_LAUNCH_CHECK("pack_qkv_bias_kernel");
+  return MOFO_OK;
+}
+
+int mofo_colsum_bf16(const mofo_bf16* X, int ldx, int M, int N, float* out, void* stream) {
+  MOFO_CHECK_ARG(X && out && M > 0 && N > 0 && N % 8 == 0 && ldx % 8 == 0, "colsum_bf16: bad argument (N, ldx must be multiples of 8)");
+  int rows_per_cta = 512;
+  dim3 grid((N + 255) / 256, (M + rows_per_cta - 1) / rows_per_cta);
+  colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(X), ldx, M, N, rows_per_cta, out);
+  MOFO_LAUNCH_CHECK("colsum_bf16_kernel");
+  return MOFO_OK;
+}
+
+int mofo_sq_norm_f32(const float* x, int64_t n, float* out, void* stream) {
+  MOFO_CHECK_ARG(x && out && n > 0, "sq_norm_f32: bad argument");
+  MOFO_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "sq_norm_f32: x must be 16-byte aligned");
+  int grid = sm_count() * 4;
+  sq_norm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+  MOFO_LAUNCH_CHECK("sq_norm_kernel");
+  return MOFO_OK;
+}
+
+}  // extern "C"

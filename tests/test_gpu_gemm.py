@@ -1,0 +1,106 @@
+"""GPU parity of the tcgen05 GEMM kernels (all fused epilogues, wgrad) against torch fp32 matmul on the same
+bf16-rounded inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mofo_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+SHAPES = [(128, 128, 64), (256, 256, 128), (5120, 768, 768), (300, 384, 192), (128, 1152, 384), (640, 64, 128),
+          (1000, 2304, 768), (4096, 1536, 384), (513, 192, 1536), (5120, 3072, 768), (32, 128, 1536)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tn_bias_and_plain(lib, M, N, K):
+    torch.manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda").bfloat16(); B = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    ref = A.float() @ B.float().t()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    lib.gemm_tn(A, B, lib.EPI_PLAIN_BF16, out)
+    e = rel(out, ref)
+    assert e < 6e-3, f"plain rel err {e}"
+    lib.gemm_tn(A, B, lib.EPI_BIAS_BF16, out, bias=bias)
+    e = rel(out, ref + bias)
+    assert e < 6e-3, f"bias rel err {e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 1536, 384), (5120, 768, 3072)])
+def test_gemm_tn_fused_epilogues(lib, M, N, K):
+    torch.manual_seed(1)
+    A = torch.randn(M, K, device="cuda").bfloat16(); B = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    ref = A.float() @ B.float().t()
+    # bias + GELU (two outputs)
+    u = torch.empty(M, N, dtype=torch.bfloat16, device="cuda"); a = torch.empty_like(u)
+    lib.gemm_tn(A, B, lib.EPI_BIAS_GELU_BF16, u, out1=a, bias=bias)
+    assert rel(u, ref + bias) < 6e-3
+    assert rel(a, torch.nn.functional.gelu(u.float())) < 6e-3
+    # bias + residual, f32 out
+    res = torch.randn(M, N, device="cuda"); o32 = torch.empty(M, N, device="cuda")
+    lib.gemm_tn(A, B, lib.EPI_BIAS_RESID_F32, o32, bias=bias, resid=res)
+    assert rel(o32, ref + bias + res) < 1e-5
+    # GELU backward
+    uu = torch.randn(M, N, device="cuda").bfloat16()
+    g = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    lib.gemm_tn(A, B, lib.EPI_GELU_BWD_BF16, g, aux=uu)
+    ur = uu.float().requires_grad_(True)
+    torch.nn.functional.gelu(ur).backward(ref)
+    assert rel(g, ur.grad) < 6e-3
+    # bias + pos + row remap (patch-embed / encoder_to_decoder epilogue)
+    group, out_group = 50, 80
+    Mg = (M // group) * group
+    ntok = 300
+    pos = torch.randn(ntok, N, device="cuda")
+    ridx = torch.randint(0, ntok, (Mg,), device="cuda").int()
+    outp = torch.zeros((Mg // group) * out_group, N, device="cuda")
+    lib.gemm_tn(A[:Mg], B, lib.EPI_BIAS_POS_F32, outp, bias=bias, pos=pos, row_idx=ridx, group_rows=group, out_group_rows=out_group)
+    want = (ref[:Mg] + bias + pos[ridx.long()]).reshape(-1, group, N)
+    got = outp.reshape(-1, out_group, N)
+    assert rel(got[:, :group], want) < 1e-5
+    assert got[:, group:].abs().max().item() == 0
+
+
+def test_gemm_tn_strided_views(lib):
+    # A operand as a column slice (lda > K), as used for per-head / sliced activations
+    torch.manual_seed(5)
+    big = torch.randn(700, 1152, device="cuda").bfloat16()
+    A = big[:, 384:768]
+    B = (torch.randn(256, 384, device="cuda") / 20).bfloat16()
+    out = torch.empty(700, 256, dtype=torch.bfloat16, device="cuda")
+    lib.gemm_tn(A, B, lib.EPI_PLAIN_BF16, out)
+    assert rel(out, A.float() @ B.float().t()) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (5120, 768, 1536), (1000, 384, 192), (6272, 1536, 384),
+                                   (5120, 2304, 768), (333, 64, 128), (4096, 384, 1536), (64, 1536, 384)])
+def test_gemm_wgrad(lib, M, N, K):
+    torch.manual_seed(M + N + K)
+    dY = torch.randn(M, N, device="cuda").bfloat16(); X = torch.randn(M, K, device="cuda").bfloat16()
+    dW = torch.zeros(N, K, device="cuda")
+    lib.gemm_wgrad(dY, X, dW)
+    ref = dY.float().t() @ X.float()
+    e = rel(dW, ref)
+    assert e < 2e-5, f"wgrad rel err {e}"
+    lib.gemm_wgrad(dY, X, dW)          # accumulates
+    assert rel(dW, 2 * ref) < 2e-5
+
+
+def test_gemm_rejects_bad_args(lib):
+    A = torch.randn(64, 60, device="cuda").bfloat16(); B = torch.randn(64, 60, device="cuda").bfloat16()
+    out = torch.empty(64, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(lib.MofoError):
+        lib.gemm_tn(A, B, lib.EPI_PLAIN_BF16, out)      # K % 8 != 0
