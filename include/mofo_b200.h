@@ -52,6 +52,13 @@ int mofo_tube_mask_bb(const double* bb_first, const uint32_t* rng_words, int B, 
 int mofo_tube_mask_plain(const uint32_t* rng_words, int B, int W, int T, int H, int Wd, int n_mask_per_frame,
                          uint8_t* mask, int32_t* vis_idx, int32_t* msk_idx, int32_t* words_used, void* stream);
 
+/* Index lists of a caller-supplied boolean mask [B,N] (1 byte per token, non-zero = masked): the ascending visible /
+ * masked token ids that x[~mask] / x[mask] enumerate (modeling_pretrain.py:90,261-262), without the device->host sync
+ * of torch.nonzero.  Every row must hold exactly n_msk masked tokens (the reference's .reshape(B,-1,C) requires equal
+ * counts); bad_rows[0] is incremented for each row that does not. */
+int mofo_mask_indices(const uint8_t* mask, int B, int N, int n_msk, int32_t* vis_idx, int32_t* msk_idx,
+                      int32_t* bad_rows, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (2) Tubelet gather for the patch embedding.
  * Replaces the input side of PatchEmbed.forward (Conv3d k=s=(2,16,16), modeling_finetune.py:238-248) followed by

@@ -24,6 +24,7 @@ SIGNATURES = {
     "mofo_sm_count": ([], C.c_int),
     "mofo_tube_mask_bb": ([_P, _P, _I, _I, _I, _I, _I, _I, _D, _P, _P, _P, _P, _P], C.c_int),
     "mofo_tube_mask_plain": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
+    "mofo_mask_indices": ([_P, _I, _I, _I, _P, _P, _P, _P], C.c_int),
     "mofo_gather_tubes": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_gemm_tn": ([_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P, _I, _P], C.c_int),
     "mofo_gemm_wgrad": ([_P, _I, _P, _I, _I, _I, _I, _P, _I, _P], C.c_int),
@@ -104,6 +105,17 @@ def tube_mask_bb(bb_first, rng_words, grid, n_mask_per_frame, ratio_bb):
                                         float(ratio_bb), _ptr(mask), _ptr(vis), _ptr(msk), _ptr(used), _stream()),
                "mofo_tube_mask_bb")
     return mask, vis, msk, used
+
+
+def mask_indices(mask, n_msk, bad_rows):
+    """mask bool/uint8 [B,N] (CUDA) -> ascending (vis_idx [B,N-n_msk], msk_idx [B,n_msk]) int32."""
+    B, N = mask.shape
+    assert mask.element_size() == 1 and mask.is_contiguous()
+    vis = torch.empty(B, N - n_msk, dtype=torch.int32, device=mask.device)
+    msk = torch.empty(B, n_msk, dtype=torch.int32, device=mask.device)
+    _check(load().mofo_mask_indices(_ptr(mask), B, N, n_msk, _ptr(vis), _ptr(msk), _ptr(bad_rows), _stream()),
+           "mofo_mask_indices")
+    return vis, msk
 
 
 def gather_tubes(video, idx, out=None):

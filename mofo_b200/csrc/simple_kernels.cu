@@ -124,6 +124,31 @@ __global__ void tube_mask_kernel(const double* __restrict__ bb_first, const uint
   }
 }
 
+// index lists of an arbitrary boolean mask: one warp per clip, ballot/popc scan (ascending order)
+__global__ void mask_indices_kernel(const uint8_t* __restrict__ mask, int B, int N, int n_msk,
+                                    int32_t* __restrict__ vis_idx, int32_t* __restrict__ msk_idx,
+                                    int32_t* __restrict__ bad_rows) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int n_vis = N - n_msk;
+  int cv = 0, cm = 0;
+  for (int base = 0; base < N; base += 32) {
+    const int id = base + lane;
+    const bool valid = id < N;
+    const bool m = valid && mask[static_cast<size_t>(b) * N + id] != 0;
+    const unsigned balm = __ballot_sync(0xffffffffu, m);
+    const unsigned balv = __ballot_sync(0xffffffffu, valid && !m);
+    const int pm = cm + __popc(balm & ((1u << lane) - 1));
+    const int pv = cv + __popc(balv & ((1u << lane) - 1));
+    if (m && pm < n_msk) msk_idx[static_cast<size_t>(b) * n_msk + pm] = id;
+    if (valid && !m && pv < n_vis) vis_idx[static_cast<size_t>(b) * n_vis + pv] = id;
+    cm += __popc(balm);
+    cv += __popc(balv);
+  }
+  if (lane == 0 && cm != n_msk) atomicAdd(bad_rows, 1);
+}
+
 // =================================================================================================
 // (2) tubelet gather (im2col of the visible tubes)  — modeling_finetune.py:238-248 + modeling_pretrain.py:90
 // =================================================================================================
@@ -539,6 +564,15 @@ int mofo_tube_mask_bb(const double* bb_first, const uint32_t* rng_words, int B, 
 int mofo_tube_mask_plain(const uint32_t* rng_words, int B, int W, int T, int H, int Wd, int n_mask_per_frame,
                          uint8_t* mask, int32_t* vis_idx, int32_t* msk_idx, int32_t* words_used, void* stream) {
   return mask_common(false, nullptr, rng_words, B, W, T, H, Wd, n_mask_per_frame, 0.0, mask, vis_idx, msk_idx, words_used, stream);
+}
+
+int mofo_mask_indices(const uint8_t* mask, int B, int N, int n_msk, int32_t* vis_idx, int32_t* msk_idx,
+                      int32_t* bad_rows, void* stream) {
+  MOFO_CHECK_ARG(mask && vis_idx && msk_idx && bad_rows, "mask_indices: null pointer");
+  MOFO_CHECK_ARG(B > 0 && N > 0 && n_msk >= 0 && n_msk <= N, "mask_indices: bad shape B=%d N=%d n_msk=%d", B, N, n_msk);
+  mask_indices_kernel<<<(B + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(mask, B, N, n_msk, vis_idx, msk_idx, bad_rows);
+  MOFO_LAUNCH_CHECK("mask_indices_kernel");
+  return MOFO_OK;
 }
 
 int mofo_gather_tubes(const float* video, const int32_t* idx, int B, int n_idx, int frames, int size, mofo_bf16* A,
