@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the MOFO pretraining step (BASELINE.json metric: ViT-B pretrain clips/s, 16x224^2, mask 0.9).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (N>1: launched with torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
+
+A step = one pass of the hot path over one batch of 32 synthetic clips per GPU: tube masking (GPU kernel, per-clip
+MT19937 words) -> fused forward + target/MSE + backward -> gradient all-reduce (N>1) -> grad-norm -> AdamW.
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definition of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MOFO ViT-B pretrain clips/s (16x224^2, tubelet 2x16x16, mask 0.9 / BB 0.75)"
+TRAIN_GFLOP_PER_CLIP = {"pretrain_videomae_base_patch16_224": 202.3, "pretrain_mae_small_patch16_224": 64.05,
+                        "pretrain_videomae_large_patch16_224": 484.4}     # BASELINE.md §3 (algorithmic, fwd+bwd)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE configs[1]: 32)")
+    ap.add_argument("--model", default="pretrain_videomae_base_patch16_224")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall budget of the reference arm")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path = the oracle port (pure-Python reference cannot travel)
+# ------------------------------------------------------------------------------------------------------------------
+def oracle_cpu_step_fn(model_name, threads):
+    import numpy as np
+    import torch
+    from oracle import mask_oracle as mo
+    from oracle import model_oracle as mdl
+    from oracle import target_oracle as tgt
+    torch.set_num_threads(threads)
+    cfg = mdl.CONFIGS[model_name]
+    sd = mdl.random_state_dict(cfg, seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=1.5e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    state = {"i": 0}
+
+    def step(n_clips):
+        i = state["i"]; state["i"] += 1
+        vid = tgt.synthetic_clip(n_clips, seed=1234 + i)
+        boxes = tgt.synthetic_boxes(n_clips, seed=4321 + i)
+        t0 = time.perf_counter()
+        masks = np.stack([mo.tube_mask_bb(boxes[b], np.random.RandomState(i * 64 + b)._bit_generator.random_raw(800), cfg.grid)[0]
+                          for b in range(n_clips)])
+        mask = torch.from_numpy(masks).bool()
+        with torch.no_grad():
+            labels = tgt.build_labels(vid, mask)
+        opt.zero_grad()
+        loss = tgt.mse_loss(mdl.forward(cfg, params, vid, mask), labels)
+        loss.backward()
+        opt.step()
+        return time.perf_counter() - t0, float(loss)
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    step = oracle_cpu_step_fn(args.model, cores)
+    t1, _ = step(1)                                   # probe (also first-touch warm-up)
+    total_steps = args.steps + args.warmup
+    n = int(max(1, min(args.batch, args.ref_budget_s / max(total_steps * t1, 1e-9))))
+    for _ in range(args.warmup):
+        step(n)
+    ts = [step(n)[0] for _ in range(args.steps)]
+    tot = sum(ts)
+    val = n * args.steps / tot
+    sample = f"{n} clip(s)/step x {args.steps} steps of the {args.batch}-clip batch; oracle port (torch fp32 CPU autograd + numpy mask), AdamW step included"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "global_batch": args.batch * args.gpus, "parallelism": f"dp{args.gpus}"},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"BASELINE configs[1]: ViT-B MOFO pretrain ({args.model}, decoder depth 4), batch {args.batch}/GPU, synthetic "
+            f"16x224x224 clips, tubelet 2x16x16, mask 0.9 / BB 0.75, full step incl. AdamW")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def param_groups(model, weight_decay=0.05):
+    """optim_factory.get_parameter_groups (optim_factory.py:49-88): no decay for 1-D params, biases and the skip list."""
+    skip = model.no_weight_decay()
+    decay, no_decay = [], []
+    for name, p in model.named_parameters():
+        (no_decay if (p.ndim == 1 or name.endswith(".bias") or name in skip) else decay).append(p)
+    return [{"params": no_decay, "weight_decay": 0.0, "lr_scale": 1.0}, {"params": decay, "weight_decay": weight_decay, "lr_scale": 1.0}]
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from mofo_b200 import _lib
+    from mofo_b200 import engine_for_pretraining as eng
+    from mofo_b200 import masking_generator as mg
+    from mofo_b200 import modeling_pretrain as mp
+    from mofo_b200 import utils as U
+    from mofo_b200.dp import GradSync
+    _lib.load()
+
+    B = args.batch
+    torch.manual_seed(0)                                  # identical init on every rank (DDP broadcasts rank 0's)
+    model = mp.create_model(args.model, pretrained=False, drop_path_rate=0.0, drop_block_rate=None, decoder_depth=4).to(dev)
+    model.train()
+    lr = 1.5e-4 * B * world / 256                         # run_mae_pretraining_BB.py:219-223
+    opt = torch.optim.AdamW(param_groups(model), lr=lr, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+    scaler = U.NativeScalerWithGradNormCount()
+    gen = mg.TubeMaskingGenerator_BB((8, 14, 14), 0.9, 0.75, device=dev)
+    mean = torch.tensor((0.485, 0.456, 0.406), device=dev)[None, :, None, None, None]
+    std = torch.tensor((0.229, 0.224, 0.225), device=dev)[None, :, None, None, None]
+
+    # synthetic inputs: POOL rotating batches so every step reads inputs that are not L2-resident
+    POOL = 4
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    rng = np.random.default_rng(4321 + rank)
+    pool = []
+    for i in range(POOL):
+        vid = (torch.rand(B, 3, 16, 224, 224, generator=g, device=dev) - mean) / std
+        w = rng.integers(32, 161, B); h = rng.integers(32, 161, B)
+        x1 = (rng.random(B) * (224 - w + 1)).astype(np.int64); y1 = (rng.random(B) * (224 - h + 1)).astype(np.int64)
+        bb = torch.from_numpy(np.stack([x1, y1, x1 + w, y1 + h], 1).astype(np.float64)).to(dev)
+        words = np.stack([mg.mt19937_words((rank * POOL + i) * B + b, 768) for b in range(B)])
+        words = torch.from_numpy(words.view(np.int32)).to(dev)
+        pool.append((vid.contiguous(), bb, words))
+    sync = GradSync()
+    runner = model._runner
+    runner._ensure_device(dev)
+    arena = runner.grad_arena()
+
+    def device_step(i):
+        vid, bb, words = pool[i % POOL]
+        mask, vis_idx, msk_idx, used = gen.generate_batch(bb, words)
+        sync.begin(arena, runner.stage_end)
+        loss = model.pretrain_step(vid, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=True, grad_scale=sync.grad_scale,
+                                   zero_grad=True, stage_done=sync.stage_done)
+        sync.finish()
+        scaler(loss, opt, clip_grad=0, parameters=None, arena=arena)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        loss = device_step(i)
+    barrier()
+    assert torch.isfinite(loss).item(), "non-finite loss in warm-up"
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    with _lib.timing("mofo_gemm_tn") as ktimer:
+        e0.record()
+        for i in range(args.steps):
+            loss = device_step(args.warmup + i)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = B * world * args.steps / (ms / 1e3)
+    n_gemm, gemm_ms, gemm_flops = ktimer.summary()
+    final_loss = loss.item()
+
+    # ---- e2e: the public engine API with HOST (pinned) batches; H2D + loss D2H inside the timed region ----------
+    e2e = None
+    if not args.no_e2e:
+        class HostLoader:
+            quiet = True
+
+            def __init__(self, n):
+                self.n = n
+                self.batches = []
+                for i in range(2):
+                    vid, bb, words = pool[i]
+                    mask = gen.generate_batch(bb, words)[0]
+                    self.batches.append((vid.cpu().pin_memory(), bb.long().cpu()[:, None, :].expand(B, 16, 4).contiguous(),
+                                         mask.double().cpu().pin_memory()))
+
+            def __len__(self):
+                return self.n
+
+            def __iter__(self):
+                for i in range(self.n):
+                    yield self.batches[i % 2]
+        loader = HostLoader(max(3, args.warmup))
+        eng.train_one_epoch_BB(model, loader, opt, dev, 0, scaler, max_norm=0, patch_size=16, normlize_target=True, start_steps=0)
+        loader = HostLoader(args.steps)
+        barrier()
+        t0 = time.perf_counter()
+        eng.train_one_epoch_BB(model, loader, opt, dev, 0, scaler, max_norm=0, patch_size=16, normlize_target=True, start_steps=0)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        vid_bytes = B * 3 * 16 * 224 * 224 * 4
+        e2e = {"value": B * world * args.steps / dt.item(), "unit": "clips/s",
+               "h2d_bytes_per_step": vid_bytes + B * 1568 * 8, "d2h_bytes_per_step": 4,
+               "api": "mofo_b200.engine_for_pretraining.train_one_epoch_BB, pinned fp32 clips + f64 masks per step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    gflop = TRAIN_GFLOP_PER_CLIP.get(args.model)
+    step_tflops = (value / world) * gflop / 1e3 if gflop else None
+    gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": f"inputs larger than L2: {POOL} rotating {B * 3 * 16 * 224 * 224 * 4 >> 20} MiB batches per GPU",
+                       "optimizer": "torch AdamW(fused) on fp32 masters (SURVEY §8f-1: optimizer kernel is a 'next' row)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "final_loss": final_loss,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05, all fused-epilogue instances)",
+                         "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": gemm_tflops / peaks["bf16_sustained"] if gemm_tflops else None, "traffic": None,
+                         "launches_timed": n_gemm, "kernel_ms_per_step": gemm_ms / args.steps,
+                         "share_of_step": gemm_ms / ms, "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"},
+            "step_mfu": {"algorithmic_tflops_per_gpu": step_tflops, "frac_of_measured_sustained": step_tflops / peaks["bf16_sustained"] if step_tflops else None,
+                         "frac_of_nominal_2250": step_tflops / 2250.0 if step_tflops else None, "gflop_per_clip": gflop}}
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        step = oracle_cpu_step_fn(args.model, cores)
+        t1, _ = step(1)
+        n = 2 if t1 < 6 else 1
+        ts = [step(n)[0] for _ in range(max(1, min(3, int(20 / max(t1 * n, 1e-9)))))]
+        line["cpu_baseline"] = {"value": n * len(ts) / sum(ts), "unit": "clips/s", "cores": cores, "kind": "port",
+                                "sample": f"{len(ts)} step(s) of {n} clip(s) of the same workload (oracle port: numpy mask + torch fp32 CPU fwd/target/MSE/bwd + AdamW)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -66,10 +66,46 @@ def load() -> C.CDLL:
     return lib
 
 
+# kernels launched per successful C-ABI call (bench.py reports the count it observed as "gpu_launches")
+_LAUNCHES = {"mofo_target_mse": 2, "mofo_attn_bwd": 3}
+launch_count = 0
+
+
+class KernelTimer:
+    """Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline leg):
+    ``with _lib.timing("mofo_gemm_tn") as t: ...`` then ``t.summary()`` -> (launches, total_ms, total_flops)."""
+
+    def __init__(self, name):
+        self.name, self.events, self.flops = name, [], 0.0
+
+    def __enter__(self):
+        global _timer
+        _timer = self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self.events)
+        return len(self.events), ms, self.flops
+
+
+_timer = None
+
+
+def timing(name):
+    return KernelTimer(name)
+
+
 def _check(rc: int, what: str):
+    global launch_count
     if rc != 0:
         msg = load().mofo_last_error()
         raise MofoError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")
+    launch_count += _LAUNCHES.get(what, 1)
 
 
 def _ptr(t):
@@ -136,11 +172,18 @@ def gemm_tn(A, Bm, epilogue, out0, out1=None, bias=None, resid=None, aux=None, p
     N = Bm.shape[0]
     assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16 and Bm.shape[1] == K
     assert A.stride(1) == 1 and Bm.stride(1) == 1 and out0.stride(-1) == 1
+    t = _timer if (_timer is not None and _timer.name == "mofo_gemm_tn") else None
+    if t is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     _check(load().mofo_gemm_tn(_ptr(A), A.stride(0), _ptr(Bm), Bm.stride(0), M, N, K, epilogue, _ptr(bias), _ptr(resid),
                                resid.stride(0) if resid is not None else 0, _ptr(aux),
                                aux.stride(0) if aux is not None else 0, _ptr(pos), _ptr(row_idx), group_rows,
                                out_group_rows, _ptr(out0), out0.stride(0), _ptr(out1),
                                out1.stride(0) if out1 is not None else 0, _stream()), "mofo_gemm_tn")
+    if t is not None:
+        e1.record()
+        t.events.append((e0, e1)); t.flops += 2.0 * M * N * K
     return out0
 
 

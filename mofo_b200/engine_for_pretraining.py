@@ -1,0 +1,142 @@
+"""B200-native look-alike of the reference's ``engine_for_pretraining.py``.
+
+``train_one_epoch_BB`` keeps the reference signature and return value (engine_for_pretraining.py:215-218,468) and the
+per-step protocol of its loop body (:228-464): table-driven lr/wd, H2D of the batch, target construction + model +
+MSE, non-finite-loss exit, optimizer step through ``loss_scaler``, the same meters.  What changes is where the work
+runs: masking index lists, target (un-normalise / patchify / per-tube normalise, :258-288), forward, loss (:299-304)
+and backward are ONE fused sequence of sm_100a kernels (``model.pretrain_step``), gradients land in a flat arena, and
+the data-parallel mean is an NCCL all-reduce of arena slices overlapped with backward (mofo_b200/dp.py) instead of
+DDP's reducer.  The dead ``video_masks`` work of :243-249 (result unused) is not performed.
+
+Two paths, chosen per call:
+  * fused (default)  — ``loss_scaler`` is ``mofo_b200.utils.NativeScalerWithGradNormCount`` (bf16: scale == 1).
+  * autograd-compat  — any other scaler object (e.g. the reference's GradScaler-based one): labels come from the
+    target kernel, ``model(videos, mask)`` runs through autograd (kernel backward), and the scaler drives
+    ``backward()`` / ``step()`` exactly as in the reference; DDP wrappers work unchanged on this path.
+Aliases for the two names ``run_mae_pretraining_BB.py`` calls but the reference never defines are exported.
+"""
+from __future__ import annotations
+
+import math
+import sys
+from typing import Iterable
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import utils as _utils
+from .dp import GradSync
+
+__all__ = ["train_one_epoch_BB", "train_one_epoch_BB_no_global_union_gradual", "build_labels"]
+
+
+def _core(model):
+    return model.module if hasattr(model, "module") else model
+
+
+def build_labels(videos, msk_idx, normalize_target=True):
+    """labels f32 [B, N_mask, 1536] from the target kernel (engine_for_pretraining.py:258-288)."""
+    B = videos.shape[0]
+    n = msk_idx.shape[1]
+    out = torch.empty(B * n, 1536, dtype=torch.float32, device=videos.device)
+    _lib.target_mse(videos, msk_idx, None, None, None, None, normalize_target, 1.0, out)
+    return out.view(B, n, 1536)
+
+
+def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer: torch.optim.Optimizer,
+                       device: torch.device, epoch: int, loss_scaler, max_norm: float = 0, patch_size: int = 16,
+                       normlize_target: bool = True, log_writer=None, lr_scheduler=None, start_steps=None,
+                       lr_schedule_values=None, wd_schedule_values=None, loss_weight=None):
+    model.train()
+    metric_logger = _utils.MetricLogger(delimiter="  ", quiet=getattr(data_loader, "quiet", False))
+    metric_logger.add_meter('lr', _utils.SmoothedValue(window_size=1, fmt='{value:.6f}'))
+    metric_logger.add_meter('min_lr', _utils.SmoothedValue(window_size=1, fmt='{value:.6f}'))
+    header = 'Epoch: [{}]'.format(epoch)
+    print_freq = 10
+    if patch_size != 16:
+        raise NotImplementedError("the target kernel is specialised for 16x16 patches, tubelet 2")
+    core = _core(model)
+    fused = isinstance(loss_scaler, _utils.NativeScalerWithGradNormCount)
+    sync = GradSync() if fused else None
+    start_steps = start_steps or 0
+
+    for step, batch in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
+        it = start_steps + step                                                         # :230
+        if lr_schedule_values is not None or wd_schedule_values is not None:
+            for i, param_group in enumerate(optimizer.param_groups):
+                if lr_schedule_values is not None:
+                    param_group["lr"] = lr_schedule_values[it] * param_group.get("lr_scale", 1.0)
+                if wd_schedule_values is not None and param_group["weight_decay"] > 0:
+                    param_group["weight_decay"] = wd_schedule_values[it]
+
+        videos, bbox, bool_masked_pos = batch                                           # :238
+        videos = videos.to(device, non_blocking=True)
+        bool_masked_pos = bool_masked_pos.to(device, non_blocking=True).flatten(1).to(torch.bool)
+
+        if fused:
+            core._runner._ensure_device(videos.device)
+            arena = core._runner.grad_arena()
+            vis_idx, msk_idx = core.indices_from_mask(bool_masked_pos)
+            sync.begin(arena, core._runner.stage_end)
+            loss = core.pretrain_step(videos, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=normlize_target,
+                                      grad_scale=sync.grad_scale, zero_grad=True, stage_done=sync.stage_done)
+            sync.finish()
+            loss_value = loss.item()                                                    # :306 (the step's D2H read)
+            if not math.isfinite(loss_value):
+                print("Loss is {}, stopping training".format(loss_value))
+                sys.exit(1)
+            grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=core.parameters(), arena=arena)
+        else:
+            vis_idx, msk_idx = core.indices_from_mask(bool_masked_pos)
+            with torch.no_grad():
+                labels = build_labels(videos.float().contiguous(), msk_idx, normlize_target)
+            outputs = model(videos, bool_masked_pos)
+            loss = nn.functional.mse_loss(outputs.float(), labels)
+            loss_value = loss.item()
+            if not math.isfinite(loss_value):
+                print("Loss is {}, stopping training".format(loss_value))
+                sys.exit(1)
+            optimizer.zero_grad()
+            is_second_order = hasattr(optimizer, 'is_second_order') and optimizer.is_second_order
+            grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=model.parameters(),
+                                    create_graph=is_second_order)
+        loss_scale_value = loss_scaler.state_dict()["scale"]
+
+        torch.cuda.synchronize()                                                        # :429
+
+        metric_logger.update(loss=loss_value)
+        metric_logger.update(loss_scale=loss_scale_value)
+        min_lr, max_lr = 10., 0.
+        for group in optimizer.param_groups:
+            min_lr = min(min_lr, group["lr"])
+            max_lr = max(max_lr, group["lr"])
+        metric_logger.update(lr=max_lr)
+        metric_logger.update(min_lr=min_lr)
+        weight_decay_value = None
+        for group in optimizer.param_groups:
+            if group["weight_decay"] > 0:
+                weight_decay_value = group["weight_decay"]
+        metric_logger.update(weight_decay=weight_decay_value)
+        metric_logger.update(grad_norm=grad_norm)
+
+        if log_writer is not None:
+            log_writer.update(loss=loss_value, head="loss")
+            log_writer.update(loss_scale=loss_scale_value, head="opt")
+            log_writer.update(lr=max_lr, head="opt")
+            log_writer.update(min_lr=min_lr, head="opt")
+            log_writer.update(weight_decay=weight_decay_value, head="opt")
+            log_writer.update(grad_norm=grad_norm, head="opt")
+            log_writer.set_step()
+        if lr_scheduler is not None:
+            lr_scheduler.step_update(start_steps + step)
+
+    core.check_mask_rows()
+    metric_logger.synchronize_between_processes()                                       # :466
+    if not metric_logger.quiet:
+        print("Averaged stats:", metric_logger)
+    return {k: meter.global_avg for k, meter in metric_logger.meters.items()}
+
+
+# run_mae_pretraining_BB.py:271 calls this undefined name; the intended binding is train_one_epoch_BB
+train_one_epoch_BB_no_global_union_gradual = train_one_epoch_BB

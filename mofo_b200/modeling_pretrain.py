@@ -1,0 +1,624 @@
+"""B200-native look-alike of the reference's ``modeling_pretrain.py``.
+
+Same public surface as /root/reference/modeling_pretrain.py (:163-338):
+  * ``PretrainVisionTransformer(...)`` with the same constructor keywords, ``forward(x, mask)``,
+    ``no_weight_decay()``, ``encoder.patch_embed.patch_size`` and — key for checkpoints — the same 218
+    ``state_dict`` names and shapes, so reference checkpoints load and finetuning's
+    ``encoder.``-prefix stripping still works;
+  * registry entry points ``pretrain_mae_small_patch16_224``, ``pretrain_videomae_base_patch16_224``,
+    ``pretrain_videomae_large_patch16_224`` (registered with timm when timm is importable).
+
+The nn.Module tree only HOLDS parameters (fp32 masters).  All arithmetic — forward and backward — runs in
+hand-written sm_100a kernels behind the C ABI of libmofo_sm100.so (include/mofo_b200.h), orchestrated by
+``_Runner`` below.  There is no PyTorch fallback: on a machine without CUDA ``forward`` raises.
+
+Two entry points share the runner:
+  * ``forward(x, mask)``: drop-in; returns predictions [B, N_mask, 1536] (bf16) wired into autograd through a
+    single ``autograd.Function`` whose backward is the manual kernel backward.
+  * ``pretrain_step(videos, mask | index lists)``: the fused step the engine uses — forward, target + MSE and
+    backward in one pass, gradients accumulated straight into the flat gradient arena (``.grad`` views).
+
+Numerics (vs. the reference under autocast): GEMM inputs bf16, fp32 accumulation; the residual
+stream, LayerNorm statistics, softmax and the loss are fp32; parameters, gradients and the arena are fp32.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["PretrainVisionTransformer", "pretrain_mae_small_patch16_224", "pretrain_videomae_base_patch16_224",
+           "pretrain_videomae_large_patch16_224", "get_sinusoid_encoding_table", "create_model"]
+
+
+def get_sinusoid_encoding_table(n_position, d_hid):
+    """Sinusoid table, f64 numpy then FloatTensor [1,n,d] (same arithmetic as modeling_finetune.py:252-262,
+    vectorised)."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)
+    tab = pos / np.power(10000, 2 * (j // 2) / d_hid)[None, :]
+    tab[:, 0::2] = np.sin(tab[:, 0::2])
+    tab[:, 1::2] = np.cos(tab[:, 1::2])
+    return torch.FloatTensor(tab).unsqueeze(0)
+
+
+def _trunc_normal_(tensor, mean=0., std=1.):
+    return nn.init.trunc_normal_(tensor, mean=mean, std=std, a=-std, b=std)   # modeling_pretrain.py:13-14
+
+
+# ----------------------------------------------------------------------------------------------------------
+# parameter holders (names / shapes / init identical to the reference modules; their forward is never used)
+# ----------------------------------------------------------------------------------------------------------
+class _Attention(nn.Module):
+    def __init__(self, dim, num_heads, qkv_bias):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=False)
+        if qkv_bias:
+            self.q_bias = nn.Parameter(torch.zeros(dim))
+            self.v_bias = nn.Parameter(torch.zeros(dim))
+        else:
+            raise NotImplementedError("mofo_b200 implements the registry models, which all use qkv_bias=True")
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio, qkv_bias, norm_layer):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = _Attention(dim, num_heads, qkv_bias)
+        self.norm2 = norm_layer(dim)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, img_size, patch_size, in_chans, embed_dim, num_frames=16, tubelet_size=2):
+        super().__init__()
+        self.img_size = (img_size, img_size)
+        self.patch_size = (patch_size, patch_size)
+        self.tubelet_size = int(tubelet_size)
+        self.num_patches = (img_size // patch_size) ** 2 * (num_frames // self.tubelet_size)
+        self.proj = nn.Conv3d(in_chans, embed_dim, kernel_size=(self.tubelet_size, patch_size, patch_size),
+                              stride=(self.tubelet_size, patch_size, patch_size))
+
+
+def _init_weights(m):
+    if isinstance(m, nn.Linear):                      # modeling_pretrain.py:60-67
+        nn.init.xavier_uniform_(m.weight)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+    elif isinstance(m, nn.LayerNorm):
+        nn.init.constant_(m.bias, 0)
+        nn.init.constant_(m.weight, 1.0)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, img_size, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, qkv_bias, norm_layer,
+                 tubelet_size):
+        super().__init__()
+        self.num_features = self.embed_dim = embed_dim
+        self.patch_embed = _PatchEmbed(img_size, patch_size, in_chans, embed_dim, tubelet_size=tubelet_size)
+        self.blocks = nn.ModuleList([_Block(embed_dim, num_heads, mlp_ratio, qkv_bias, norm_layer) for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        self.head = nn.Identity()
+        self.apply(_init_weights)
+
+    def get_num_layers(self):
+        return len(self.blocks)
+
+    def no_weight_decay(self):
+        return {'pos_embed', 'cls_token'}
+
+
+class _Decoder(nn.Module):
+    def __init__(self, patch_size, num_classes, embed_dim, depth, num_heads, mlp_ratio, qkv_bias, norm_layer,
+                 tubelet_size):
+        super().__init__()
+        assert num_classes == 3 * tubelet_size * patch_size ** 2          # modeling_pretrain.py:112
+        self.num_classes = num_classes
+        self.num_features = self.embed_dim = embed_dim
+        self.patch_size = patch_size
+        self.blocks = nn.ModuleList([_Block(embed_dim, num_heads, mlp_ratio, qkv_bias, norm_layer) for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        self.head = nn.Linear(embed_dim, num_classes)
+        self.apply(_init_weights)
+
+    def get_num_layers(self):
+        return len(self.blocks)
+
+    def no_weight_decay(self):
+        return {'pos_embed', 'cls_token'}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# kernel orchestration
+# ----------------------------------------------------------------------------------------------------------
+class _Runner:
+    """Owns the device-side state of one model: bf16 weight copies, position tables, activation workspace and the
+    flat gradient arena, and sequences the C-ABI calls of one forward / backward."""
+
+    def __init__(self, model: "PretrainVisionTransformer"):
+        self.m = model
+        self.bufs = {}
+        self.wcache = {}
+        self.wversion = None
+        self.device = None
+        self.arena = None
+        self.arena_views = None
+        self.scratch_arena = None
+        self.enc_group = 4          # encoder blocks per gradient-sync stage
+        self.stage_end = None
+
+    # ---- memory -------------------------------------------------------------------------------------------
+    def buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(*shape, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        return t
+
+    def _ensure_device(self, device):
+        if self.device != device:
+            self.device = device
+            self.bufs.clear(); self.wcache.clear(); self.wversion = None
+            self.arena = None; self.arena_views = None; self.scratch_arena = None
+            m = self.m
+            self.pos_enc = m.encoder_pos_embed[0].to(device).contiguous()
+            self.pos_dec = m.pos_embed[0].to(device).contiguous()
+
+    def backward_order(self):
+        """Parameter names in the order the backward pass finishes their gradients, with the stage index at which
+        each becomes final: stage 0 = decoder (+ head, mask_token, encoder_to_decoder), then encoder blocks in
+        groups of ``enc_group`` from the last to the first, the patch embedding riding with the final group."""
+        m = self.m
+        names = dict(m.named_parameters())
+        order, stage_of = [], {}
+
+        def add(prefix, stage):
+            for n in names:
+                if (n == prefix or n.startswith(prefix + ".")) and n not in stage_of:
+                    order.append(n); stage_of[n] = stage
+
+        add("decoder.head", 0); add("decoder.norm", 0)
+        for i in range(len(m.decoder.blocks) - 1, -1, -1):
+            add(f"decoder.blocks.{i}", 0)
+        add("mask_token", 0); add("encoder_to_decoder", 0); add("encoder.norm", 0)
+        ne = len(m.encoder.blocks)
+        for i in range(ne - 1, -1, -1):
+            add(f"encoder.blocks.{i}", 1 + (ne - 1 - i) // self.enc_group)
+        last = 1 + (ne - 1) // self.enc_group
+        add("encoder.patch_embed", last)
+        assert len(order) == len(names)
+        return order, stage_of, last + 1
+
+    def _make_arena(self):
+        params = dict(self.m.named_parameters())
+        order, stage_of, n_stages = self.backward_order()
+        total = sum((params[n].numel() + 3) // 4 * 4 for n in order)     # 16-byte aligned slices
+        arena = torch.zeros(total, dtype=torch.float32, device=self.device)
+        views, off = {}, 0
+        stage_end = [0] * n_stages
+        for n in order:
+            p = params[n]
+            views[n] = arena[off:off + p.numel()].view(p.shape)
+            off += (p.numel() + 3) // 4 * 4
+            stage_end[stage_of[n]] = off
+        self.stage_end = stage_end
+        return arena, views
+
+    def grad_arena(self):
+        """Flat fp32 gradient arena; every parameter's ``.grad`` is a view into it (reverse-order slices make it
+        directly usable for bucketed NCCL all-reduce)."""
+        if self.arena is None:
+            self.arena, self.arena_views = self._make_arena()
+        for n, p in self.m.named_parameters():
+            v = self.arena_views[n]
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+        return self.arena
+
+    # ---- weights ------------------------------------------------------------------------------------------
+    def prepare_weights(self):
+        m = self.m
+        version = tuple(p._version for p in m.parameters())
+        if version == self.wversion:
+            return
+        self.wversion = version
+        wc = self.wcache
+
+        def cast(name, W, need_t=True):
+            R = W.shape[0]
+            C = W.numel() // R
+            if name not in wc:
+                wc[name] = (torch.empty(R, C, dtype=torch.bfloat16, device=self.device),
+                            torch.empty(C, R, dtype=torch.bfloat16, device=self.device) if need_t else None)
+            wb, wt = wc[name]
+            _lib.cast_weight(W.detach(), wb, wt)
+
+        cast("pe", m.encoder.patch_embed.proj.weight, need_t=False)
+        for tag, blocks in (("enc", m.encoder.blocks), ("dec", m.decoder.blocks)):
+            for i, blk in enumerate(blocks):
+                pre = f"{tag}{i}"
+                cast(pre + ".qkv", blk.attn.qkv.weight)
+                cast(pre + ".proj", blk.attn.proj.weight)
+                cast(pre + ".fc1", blk.mlp.fc1.weight)
+                cast(pre + ".fc2", blk.mlp.fc2.weight)
+                qb = self.buf(pre + ".qkvbias", (3 * blk.attn.q_bias.numel(),), torch.float32)
+                _lib.pack_qkv_bias(blk.attn.q_bias.detach(), blk.attn.v_bias.detach(), qb)
+        cast("e2d", m.encoder_to_decoder.weight)
+        cast("head", m.decoder.head.weight)
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def _block_fwd(self, pre, blk, x, M, S, B, D):
+        H = blk.attn.num_heads
+        bf, f32 = torch.bfloat16, torch.float32
+        wc = self.wcache
+        h1 = self.buf(pre + ".h1", (M, D), bf); mean1 = self.buf(pre + ".mean1", (M,), f32); rstd1 = self.buf(pre + ".rstd1", (M,), f32)
+        _lib.layernorm_fwd(x, blk.norm1.weight, blk.norm1.bias, h1, mean1, rstd1, M, D, blk.norm1.eps)
+        qkv = self.buf(pre + ".qkv", (M, 3 * D), bf)
+        _lib.gemm_tn(h1, wc[pre + ".qkv"][0], _lib.EPI_BIAS_BF16, qkv, bias=self.buf(pre + ".qkvbias", (3 * D,), f32))
+        o = self.buf(pre + ".o", (M, D), bf); lse = self.buf(pre + ".lse", (B, H, S), f32)
+        _lib.attn_fwd(qkv, B, S, H, blk.attn.scale, o, lse)
+        xm = self.buf(pre + ".xm", (M, D), f32)
+        _lib.gemm_tn(o, wc[pre + ".proj"][0], _lib.EPI_BIAS_RESID_F32, xm, bias=blk.attn.proj.bias, resid=x)
+        h2 = self.buf(pre + ".h2", (M, D), bf); mean2 = self.buf(pre + ".mean2", (M,), f32); rstd2 = self.buf(pre + ".rstd2", (M,), f32)
+        _lib.layernorm_fwd(xm, blk.norm2.weight, blk.norm2.bias, h2, mean2, rstd2, M, D, blk.norm2.eps)
+        Dh = blk.mlp.fc1.weight.shape[0]
+        u = self.buf(pre + ".u", (M, Dh), bf); a = self.buf(pre + ".a", (M, Dh), bf)
+        _lib.gemm_tn(h2, wc[pre + ".fc1"][0], _lib.EPI_BIAS_GELU_BF16, u, out1=a, bias=blk.mlp.fc1.bias)
+        xo = self.buf(pre + ".xo", (M, D), f32)
+        _lib.gemm_tn(a, wc[pre + ".fc2"][0], _lib.EPI_BIAS_RESID_F32, xo, bias=blk.mlp.fc2.bias, resid=xm)
+        return xo
+
+    def forward(self, x, vis_idx, msk_idx):
+        m = self.m
+        self._ensure_device(x.device)
+        self.prepare_weights()
+        bf, f32 = torch.bfloat16, torch.float32
+        B = x.shape[0]
+        Nv, Nm = vis_idx.shape[1], msk_idx.shape[1]
+        N = Nv + Nm
+        D, Dd = m.encoder.embed_dim, m.decoder.embed_dim
+        wc = self.wcache
+        self.shape = (B, Nv, Nm)
+        # patch embed on the visible tubes only + bias + pos  (modeling_pretrain.py:85-90)
+        A_pe = self.buf("A_pe", (B * Nv, 1536), bf)
+        _lib.gather_tubes(x, vis_idx, A_pe)
+        xe = self.buf("x0", (B * Nv, D), f32)
+        pe = m.encoder.patch_embed.proj
+        _lib.gemm_tn(A_pe, wc["pe"][0], _lib.EPI_BIAS_POS_F32, xe, bias=pe.bias, pos=self.pos_enc, row_idx=vis_idx,
+                     group_rows=Nv, out_group_rows=Nv)
+        for i, blk in enumerate(m.encoder.blocks):
+            xe = self._block_fwd(f"enc{i}", blk, xe, B * Nv, Nv, B, D)
+        self.x_enc_out = xe
+        hn = self.buf("enc.hn", (B * Nv, D), bf); mean = self.buf("enc.mean", (B * Nv,), f32); rstd = self.buf("enc.rstd", (B * Nv,), f32)
+        _lib.layernorm_fwd(xe, m.encoder.norm.weight, m.encoder.norm.bias, hn, mean, rstd, B * Nv, D, m.encoder.norm.eps)
+        # encoder_to_decoder + pos_vis written into the first Nv rows of each clip; mask tokens fill the rest
+        xf = self.buf("xfull", (B * N, Dd), f32)
+        _lib.gemm_tn(hn, wc["e2d"][0], _lib.EPI_BIAS_POS_F32, xf, pos=self.pos_dec, row_idx=vis_idx, group_rows=Nv,
+                     out_group_rows=N)
+        _lib.decoder_assemble_fwd(m.mask_token, self.pos_dec, msk_idx, B, Nv, Nm, Dd, xf)
+        xd = xf
+        for i, blk in enumerate(m.decoder.blocks):
+            xd = self._block_fwd(f"dec{i}", blk, xd, B * N, N, B, Dd)
+        self.x_dec_out = xd
+        hd = self.buf("dec.hd", (B * Nm, Dd), bf); mean = self.buf("dec.mean", (B * Nm,), f32); rstd = self.buf("dec.rstd", (B * Nm,), f32)
+        _lib.layernorm_fwd(xd, m.decoder.norm.weight, m.decoder.norm.bias, hd, mean, rstd, B * Nm, Dd, m.decoder.norm.eps,
+                           group_rows=Nm, in_group_rows=N, in_row_offset=Nv)
+        pred = self.buf("pred", (B * Nm, m.decoder.num_classes), bf)
+        _lib.gemm_tn(hd, wc["head"][0], _lib.EPI_BIAS_BF16, pred, bias=m.decoder.head.bias)
+        return pred
+
+    # ---- backward -----------------------------------------------------------------------------------------
+    def _block_bwd(self, pre, blk, g, x_in, dxA, dxA16, dxB, dxB16, M, S, B, D):
+        """dxA/dxA16 hold d(loss)/d(block output) (f32 + bf16).  On return they hold d(loss)/d(block input)."""
+        H = blk.attn.num_heads
+        bf, f32 = torch.bfloat16, torch.float32
+        wc = self.wcache
+        Dh = blk.mlp.fc1.weight.shape[0]
+        name = blk._mofo_name
+        h1 = self.buf(pre + ".h1", (M, D), bf); mean1 = self.buf(pre + ".mean1", (M,), f32); rstd1 = self.buf(pre + ".rstd1", (M,), f32)
+        qkv = self.buf(pre + ".qkv", (M, 3 * D), bf); o = self.buf(pre + ".o", (M, D), bf); lse = self.buf(pre + ".lse", (B, H, S), f32)
+        xm = self.buf(pre + ".xm", (M, D), f32)
+        h2 = self.buf(pre + ".h2", (M, D), bf); mean2 = self.buf(pre + ".mean2", (M,), f32); rstd2 = self.buf(pre + ".rstd2", (M,), f32)
+        u = self.buf(pre + ".u", (M, Dh), bf); a = self.buf(pre + ".a", (M, Dh), bf)
+        # fc2
+        _lib.gemm_wgrad(dxA16, a, g[name + ".mlp.fc2.weight"])
+        _lib.colsum_bf16(dxA16, M, D, g[name + ".mlp.fc2.bias"])
+        du = self.buf("bwd.du", (M, Dh), bf)
+        _lib.gemm_tn(dxA16, wc[pre + ".fc2"][1], _lib.EPI_GELU_BWD_BF16, du, aux=u)
+        # fc1
+        _lib.gemm_wgrad(du, h2, g[name + ".mlp.fc1.weight"])
+        _lib.colsum_bf16(du, M, Dh, g[name + ".mlp.fc1.bias"])
+        dh = self.buf("bwd.dh", (M, D), bf)
+        _lib.gemm_tn(du, wc[pre + ".fc1"][1], _lib.EPI_PLAIN_BF16, dh)
+        # norm2 (+ residual gradient)
+        _lib.layernorm_bwd(dh, xm, blk.norm2.weight, mean2, rstd2, dxA, M, D, dxB, dxB16, g[name + ".norm2.weight"],
+                           g[name + ".norm2.bias"])
+        # proj
+        _lib.gemm_wgrad(dxB16, o, g[name + ".attn.proj.weight"])
+        _lib.colsum_bf16(dxB16, M, D, g[name + ".attn.proj.bias"])
+        do = self.buf("bwd.do", (M, D), bf)
+        _lib.gemm_tn(dxB16, wc[pre + ".proj"][1], _lib.EPI_PLAIN_BF16, do)
+        # attention
+        dqkv = self.buf("bwd.dqkv", (M, 3 * D), bf); delta = self.buf("bwd.delta", (B, H, S), f32)
+        _lib.attn_bwd(qkv, o, do, lse, B, S, H, blk.attn.scale, dqkv, delta)
+        # qkv
+        _lib.gemm_wgrad(dqkv, h1, g[name + ".attn.qkv.weight"])
+        _lib.colsum_bf16(dqkv[:, :D], M, D, g[name + ".attn.q_bias"])
+        _lib.colsum_bf16(dqkv[:, 2 * D:], M, D, g[name + ".attn.v_bias"])
+        _lib.gemm_tn(dqkv, wc[pre + ".qkv"][1], _lib.EPI_PLAIN_BF16, dh)
+        # norm1 (+ residual gradient)
+        _lib.layernorm_bwd(dh, x_in, blk.norm1.weight, mean1, rstd1, dxB, M, D, dxA, dxA16, g[name + ".norm1.weight"],
+                           g[name + ".norm1.bias"])
+
+    def backward(self, dpred, g, stage_done=None):
+        """dpred bf16 [B*Nm, 1536]; g: name -> fp32 tensor that the parameter gradient is ACCUMULATED into.
+        ``stage_done(k)`` is called as soon as every gradient of arena stage k has been enqueued (see
+        ``backward_order``), so the caller can start that slice's all-reduce while backward continues."""
+        m = self.m
+        bf, f32 = torch.bfloat16, torch.float32
+        B, Nv, Nm = self.shape
+        N = Nv + Nm
+        D, Dd = m.encoder.embed_dim, m.decoder.embed_dim
+        wc = self.wcache
+        C = m.decoder.num_classes
+        # head
+        hd = self.buf("dec.hd", (B * Nm, Dd), bf)
+        _lib.gemm_wgrad(dpred, hd, g["decoder.head.weight"])
+        _lib.colsum_bf16(dpred, B * Nm, C, g["decoder.head.bias"])
+        dhd = self.buf("bwd.dhd", (B * Nm, Dd), bf)
+        _lib.gemm_tn(dpred, wc["head"][1], _lib.EPI_PLAIN_BF16, dhd)
+        # decoder.norm on the masked rows; visible rows receive zero gradient from the head
+        dxA = self.buf("bwd.dec.dxA", (B * N, Dd), f32); dxA16 = self.buf("bwd.dec.dxA16", (B * N, Dd), bf)
+        dxB = self.buf("bwd.dec.dxB", (B * N, Dd), f32); dxB16 = self.buf("bwd.dec.dxB16", (B * N, Dd), bf)
+        dxA.zero_(); dxA16.zero_()
+        _lib.layernorm_bwd(dhd, self.x_dec_out, m.decoder.norm.weight, self.buf("dec.mean", (B * Nm,), f32),
+                           self.buf("dec.rstd", (B * Nm,), f32), None, B * Nm, Dd, dxA, dxA16, g["decoder.norm.weight"],
+                           g["decoder.norm.bias"], group_rows=Nm, in_group_rows=N, in_row_offset=Nv)
+        nd = len(m.decoder.blocks)
+        for i in range(nd - 1, -1, -1):
+            x_in = self.buf("xfull", (B * N, Dd), f32) if i == 0 else self.buf(f"dec{i - 1}.xo", (B * N, Dd), f32)
+            self._block_bwd(f"dec{i}", m.decoder.blocks[i], g, x_in, dxA, dxA16, dxB, dxB16, B * N, N, B, Dd)
+        # decoder input assembly: mask_token gradient + gradient entering encoder_to_decoder
+        dvis = self.buf("bwd.dvis", (B * Nv, Dd), bf)
+        _lib.decoder_assemble_bwd(dxA, B, Nv, Nm, Dd, g["mask_token"], dvis)
+        hn = self.buf("enc.hn", (B * Nv, D), bf)
+        _lib.gemm_wgrad(dvis, hn, g["encoder_to_decoder.weight"])
+        dhn = self.buf("bwd.dhn", (B * Nv, D), bf)
+        _lib.gemm_tn(dvis, wc["e2d"][1], _lib.EPI_PLAIN_BF16, dhn)
+        exA = self.buf("bwd.enc.dxA", (B * Nv, D), f32); exA16 = self.buf("bwd.enc.dxA16", (B * Nv, D), bf)
+        exB = self.buf("bwd.enc.dxB", (B * Nv, D), f32); exB16 = self.buf("bwd.enc.dxB16", (B * Nv, D), bf)
+        _lib.layernorm_bwd(dhn, self.x_enc_out, m.encoder.norm.weight, self.buf("enc.mean", (B * Nv,), f32),
+                           self.buf("enc.rstd", (B * Nv,), f32), None, B * Nv, D, exA, exA16, g["encoder.norm.weight"],
+                           g["encoder.norm.bias"])
+        if stage_done is not None:
+            stage_done(0)
+        ne = len(m.encoder.blocks)
+        last_stage = 1 + (ne - 1) // self.enc_group
+        for i in range(ne - 1, -1, -1):
+            x_in = self.buf("x0", (B * Nv, D), f32) if i == 0 else self.buf(f"enc{i - 1}.xo", (B * Nv, D), f32)
+            self._block_bwd(f"enc{i}", m.encoder.blocks[i], g, x_in, exA, exA16, exB, exB16, B * Nv, Nv, B, D)
+            stage = 1 + (ne - 1 - i) // self.enc_group
+            if stage_done is not None and stage != last_stage and (i == 0 or 1 + (ne - i) // self.enc_group != stage):
+                stage_done(stage)
+        # patch embedding (no input gradient)
+        A_pe = self.buf("A_pe", (B * Nv, 1536), bf)
+        _lib.gemm_wgrad(exA16, A_pe, g["encoder.patch_embed.proj.weight"])
+        _lib.colsum_bf16(exA16, B * Nv, D, g["encoder.patch_embed.proj.bias"])
+        if stage_done is not None:
+            stage_done(last_stage)
+
+
+class _ForwardFn(torch.autograd.Function):
+    """pred = model(x, mask) with the manual kernel backward (drop-in autograd path)."""
+
+    @staticmethod
+    def forward(ctx, runner, x, vis_idx, msk_idx, *params):
+        pred = runner.forward(x, vis_idx, msk_idx)
+        ctx.runner = runner
+        B, Nv, Nm = runner.shape
+        return pred.view(B, Nm, -1).clone()
+
+    @staticmethod
+    def backward(ctx, dpred):
+        r = ctx.runner
+        B, Nv, Nm = r.shape
+        if r.scratch_arena is None:
+            r.scratch_arena = r._make_arena()
+        arena, views = r.scratch_arena
+        arena.zero_()
+        dp = dpred.reshape(B * Nm, -1).to(torch.bfloat16).contiguous()
+        r.backward(dp, views)
+        grads = tuple(views[n] for n, _ in r.m.named_parameters())
+        return (None, None, None, None) + grads
+
+
+class PretrainVisionTransformer(nn.Module):
+    """See module docstring; constructor signature of modeling_pretrain.py:166-190."""
+
+    def __init__(self, img_size=224, patch_size=16, encoder_in_chans=3, encoder_num_classes=0, encoder_embed_dim=768,
+                 encoder_depth=12, encoder_num_heads=12, decoder_num_classes=1536, decoder_embed_dim=512,
+                 decoder_depth=8, decoder_num_heads=8, mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0., norm_layer=nn.LayerNorm, init_values=0.,
+                 use_learnable_pos_emb=False, tubelet_size=2, num_classes=0, in_chans=0):
+        super().__init__()
+        unsupported = dict(encoder_num_classes=(encoder_num_classes, 0), qk_scale=(qk_scale, None),
+                           drop_rate=(drop_rate, 0.), attn_drop_rate=(attn_drop_rate, 0.),
+                           drop_path_rate=(drop_path_rate, 0.), init_values=(init_values, 0.),
+                           use_learnable_pos_emb=(use_learnable_pos_emb, False), tubelet_size=(tubelet_size, 2),
+                           patch_size=(patch_size, 16), encoder_in_chans=(encoder_in_chans, 3))
+        for k, (v, want) in unsupported.items():
+            if v != want and not (v is None and want is None):
+                raise NotImplementedError(f"mofo_b200 pretraining path supports {k}={want!r} only (got {v!r}); "
+                                          "these are the values run_mae_pretraining_BB.py uses")
+        if encoder_embed_dim // encoder_num_heads != 64 or decoder_embed_dim // decoder_num_heads != 64:
+            raise NotImplementedError("attention kernels are specialised for head_dim 64 (all registry models)")
+        self.encoder = _Encoder(img_size, patch_size, encoder_in_chans, encoder_embed_dim, encoder_depth,
+                                encoder_num_heads, mlp_ratio, qkv_bias, norm_layer, tubelet_size)
+        self.decoder = _Decoder(patch_size, decoder_num_classes, decoder_embed_dim, decoder_depth, decoder_num_heads,
+                                mlp_ratio, qkv_bias, norm_layer, tubelet_size)
+        self.encoder_to_decoder = nn.Linear(encoder_embed_dim, decoder_embed_dim, bias=False)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, decoder_embed_dim))
+        # plain tensor attributes, NOT buffers: absent from state_dict like the reference (modeling_pretrain.py:42,232)
+        self.encoder_pos_embed = get_sinusoid_encoding_table(self.encoder.patch_embed.num_patches, encoder_embed_dim)
+        self.pos_embed = get_sinusoid_encoding_table(self.encoder.patch_embed.num_patches, decoder_embed_dim)
+        self.encoder.pos_embed = self.encoder_pos_embed
+        _trunc_normal_(self.mask_token, std=.02)
+        for i, blk in enumerate(self.encoder.blocks):
+            blk._mofo_name = f"encoder.blocks.{i}"
+        for i, blk in enumerate(self.decoder.blocks):
+            blk._mofo_name = f"decoder.blocks.{i}"
+        self._runner = _Runner(self)
+        self._n_msk = None
+        self._bad_rows = None
+
+    def get_num_layers(self):
+        return len(self.encoder.blocks)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'pos_embed', 'cls_token', 'mask_token'}       # modeling_pretrain.py:250-251
+
+    # ---- helpers ------------------------------------------------------------------------------------------
+    def _require_cuda(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("mofo_b200.PretrainVisionTransformer runs on CUDA (sm_100a) only; there is no CPU path")
+        if self.mask_token.device != x.device:
+            raise RuntimeError("model parameters and input must be on the same CUDA device (call model.to(device))")
+
+    def indices_from_mask(self, mask):
+        """bool [B,N] -> ascending (vis_idx, msk_idx) int32 on device; the masked count per row is read once
+        (first call) and verified on device afterwards (``check_mask_rows``)."""
+        mask = mask.reshape(mask.shape[0], -1)
+        if mask.dtype != torch.bool and mask.dtype != torch.uint8:
+            mask = mask.to(torch.bool)
+        mask = mask.contiguous()
+        if self._n_msk is None:
+            self._n_msk = int(mask[0].sum().item())
+        if self._bad_rows is None or self._bad_rows.device != mask.device:
+            self._bad_rows = torch.zeros(1, dtype=torch.int32, device=mask.device)
+        return _lib.mask_indices(mask, self._n_msk, self._bad_rows)
+
+    def check_mask_rows(self):
+        if self._bad_rows is not None and int(self._bad_rows.item()) != 0:
+            raise RuntimeError("mask rows with unequal masked-token counts (the reference's x[~mask].reshape(B,-1,C) "
+                               "raises here too, modeling_pretrain.py:90)")
+
+    def zero_grad_arena(self):
+        arena = self._runner.grad_arena() if self._runner.device is not None else None
+        if arena is not None:
+            arena.zero_()
+        return arena
+
+    # ---- reference API ------------------------------------------------------------------------------------
+    def forward(self, x, mask):
+        """x: CUDA f32 [B,3,16,224,224]; mask: bool [B,N] (True = masked) -> [B, N_mask, 1536] bf16."""
+        self._require_cuda(x)
+        x = x.float().contiguous()
+        vis_idx, msk_idx = self.indices_from_mask(mask)
+        r = self._runner
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return _ForwardFn.apply(r, x, vis_idx, msk_idx, *self.parameters())
+        with torch.no_grad():
+            pred = r.forward(x, vis_idx, msk_idx)
+            B, Nv, Nm = r.shape
+            return pred.view(B, Nm, -1).clone()
+
+    # ---- fused training step (used by mofo_b200.engine_for_pretraining) --------------------------------
+    def pretrain_step(self, videos, mask=None, vis_idx=None, msk_idx=None, normalize_target=True, grad_scale=1.0,
+                      zero_grad=True, stage_done=None):
+        """One fused pass: forward, target + MSE (engine_for_pretraining.py:258-304) and backward.  Gradients are
+        accumulated into the flat arena (``p.grad`` views).  Returns the loss as a 1-element CUDA tensor (no sync)."""
+        self._require_cuda(videos)
+        videos = videos.float().contiguous()
+        if vis_idx is None:
+            vis_idx, msk_idx = self.indices_from_mask(mask)
+        r = self._runner
+        with torch.no_grad():
+            pred = r.forward(videos, vis_idx, msk_idx)
+            arena = r.grad_arena()
+            if zero_grad:
+                arena.zero_()
+            B, Nv, Nm = r.shape
+            lp = r.buf("loss_partials", (B * Nm,), torch.float32)
+            loss = r.buf("loss", (1,), torch.float32)
+            dpred = r.buf("dpred", (B * Nm, self.decoder.num_classes), torch.bfloat16)
+            _lib.target_mse(videos, msk_idx, pred, lp, loss, dpred, normalize_target, grad_scale)
+            r.backward(dpred, r.arena_views, stage_done)
+        return loss
+
+
+# ----------------------------------------------------------------------------------------------------------
+# registry (modeling_pretrain.py:268-338)
+# ----------------------------------------------------------------------------------------------------------
+_REGISTRY = {}
+
+
+def _register(fn):
+    _REGISTRY[fn.__name__] = fn
+    try:                                          # make timm.create_model(name, ...) work when timm is present
+        from timm.models.registry import register_model
+        register_model(fn)
+    except Exception:
+        pass
+    return fn
+
+
+def _finish(model, pretrained, kwargs):
+    model.default_cfg = {'url': '', 'num_classes': 400, 'input_size': (3, 224, 224), 'pool_size': None, 'crop_pct': .9,
+                         'interpolation': 'bicubic', 'mean': (0.5, 0.5, 0.5), 'std': (0.5, 0.5, 0.5)}
+    if pretrained:
+        checkpoint = torch.load(kwargs["init_ckpt"], map_location="cpu")
+        model.load_state_dict(checkpoint["model"])
+    return model
+
+
+@_register
+def pretrain_mae_small_patch16_224(pretrained=False, **kwargs):
+    init_ckpt = {k: kwargs.pop(k) for k in ("init_ckpt",) if k in kwargs}
+    model = PretrainVisionTransformer(img_size=224, patch_size=16, encoder_embed_dim=384, encoder_depth=12,
+                                      encoder_num_heads=6, encoder_num_classes=0, decoder_num_classes=1536,
+                                      decoder_embed_dim=192, decoder_num_heads=3, mlp_ratio=4, qkv_bias=True,
+                                      norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+    return _finish(model, pretrained, init_ckpt)
+
+
+@_register
+def pretrain_videomae_base_patch16_224(pretrained=False, **kwargs):
+    init_ckpt = {k: kwargs.pop(k) for k in ("init_ckpt",) if k in kwargs}
+    model = PretrainVisionTransformer(img_size=224, patch_size=16, encoder_embed_dim=768, encoder_depth=12,
+                                      encoder_num_heads=12, encoder_num_classes=0, decoder_num_classes=1536,
+                                      decoder_embed_dim=384, decoder_num_heads=6, mlp_ratio=4, qkv_bias=True,
+                                      norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+    return _finish(model, pretrained, init_ckpt)
+
+
+@_register
+def pretrain_videomae_large_patch16_224(pretrained=False, **kwargs):
+    init_ckpt = {k: kwargs.pop(k) for k in ("init_ckpt",) if k in kwargs}
+    model = PretrainVisionTransformer(img_size=224, patch_size=16, encoder_embed_dim=1024, encoder_depth=24,
+                                      encoder_num_heads=16, encoder_num_classes=0, decoder_num_classes=1536,
+                                      decoder_embed_dim=512, decoder_num_heads=8, mlp_ratio=4, qkv_bias=True,
+                                      norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+    return _finish(model, pretrained, init_ckpt)
+
+
+def create_model(name, pretrained=False, **kwargs):
+    """timm.create_model look-alike (drops None-valued kwargs like timm 0.4.12; run_mae_pretraining_BB.py:141-147)."""
+    kwargs = {k: v for k, v in kwargs.items() if v is not None}
+    return _REGISTRY[name](pretrained=pretrained, **kwargs)
