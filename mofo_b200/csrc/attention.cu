@@ -57,9 +57,10 @@ __device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t p_tile, uint32_
 // =================================================================================================
 // forward
 // =================================================================================================
-constexpr int FWD_SMEM = 7 * TILE_BYTES + 64;   // Q, K0, V0, K1, V1, P(2)  + barriers
+constexpr int FWD_SMEM = 7 * TILE_BYTES + 2048 + 64;   // Q, K0, V0, K1, V1, P(2), max/sum exchange, barriers
+constexpr int ATT_THREADS = 256;                       // 2 threads per tile row: each owns half of the columns
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float c /*scale*log2e*/,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -68,11 +69,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
   const uint32_t sQ = base, sP = base + 5 * TILE_BYTES;
   auto sK = [&](int b) { return base + (1 + 2 * b) * TILE_BYTES; };
   auto sV = [&](int b) { return base + (2 + 2 * b) * TILE_BYTES; };
-  const uint32_t bars = base + 7 * TILE_BYTES;
+  float* xch = reinterpret_cast<float*>(smem_raw + 7 * TILE_BYTES);   // [2][128] max, [2][128] sum
+  const uint32_t bars = base + 7 * TILE_BYTES + 2048;
   const uint32_t bar_q = bars, bar_s = bars + 8, bar_o = bars + 16, tmem_slot = bars + 40;
   auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   const int q0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * S;
   const int n_kv = (S + AT - 1) / AT;
@@ -88,8 +91,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t tS = tmem_base + lane_off + half * 64, tO = tmem_base + lane_off + 128 + half * 32;
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, TILE_BYTES);
@@ -99,10 +102,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
     tma_load_2d(sV(0), &tm_qkv, bar_kv(0), (2 * H + h) * 64, row0);
   }
 
-  float o_acc[64];
+  float o_acc[32];
 #pragma unroll
-  for (int e = 0; e < 64; ++e) o_acc[e] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+  for (int e = 0; e < 32; ++e) o_acc[e] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;   // l_run: partial row sum over this thread's columns
 
   for (int j = 0; j < n_kv; ++j) {
     const int buf = j & 1;
@@ -115,39 +118,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
       if (j == 0) mbar_wait(bar_q, 0);
       mbar_wait(bar_kv(buf), (j >> 1) & 1);
       tc_fence_after();
-      mma_qk(tS, sQ, sK(buf));
+      mma_qk(tmem_base, sQ, sK(buf));
       tc_commit(bar_s);
     }
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
-    const int kv_valid = S - j * AT;   // columns >= kv_valid are padding
-    // pass 1: row max
+    const int kv_valid = S - j * AT - half * 64;   // own columns >= kv_valid are padding
+    uint32_t r0[32], r1[32];
+    tmem_ld32(tS, r0);
+    tmem_ld32(tS + 32, r1);
+    tc_wait_ld();
     float mx = -INFINITY;
-#pragma unroll 1
-    for (int c0 = 0; c0 < AT; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tS + lane_off + c0, r);
-      tc_wait_ld();
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (c0 + e < kv_valid) mx = fmaxf(mx, __uint_as_float(r[e]));
+    for (int e = 0; e < 32; ++e) {
+      if (e < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[e]));
+      if (32 + e < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[e]));
     }
+    xch[half * 128 + row] = mx;
+    __syncthreads();
+    mx = fmaxf(xch[row], xch[128 + row]);
     const float m_new = fmaxf(m_run, mx * c);
     const float alpha = exp2f(m_run - m_new);
-    // pass 2: p = exp2(t - m), row sum, bf16 P tile
     float rs = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < AT; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tS + lane_off + c0, r);
-      tc_wait_ld();
+    {
       float p[32];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        p[e] = (c0 + e < kv_valid) ? exp2f(__uint_as_float(r[e]) * c - m_new) : 0.f;
-        rs += p[e];
-      }
-      store_p_chunk(sP, tid, c0, p);
+      for (int e = 0; e < 32; ++e) { p[e] = (e < kv_valid) ? exp2f(__uint_as_float(r0[e]) * c - m_new) : 0.f; rs += p[e]; }
+      store_p_chunk(sP, row, half * 64, p);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) { p[e] = (32 + e < kv_valid) ? exp2f(__uint_as_float(r1[e]) * c - m_new) : 0.f; rs += p[e]; }
+      store_p_chunk(sP, row, half * 64 + 32, p);
     }
     l_run = l_run * alpha + rs;
     m_run = m_new;
@@ -156,28 +156,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_pv(tO, sP, sV(buf), false);
+      mma_pv(tmem_base + 128, sP, sV(buf), false);
       tc_commit(bar_o);
     }
     mbar_wait(bar_o, j & 1);
     tc_fence_after();
+    tmem_ld32(tO, r0);
+    tc_wait_ld();
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tO + lane_off + c0, r);
-      tc_wait_ld();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) o_acc[c0 + e] = o_acc[c0 + e] * alpha + __uint_as_float(r[e]);
-    }
+    for (int e = 0; e < 32; ++e) o_acc[e] = o_acc[e] * alpha + __uint_as_float(r0[e]);
     tc_fence_before();
   }
 
-  const int q = q0 + tid;
+  xch[256 + half * 128 + row] = l_run;
+  __syncthreads();
+  const float l_tot = xch[256 + row] + xch[256 + 128 + row];
+  const int q = q0 + row;
   if (q < S) {
-    const float inv = 1.0f / l_run;
-    __nv_bfloat16* dst = out + (static_cast<size_t>(row0 + q) * H + h) * 64;
+    const float inv = 1.0f / l_tot;
+    __nv_bfloat16* dst = out + (static_cast<size_t>(row0 + q) * H + h) * 64 + half * 32;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < 4; ++g) {
       uint4 o;
       o.x = pack_bf16(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
       o.y = pack_bf16(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
@@ -185,7 +184,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
       o.w = pack_bf16(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
       reinterpret_cast<uint4*>(dst)[g] = o;
     }
-    lse[(static_cast<size_t>(b) * H + h) * S + q] = m_run + log2f(l_run);
+    if (half == 0) lse[(static_cast<size_t>(b) * H + h) * S + q] = m_run + log2f(l_tot);
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -217,7 +216,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
 // =================================================================================================
 constexpr int DQ_SMEM = 8 * TILE_BYTES + 64;   // Q, dO, K0, V0, K1, V1, dS(2)
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, int S, int H,
                    float c, float scale, const float* __restrict__ lse, const float* __restrict__ delta,
                    __nv_bfloat16* __restrict__ dqkv) {
@@ -231,7 +230,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t bar_q = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
   auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   const int q0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * S;
   const int n_kv = (S + AT - 1) / AT;
@@ -247,10 +247,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdQ = tmem_base + 256;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t tS = tmem_base + lane_off + half * 64, tdP = tmem_base + lane_off + 128 + half * 64;
+  const uint32_t tdQ = tmem_base + lane_off + 256 + half * 32;
 
-  const int q = q0 + tid;
+  const int q = q0 + row;
   const bool q_ok = q < S;
   const float my_lse = q_ok ? lse[(static_cast<size_t>(b) * H + h) * S + q] : 0.f;
   const float my_delta = q_ok ? delta[(static_cast<size_t>(b) * H + h) * S + q] : 0.f;
@@ -265,8 +266,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_wait(bar_q, 0);
     mbar_wait(bar_kv(0), 0);
     tc_fence_after();
-    mma_qk(tS, sQ, sK(0));      // S  = Q K^T
-    mma_qk(tdP, sdO, sV(0));    // dP = dO V^T
+    mma_qk(tmem_base, sQ, sK(0));            // S  = Q K^T
+    mma_qk(tmem_base + 128, sdO, sV(0));     // dP = dO V^T
     tc_commit(bar_12);
   }
 
@@ -279,12 +280,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tma_load_2d(sK(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * AT);
       tma_load_2d(sV(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * AT);
     }
-    const int kv_valid = S - j * AT;
+    const int kv_valid = S - j * AT - half * 64;
 #pragma unroll 1
-    for (int c0 = 0; c0 < AT; c0 += 32) {
+    for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t rs[32], rp[32];
-      tmem_ld32(tS + lane_off + c0, rs);
-      tmem_ld32(tdP + lane_off + c0, rp);
+      tmem_ld32(tS + c0, rs);
+      tmem_ld32(tdP + c0, rp);
       tc_wait_ld();
       float ds[32];
 #pragma unroll
@@ -293,19 +294,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         const float p = ok ? exp2f(__uint_as_float(rs[e]) * c - my_lse) : 0.f;
         ds[e] = ok ? p * (__uint_as_float(rp[e]) - my_delta) : 0.f;
       }
-      store_p_chunk(sdS, tid, c0, ds);
+      store_p_chunk(sdS, row, half * 64 + c0, ds);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_pv(tdQ, sdS, sK(buf), j != 0);          // dQ += dS K
+      mma_pv(tmem_base + 256, sdS, sK(buf), j != 0);          // dQ += dS K
       if (j + 1 < n_kv) {
         mbar_wait(bar_kv(buf ^ 1), ((j + 1) >> 1) & 1);
         tc_fence_after();
-        mma_qk(tS, sQ, sK(buf ^ 1));
-        mma_qk(tdP, sdO, sV(buf ^ 1));
+        mma_qk(tmem_base, sQ, sK(buf ^ 1));
+        mma_qk(tmem_base + 128, sdO, sV(buf ^ 1));
         tc_commit(bar_12);
       } else {
         tc_commit(bar_fin);
@@ -314,23 +315,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   mbar_wait(bar_fin, 0);
   tc_fence_after();
-  if (true) {
-    __nv_bfloat16* dst = dqkv + static_cast<size_t>(row0 + q) * (3 * H * 64) + h * 64;
+  {
+    __nv_bfloat16* dst = dqkv + static_cast<size_t>(row0 + q) * (3 * H * 64) + h * 64 + half * 32;
+    uint32_t r[32];
+    tmem_ld32(tdQ, r);
+    tc_wait_ld();
+    if (q_ok) {
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tdQ + lane_off + c0, r);
-      tc_wait_ld();
-      if (q_ok) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(r[g * 8 + 0]) * scale, __uint_as_float(r[g * 8 + 1]) * scale);
-          o.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * scale, __uint_as_float(r[g * 8 + 3]) * scale);
-          o.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * scale, __uint_as_float(r[g * 8 + 5]) * scale);
-          o.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * scale, __uint_as_float(r[g * 8 + 7]) * scale);
-          reinterpret_cast<uint4*>(dst + c0)[g] = o;
-        }
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(r[g * 8 + 0]) * scale, __uint_as_float(r[g * 8 + 1]) * scale);
+        o.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * scale, __uint_as_float(r[g * 8 + 3]) * scale);
+        o.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * scale, __uint_as_float(r[g * 8 + 5]) * scale);
+        o.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * scale, __uint_as_float(r[g * 8 + 7]) * scale);
+        reinterpret_cast<uint4*>(dst)[g] = o;
       }
     }
   }
@@ -344,7 +342,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 // =================================================================================================
 constexpr int DKV_SMEM = 10 * TILE_BYTES + 2048 + 64;   // K, V, Q0, dO0, Q1, dO1, P^T(2), dS^T(2), lse/delta x2
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, int S, int H,
                     float c, float scale, const float* __restrict__ lse, const float* __restrict__ delta,
                     __nv_bfloat16* __restrict__ dqkv) {
@@ -359,7 +357,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   const uint32_t bar_kv = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
   auto bar_q = [&](int b) { return bars + 24 + 8 * b; };
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   const int kv0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * S;
   const int n_q = (S + AT - 1) / AT;
@@ -375,10 +374,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t tS = tmem_base + lane_off + half * 64, tdP = tmem_base + lane_off + 128 + half * 64;
 
-  const int kv = kv0 + tid;
+  const int kv = kv0 + row;
   const bool kv_ok = kv < S;
 
   if (tid == 0) {
@@ -391,18 +390,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     mbar_wait(bar_kv, 0);
     mbar_wait(bar_q(0), 0);
     tc_fence_after();
-    mma_qk(tS, sK, sQ(0));       // S^T  = K Q^T
-    mma_qk(tdP, sV, sdO(0));     // dP^T = V dO^T
+    mma_qk(tmem_base, sK, sQ(0));             // S^T  = K Q^T
+    mma_qk(tmem_base + 128, sV, sdO(0));      // dP^T = V dO^T
     tc_commit(bar_12);
   }
 
   for (int i = 0; i < n_q; ++i) {
     const int buf = i & 1;
-    {   // per-column (q) statistics of this q tile
-      const int qq = i * AT + tid;
-      const bool ok = qq < S;
-      vec[buf * 256 + tid] = ok ? lse[(static_cast<size_t>(b) * H + h) * S + qq] : 0.f;
-      vec[buf * 256 + 128 + tid] = ok ? delta[(static_cast<size_t>(b) * H + h) * S + qq] : 0.f;
+    {   // per-column (q) statistics of this q tile: threads 0-127 fetch lse, 128-255 fetch delta
+      const int qq = i * AT + (tid & 127);
+      const float* src = tid < 128 ? lse : delta;
+      vec[buf * 256 + tid] = qq < S ? src[(static_cast<size_t>(b) * H + h) * S + qq] : 0.f;
     }
     mbar_wait(bar_12, i & 1);    // also covers MMA3/4 of iteration i-1
     tc_fence_after();
@@ -412,37 +410,38 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tma_load_2d(sQ(buf ^ 1), &tm_qkv, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * AT);
       tma_load_2d(sdO(buf ^ 1), &tm_do, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * AT);
     }
-    const int q_valid = S - i * AT;
-    const float* lse_s = vec + buf * 256;
+    const int q_valid = S - i * AT - half * 64;
+    const float* lse_s = vec + buf * 256 + half * 64;
     const float* del_s = lse_s + 128;
 #pragma unroll 1
-    for (int c0 = 0; c0 < AT; c0 += 32) {
+    for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t rs[32], rp[32];
-      tmem_ld32(tS + lane_off + c0, rs);
-      tmem_ld32(tdP + lane_off + c0, rp);
+      tmem_ld32(tS + c0, rs);
+      tmem_ld32(tdP + c0, rp);
       tc_wait_ld();
-      float p[32], ds[32];
+      float p[32];
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
         const bool ok = kv_ok && (c0 + e < q_valid);
         p[e] = ok ? exp2f(__uint_as_float(rs[e]) * c - lse_s[c0 + e]) : 0.f;
-        ds[e] = ok ? p[e] * (__uint_as_float(rp[e]) - del_s[c0 + e]) : 0.f;
       }
-      store_p_chunk(sP, tid, c0, p);
-      store_p_chunk(sdS, tid, c0, ds);
+      store_p_chunk(sP, row, half * 64 + c0, p);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) p[e] = p[e] * (__uint_as_float(rp[e]) - del_s[c0 + e]);
+      store_p_chunk(sdS, row, half * 64 + c0, p);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_pv(tdV, sP, sdO(buf), i != 0);       // dV += P^T dO
-      mma_pv(tdK, sdS, sQ(buf), i != 0);       // dK += dS^T Q
+      mma_pv(tmem_base + 256, sP, sdO(buf), i != 0);       // dV += P^T dO
+      mma_pv(tmem_base + 320, sdS, sQ(buf), i != 0);       // dK += dS^T Q
       if (i + 1 < n_q) {
         mbar_wait(bar_q(buf ^ 1), ((i + 1) >> 1) & 1);
         tc_fence_after();
-        mma_qk(tS, sK, sQ(buf ^ 1));
-        mma_qk(tdP, sV, sdO(buf ^ 1));
+        mma_qk(tmem_base, sK, sQ(buf ^ 1));
+        mma_qk(tmem_base + 128, sV, sdO(buf ^ 1));
         tc_commit(bar_12);
       } else {
         tc_commit(bar_fin);
@@ -451,17 +450,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   }
   mbar_wait(bar_fin, 0);
   tc_fence_after();
-  {
-    __nv_bfloat16* dk = dqkv + static_cast<size_t>(row0 + kv) * (3 * H * 64) + (H + h) * 64;
-    __nv_bfloat16* dv = dqkv + static_cast<size_t>(row0 + kv) * (3 * H * 64) + (2 * H + h) * 64;
+  {   // half 0 writes dV, half 1 writes dK (64 columns each)
+    __nv_bfloat16* dst = dqkv + static_cast<size_t>(row0 + kv) * (3 * H * 64) + ((half == 0 ? 2 * H : H) + h) * 64;
+    const float sc = half == 0 ? 1.0f : scale;
+    const uint32_t tsrc = tmem_base + lane_off + (half == 0 ? 256 : 320);
 #pragma unroll
-    for (int half = 0; half < 4; ++half) {   // 0,1: dV cols 0-31/32-63 ; 2,3: dK
+    for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t r[32];
-      tmem_ld32((half < 2 ? tdV : tdK) + lane_off + (half & 1) * 32, r);
+      tmem_ld32(tsrc + c0, r);
       tc_wait_ld();
       if (kv_ok) {
-        const float sc = half < 2 ? 1.0f : scale;
-        __nv_bfloat16* dst = (half < 2 ? dv : dk) + (half & 1) * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 o;
@@ -469,7 +467,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           o.y = pack_bf16(__uint_as_float(r[g * 8 + 2]) * sc, __uint_as_float(r[g * 8 + 3]) * sc);
           o.z = pack_bf16(__uint_as_float(r[g * 8 + 4]) * sc, __uint_as_float(r[g * 8 + 5]) * sc);
           o.w = pack_bf16(__uint_as_float(r[g * 8 + 6]) * sc, __uint_as_float(r[g * 8 + 7]) * sc);
-          reinterpret_cast<uint4*>(dst)[g] = o;
+          reinterpret_cast<uint4*>(dst + c0)[g] = o;
         }
       }
     }
@@ -499,7 +497,7 @@ int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_b
     attr_set = true;
   }
   dim3 grid((S + AT - 1) / AT, H, B);
-  attn_fwd_kernel<<<grid, 128, FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, S, H, scale * 1.4426950408889634f,
+  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, S, H, scale * 1.4426950408889634f,
                                                                             reinterpret_cast<__nv_bfloat16*>(out), lse);
   MOFO_LAUNCH_CHECK("attn_fwd_kernel");
   return MOFO_OK;
@@ -527,9 +525,9 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
   MOFO_LAUNCH_CHECK("attn_delta_kernel");
   dim3 grid((S + AT - 1) / AT, H, B);
   const float c = scale * 1.4426950408889634f;
-  attn_bwd_dq_kernel<<<grid, 128, DQ_SMEM, s>>>(tq, td, S, H, c, scale, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv));
+  attn_bwd_dq_kernel<<<grid, ATT_THREADS, DQ_SMEM, s>>>(tq, td, S, H, c, scale, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv));
   MOFO_LAUNCH_CHECK("attn_bwd_dq_kernel");
-  attn_bwd_dkv_kernel<<<grid, 128, DKV_SMEM, s>>>(tq, td, S, H, c, scale, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv));
+  attn_bwd_dkv_kernel<<<grid, ATT_THREADS, DKV_SMEM, s>>>(tq, td, S, H, c, scale, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv));
   MOFO_LAUNCH_CHECK("attn_bwd_dkv_kernel");
   return MOFO_OK;
 }

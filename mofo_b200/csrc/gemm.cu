@@ -19,8 +19,10 @@ namespace mofo {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
-constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int EPI_WARPS = 8;                       // warps 0-7: epilogue; warp 8: TMA producer; warp 9: MMA issuer
+constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;
+constexpr int A_TILE_BYTES = BM * BK * 2;          // 16 KB
+constexpr int STAGING_BYTES = EPI_WARPS * 4096;    // per epilogue warp: 32 rows x 128 B
 
 struct EpiParams {
   const float* bias;
@@ -42,75 +44,144 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
-__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
-  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+// ---- per-warp staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7) ---------------------------
+// "own row" access: thread `lane` touches row `lane`;  "cooperative" access: instruction i touches rows 4i..4i+3,
+// 8 lanes per row -> every global instruction covers 4 full 128-byte lines.  Both patterns are bank-conflict free.
+__device__ __forceinline__ uint32_t stg_addr(uint32_t stg, int row, int chunk) {
+  return stg + static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
 }
-__device__ __forceinline__ void store8_f32(float* p, const float (&v)[8]) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
-  uint4 o;
-  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(p) = o;
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
-// One thread owns row `row`, 32 consecutive columns starting at n0 (accumulators in r[]).
-template <int EPI>
-__device__ __forceinline__ void epilogue_store(const EpiParams& ep, int row, int M, int n0, int N, const uint32_t (&r)[32]) {
-  if (row >= M) return;
-  size_t orow = row;
-  const float* posrow = nullptr;
-  if (EPI == MOFO_EPI_BIAS_POS_F32) {
-    orow = static_cast<size_t>(row / ep.group_rows) * ep.out_group_rows + (row % ep.group_rows);
-    posrow = ep.pos + static_cast<size_t>(ep.row_idx[row]) * N;
+// cooperative global -> staging: rows row_base..+31 of a row-major matrix, 128 bytes per row starting where
+// `rowptr(grow)` points (rows >= M and chunks >= valid_chunks are zero filled).
+template <typename RowPtr>
+__device__ __forceinline__ void coop_load(uint32_t stg, int lane, int row_base, int M, int valid_chunks, RowPtr rowptr) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * i + (lane >> 3), chunk = lane & 7;
+    const int grow = row_base + row;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (grow < M && chunk < valid_chunks) v = __ldg(reinterpret_cast<const uint4*>(rowptr(grow)) + chunk);
+    sts128(stg_addr(stg, row, chunk), v);
   }
+}
+template <typename RowPtr>
+__device__ __forceinline__ void coop_store(uint32_t stg, int lane, int row_base, int M, int valid_chunks, RowPtr rowptr) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int n = n0 + g * 8;
-    if (n >= N) break;
-    float v[8];
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * i + (lane >> 3), chunk = lane & 7;
+    const int grow = row_base + row;
+    if (grow < M && chunk < valid_chunks) *(reinterpret_cast<uint4*>(rowptr(grow)) + chunk) = lds128(stg_addr(stg, row, chunk));
+  }
+}
+
+// One warp, one chunk of 128 output bytes per row (64 bf16 or 32 f32 columns) starting at column n0.
+// `taddr` already points at this warp's TMEM lanes and the chunk's first accumulator column.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, uint32_t stg, int lane, int row_base, int M, int n0,
+                                               int N, uint32_t taddr) {
+  constexpr bool F32_OUT = (EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32);
+  constexpr int COLS = F32_OUT ? 32 : 64;
+  constexpr bool HAS_BIAS = (EPI == MOFO_EPI_BIAS_BF16 || EPI == MOFO_EPI_BIAS_GELU_BF16 ||
+                             EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32);
+  const int rem = N - n0;                                   // > 0
+  const int valid_chunks = rem >= COLS ? 8 : (F32_OUT ? rem / 4 : rem / 8);
+  float v[COLS];
+  {
+    uint32_t r[32];
+    tmem_ld32(taddr, r);
+    tc_wait_ld();
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[g * 8 + e]);
-    if (EPI == MOFO_EPI_BIAS_BF16 || EPI == MOFO_EPI_BIAS_GELU_BF16 || EPI == MOFO_EPI_BIAS_RESID_F32 ||
-        EPI == MOFO_EPI_BIAS_POS_F32) {
-      if (ep.bias) {
-        float b[8];
-        load8(ep.bias + n, b);
+    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+    if (COLS == 64) {
+      tmem_ld32(taddr + 32, r);
+      tc_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += b[e];
+      for (int e = 0; e < 32; ++e) v[(COLS == 64 ? 32 : 0) + e] = __uint_as_float(r[e]);
+    }
+  }
+  if (HAS_BIAS && ep.bias) {
+#pragma unroll
+    for (int c = 0; c < COLS / 4; ++c) {
+      if (n0 + c * 4 < N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + c);
+        v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
       }
     }
-    if (EPI == MOFO_EPI_BIAS_BF16 || EPI == MOFO_EPI_PLAIN_BF16) {
-      store8_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out0) + orow * ep.ldo0 + n, v);
-    } else if (EPI == MOFO_EPI_BIAS_GELU_BF16) {
-      // the pre-activation is rounded to bf16 first (it is what F.linear returns under autocast), GELU acts on that
-      float u[8];
+  }
+  auto out_row = [&](int grow) -> size_t {
+    return EPI == MOFO_EPI_BIAS_POS_F32
+               ? static_cast<size_t>(grow / ep.group_rows) * ep.out_group_rows + (grow % ep.group_rows)
+               : static_cast<size_t>(grow);
+  };
+  if (F32_OUT) {
+    // additive f32 operand (residual stream or gathered position row), staged for coalesced access
+    if (EPI == MOFO_EPI_BIAS_RESID_F32)
+      coop_load(stg, lane, row_base, M, valid_chunks, [&](int g) { return ep.resid + static_cast<size_t>(g) * ep.ldr + n0; });
+    else
+      coop_load(stg, lane, row_base, M, valid_chunks, [&](int g) { return ep.pos + static_cast<size_t>(ep.row_idx[g]) * N + n0; });
+    __syncwarp();
 #pragma unroll
-      for (int e = 0; e < 8; ++e) u[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
-      store8_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out0) + orow * ep.ldo0 + n, u);
+    for (int c = 0; c < 8; ++c) {
+      const uint4 q = lds128(stg_addr(stg, lane, c));
+      v[c * 4 + 0] += __uint_as_float(q.x); v[c * 4 + 1] += __uint_as_float(q.y);
+      v[c * 4 + 2] += __uint_as_float(q.z); v[c * 4 + 3] += __uint_as_float(q.w);
+    }
+    __syncwarp();
 #pragma unroll
-      for (int e = 0; e < 8; ++e) u[e] = gelu_erf(u[e]);
-      store8_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out1) + orow * ep.ldo1 + n, u);
-    } else if (EPI == MOFO_EPI_BIAS_RESID_F32) {
-      float q[8];
-      load8(ep.resid + orow * ep.ldr + n, q);
+    for (int c = 0; c < 8; ++c)
+      sts128(stg_addr(stg, lane, c), make_uint4(__float_as_uint(v[c * 4]), __float_as_uint(v[c * 4 + 1]),
+                                                 __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3])));
+    __syncwarp();
+    coop_store(stg, lane, row_base, M, valid_chunks,
+               [&](int g) { return reinterpret_cast<float*>(ep.out0) + out_row(g) * ep.ldo0 + n0; });
+    __syncwarp();
+  } else {
+    if (EPI == MOFO_EPI_GELU_BWD_BF16) {
+      coop_load(stg, lane, row_base, M, valid_chunks, [&](int g) { return ep.aux + static_cast<size_t>(g) * ep.ldaux + n0; });
+      __syncwarp();
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] += q[e];
-      store8_f32(reinterpret_cast<float*>(ep.out0) + orow * ep.ldo0 + n, v);
-    } else if (EPI == MOFO_EPI_GELU_BWD_BF16) {
-      uint4 a = __ldg(reinterpret_cast<const uint4*>(ep.aux + orow * ep.ldaux + n));
-      float u[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y), bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
+      for (int c = 0; c < 8; ++c) {
+        const uint4 a = lds128(stg_addr(stg, lane, c));
+        v[c * 8 + 0] *= gelu_erf_grad(bf16_lo(a.x)); v[c * 8 + 1] *= gelu_erf_grad(bf16_hi(a.x));
+        v[c * 8 + 2] *= gelu_erf_grad(bf16_lo(a.y)); v[c * 8 + 3] *= gelu_erf_grad(bf16_hi(a.y));
+        v[c * 8 + 4] *= gelu_erf_grad(bf16_lo(a.z)); v[c * 8 + 5] *= gelu_erf_grad(bf16_hi(a.z));
+        v[c * 8 + 6] *= gelu_erf_grad(bf16_lo(a.w)); v[c * 8 + 7] *= gelu_erf_grad(bf16_hi(a.w));
+      }
+      __syncwarp();
+    }
+    if (EPI == MOFO_EPI_BIAS_GELU_BF16) {
+      // the pre-activation is rounded to bf16 first (what F.linear returns under autocast); GELU acts on that
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] *= gelu_erf_grad(u[e]);
-      store8_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out0) + orow * ep.ldo0 + n, v);
-    } else if (EPI == MOFO_EPI_BIAS_POS_F32) {
-      float q[8];
-      load8(posrow + n, q);
+      for (int e = 0; e < COLS; ++e) v[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+    }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] += q[e];
-      store8_f32(reinterpret_cast<float*>(ep.out0) + orow * ep.ldo0 + n, v);
+    for (int c = 0; c < 8; ++c)
+      sts128(stg_addr(stg, lane, c), make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
+                                                 pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16(v[c * 8 + 6], v[c * 8 + 7])));
+    __syncwarp();
+    coop_store(stg, lane, row_base, M, valid_chunks,
+               [&](int g) { return reinterpret_cast<__nv_bfloat16*>(ep.out0) + static_cast<size_t>(g) * ep.ldo0 + n0; });
+    __syncwarp();
+    if (EPI == MOFO_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float u[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) u[e] = gelu_erf(v[c * 8 + e]);
+        sts128(stg_addr(stg, lane, c), make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7])));
+      }
+      __syncwarp();
+      coop_store(stg, lane, row_base, M, valid_chunks,
+                 [&](int g) { return reinterpret_cast<__nv_bfloat16*>(ep.out1) + static_cast<size_t>(g) * ep.ldo1 + n0; });
+      __syncwarp();
     }
   }
 }
@@ -119,9 +190,9 @@ template <int BN>
 struct TnCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = BN == 128 ? 6 : (BN == 192 ? 5 : 4);
+  static constexpr int STAGES = BN == 128 ? 6 : 4;
   static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BN, int EPI>
@@ -132,7 +203,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t stg_base = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stg_base + STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
@@ -148,18 +220,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
-  if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == EPI_WARPS && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == EPI_WARPS + 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     if (lane == 0) {  // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
@@ -174,7 +246,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     if (lane == 0) {  // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
       int stage = 0, acc = 0;
@@ -200,21 +272,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {  // ===== epilogue warps 0..3 (TMEM lanes 32*warp .. +31) =====
+  } else {  // ===== epilogue warps: quarter = TMEM lane group, grp = which chunks of the tile =====
+    constexpr bool F32_OUT = (EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32);
+    constexpr int COLS = F32_OUT ? 32 : 64;
+    const int quarter = warp & 3, grp = warp >> 2;
+    const uint32_t stg = stg_base + warp * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + warp * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * BN;
+      const int row_base = m_blk * BM + quarter * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        tc_wait_ld();
-        epilogue_store<EPI>(ep, row, M, n_blk * BN + c0, N, r);
+      for (int ch = grp; ch < BN / COLS; ch += 2) {
+        const int n0 = n_blk * BN + ch * COLS;
+        if (n0 >= N) break;
+        epilogue_chunk<EPI>(ep, stg, lane, row_base, M, n0, N, taddr + ch * COLS);
       }
       tc_fence_before();
       __syncwarp();
@@ -225,7 +300,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == EPI_WARPS + 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -236,9 +311,9 @@ struct WgCfg {
   static constexpr int A_BYTES = 2 * 64 * 128;            // two 64-wide n panels x 64 m rows
   static constexpr int B_BYTES = (BNW / 64) * 64 * 128;   // BNW/64 panels
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BNW == 256 ? 4 : (BNW == 192 ? 5 : 6);
+  static constexpr int STAGES = BNW == 128 ? 6 : 4;
   static constexpr int TMEM_COLS = BNW == 128 ? 128 : 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
 template <int BNW>
@@ -249,7 +324,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t stg_base = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stg_base + STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
@@ -270,15 +346,15 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmX); }
-  if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == EPI_WARPS && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmX); }
+  if (warp == EPI_WARPS + 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -293,7 +369,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);
       int stage = 0;
@@ -313,26 +389,39 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       tc_commit(tfull_bar);
     }
   } else {
+    // epilogue: TMEM -> staging tile -> row-coalesced fp32 red.add (one 128-byte line per warp instruction)
+    const int quarter = warp & 3, grp = warp >> 2;
+    const uint32_t stg = stg_base + warp * 4096;
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
-    const int n = n_blk * 128 + warp * 32 + lane;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int n_base = n_blk * 128 + quarter * 32;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BNW; c0 += 32) {
+    for (int ch = grp; ch < BNW / 32; ch += 2) {
+      const int k0 = k_blk * BNW + ch * 32;
+      if (k0 >= K) break;
       uint32_t r[32];
-      tmem_ld32(taddr + c0, r);
+      tmem_ld32(taddr + ch * 32, r);
       tc_wait_ld();
-      if (n < N) {
-        float* dst = dW + static_cast<size_t>(n) * ldw + k_blk * BNW + c0;
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (k_blk * BNW + c0 + e < K) atomicAdd(dst + e, __uint_as_float(r[e]));
+      for (int c = 0; c < 8; ++c) sts128(stg_addr(stg, lane, c), make_uint4(r[c * 4], r[c * 4 + 1], r[c * 4 + 2], r[c * 4 + 3]));
+      __syncwarp();
+      if (k0 + lane < K) {
+#pragma unroll 8
+        for (int row = 0; row < 32; ++row) {
+          const int n = n_base + row;
+          if (n >= N) break;
+          float val;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(stg_addr(stg, row, lane >> 2) + (lane & 3) * 4) : "memory");
+          atomicAdd(dW + static_cast<size_t>(n) * ldw + k0 + lane, val);
+        }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == EPI_WARPS + 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------

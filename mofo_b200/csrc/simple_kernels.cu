@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 
 // warp per row, grid-stride over rows; per-lane register partials of dgamma/dbeta, reduced through shared
 // memory per CTA and accumulated with one atomicAdd per column per CTA.
+template <int NCH>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres, int M, int D,
@@ -236,19 +237,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
   extern __shared__ float red[];  // [warps][2*D]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int nch = D >> 2;
-  float4 dg[LN_MAX_CHUNKS], db[LN_MAX_CHUNKS];
+  float4 dg[NCH], db[NCH];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_CHUNKS; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < NCH; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
 
   for (int m = blockIdx.x * warps + wid; m < M; m += gridDim.x * warps) {
     const size_t xrow = map_row(m, group_rows, in_group_rows, in_row_offset);
     const float4* xr = reinterpret_cast<const float4*>(x + xrow * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(m) * D);
     const float mu = mean[m], rs = rstd[m];
-    float4 xh[LN_MAX_CHUNKS], g[LN_MAX_CHUNKS];
+    float4 xh[NCH], g[NCH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       int ch = lane + i * 32;
       if (ch < nch) {
         float4 xv = xr[ch];
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     s1 = warp_sum(s1) / D;
     s2 = warp_sum(s2) / D;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       int ch = lane + i * 32;
       if (ch < nch) {
         float4 o = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
   // CTA reduction of the parameter-gradient partials
   float* mine = red + static_cast<size_t>(wid) * 2 * D;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     int ch = lane + i * 32;
     if (ch < nch) {
       reinterpret_cast<float4*>(mine)[ch] = dg[i];
@@ -478,7 +479,7 @@ __global__ void pack_qkv_bias_kernel(const float* __restrict__ qb, const float* 
   if (i < 3 * D) out[i] = i < D ? qb[i] : (i < 2 * D ? 0.f : vb[i - 2 * D]);
 }
 
-// grid (ceil(N/256), row chunks); 256 threads = 8 warps; lane owns 8 consecutive columns.
+// grid (ceil(N/256), row chunks); 256 threads = 8 warps; lane owns 8 consecutive columns; 4 row loads in flight.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int M, int N,
                                                           int rows_per_cta, float* __restrict__ out) {
   __shared__ float red[8][256];
@@ -487,10 +488,18 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < N) {
-    for (int r = r0 + wid; r < r1; r += 8) {
-      uint4 v = __ldg(reinterpret_cast<const uint4*>(X + static_cast<size_t>(r) * ldx + col));
-      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
-      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    for (int r = r0 + wid; r < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + 8 * u;
+        v[u] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(X + static_cast<size_t>(rr) * ldx + col)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x); acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
+        acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z); acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
+      }
     }
   }
 #pragma unroll
@@ -498,10 +507,10 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   __syncthreads();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c < N) {
-    float s = 0.f;
+    float s2 = 0.f;
 #pragma unroll
-    for (int w2 = 0; w2 < 8; ++w2) s += red[w2][threadIdx.x];
-    atomicAdd(out + c, s);
+    for (int w2 = 0; w2 < 8; ++w2) s2 += red[w2][threadIdx.x];
+    atomicAdd(out + c, s2);
   }
 }
 
@@ -601,13 +610,25 @@ int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, 
   MOFO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_CHUNKS && group_rows > 0, "layernorm_bwd: unsupported M=%d D=%d", M, D);
   const int warps = 8;
   int grid = (M + warps - 1) / warps;
-  int cap = sm_count() * 4;
+  int cap = sm_count() * (D <= 512 ? 4 : 2);
   if (grid > cap) grid = cap;
   size_t smem = static_cast<size_t>(warps) * 2 * D * sizeof(float);
-  if (smem > 48 * 1024) MOFO_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  layernorm_bwd_kernel<<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, M, D, group_rows, in_group_rows, in_row_offset,
-      dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta);
+  const int nch = (D + 127) / 128;
+#define MOFO_LN_BWD(NCH)                                                                                               \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024)                                                                                              \
+      MOFO_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    layernorm_bwd_kernel<NCH><<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(                          \
+        reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, M, D, group_rows, in_group_rows,       \
+        in_row_offset, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta);                              \
+  } while (0)
+  if (nch <= 1) MOFO_LN_BWD(1);
+  else if (nch == 2) MOFO_LN_BWD(2);
+  else if (nch == 3) MOFO_LN_BWD(3);
+  else if (nch == 4) MOFO_LN_BWD(4);
+  else if (nch <= 6) MOFO_LN_BWD(6);
+  else MOFO_LN_BWD(8);
+#undef MOFO_LN_BWD
   MOFO_LAUNCH_CHECK("layernorm_bwd_kernel");
   return MOFO_OK;
 }
@@ -670,7 +691,7 @@ int mofo_pack_qkv_bias(const float* q_bias, const float* v_bias, int D, float* o
 
 int mofo_colsum_bf16(const mofo_bf16* X, int ldx, int M, int N, float* out, void* stream) {
   MOFO_CHECK_ARG(X && out && M > 0 && N > 0 && N % 8 == 0 && ldx % 8 == 0, "colsum_bf16: bad argument (N, ldx must be multiples of 8)");
-  int rows_per_cta = 512;
+  int rows_per_cta = 128;
   dim3 grid((N + 255) / 256, (M + rows_per_cta - 1) / rows_per_cta);
   colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(X), ldx, M, N, rows_per_cta, out);
   MOFO_LAUNCH_CHECK("colsum_bf16_kernel");
