@@ -13,9 +13,11 @@
 
 namespace mofo {
 
-constexpr int AT = 128;                       // tile rows (q or kv)
+constexpr int AT = 128;                       // rows per CTA tile (q rows in fwd/dq, kv rows in dkv)
+constexpr int BT = 64;                        // inner (streamed) tile: kv rows in fwd/dq, q rows in dkv
 constexpr int TILE_BYTES = AT * 64 * 2;       // 16 KB: [128 x 64] bf16
-constexpr int PTILE_BYTES = 2 * TILE_BYTES;   // 32 KB: [128 x 128] bf16 as two 64-wide K panels
+constexpr int HTILE_BYTES = BT * 64 * 2;      //  8 KB: [ 64 x 64] bf16
+constexpr int ATT_THREADS = 256;              // 2 threads per tile row: each owns 32 of the 64 inner columns
 
 __device__ __forceinline__ void check_align(uint32_t base) {
   if (base & 1023u) {
@@ -24,13 +26,12 @@ __device__ __forceinline__ void check_align(uint32_t base) {
   }
 }
 
-// write 32 consecutive columns [c0, c0+32) of row `row` of a [128 x 128] bf16 K-major SW128 tile pair
+// write 32 consecutive columns [c0, c0+32) (c0 = 0 or 32) of row `row` of a [128 x 64] bf16 K-major SW128 tile
 __device__ __forceinline__ void store_p_chunk(uint32_t tile_base, int row, int c0, const float (&v)[32]) {
-  const uint32_t panel = tile_base + (c0 >> 6) * TILE_BYTES;
-  const int chunk0 = (c0 & 63) >> 3;
+  const int chunk0 = c0 >> 3;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const uint32_t addr = panel + sw128_offset(row, chunk0 + g);
+    const uint32_t addr = tile_base + sw128_offset(row, chunk0 + g);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(v[g * 8 + 0], v[g * 8 + 1])),
                  "r"(pack_bf16(v[g * 8 + 2], v[g * 8 + 3])), "r"(pack_bf16(v[g * 8 + 4], v[g * 8 + 5])),
                  "r"(pack_bf16(v[g * 8 + 6], v[g * 8 + 7]))
@@ -38,39 +39,39 @@ __device__ __forceinline__ void store_p_chunk(uint32_t tile_base, int row, int c
   }
 }
 
-// issue the 4 K-steps of a [128 x 64] · [128 x 64]^T product (both K-major) into d_tmem (N = 128)
-__device__ __forceinline__ void mma_qk(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
-  constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+// D[128 x 64] = A[128 x 64] · B[64 x 64]^T, both K-major SW128 tiles straight from TMA (4 K-steps of 16)
+__device__ __forceinline__ void mma_ab_t(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+  const uint64_t a0 = umma_desc_kmajor(a_tile), b0 = umma_desc_kmajor(b_tile);
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    umma_bf16(d_tmem, umma_desc_kmajor(a_tile + k * 32), umma_desc_kmajor(b_tile + k * 32), idesc, k != 0);
+  for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k != 0);
 }
-// D[128 x 64] (+)= P[128 x 128] (K-major pair) · T[128 x 64] (MN-major: rows = reduction index)
-__device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t p_tile, uint32_t t_tile, bool accumulate) {
+// D[128 x 64] (+)= P[128 x 64] (K-major, written by the threads) · T[64 x 64] (MN-major: rows = reduction index)
+__device__ __forceinline__ void mma_p_t(uint32_t d_tmem, uint32_t p_tile, uint32_t t_tile, bool accumulate) {
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+  const uint64_t a0 = umma_desc_kmajor(p_tile), b0 = umma_desc_mnmajor(t_tile, 8192);
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    umma_bf16(d_tmem, umma_desc_kmajor(p_tile + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-              umma_desc_mnmajor(t_tile + k * 2048, 8192), idesc, (accumulate || k != 0) ? 1u : 0u);
+  for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 128 * k, idesc, (accumulate || k != 0) ? 1u : 0u);
 }
 
 // =================================================================================================
-// forward
+// forward: CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles (double buffered).
+// TMEM: S [0,64) | O_part [64,128).  smem 64.6 KB -> up to 3 CTAs / SM.
 // =================================================================================================
-constexpr int FWD_SMEM = 7 * TILE_BYTES + 2048 + 64;   // Q, K0, V0, K1, V1, P(2), max/sum exchange, barriers
-constexpr int ATT_THREADS = 256;                       // 2 threads per tile row: each owns half of the columns
+constexpr int FWD_SMEM = TILE_BYTES + 4 * HTILE_BYTES + TILE_BYTES + 512 + 64;   // Q, K0,V0,K1,V1, P, max xchg, barriers
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float c /*scale*log2e*/,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+__global__ void __launch_bounds__(ATT_THREADS, 3)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int S, int H,
+                float c /*scale*log2e*/, __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   check_align(base);
-  const uint32_t sQ = base, sP = base + 5 * TILE_BYTES;
-  auto sK = [&](int b) { return base + (1 + 2 * b) * TILE_BYTES; };
-  auto sV = [&](int b) { return base + (2 + 2 * b) * TILE_BYTES; };
-  float* xch = reinterpret_cast<float*>(smem_raw + 7 * TILE_BYTES);   // [2][128] max, [2][128] sum
-  const uint32_t bars = base + 7 * TILE_BYTES + 2048;
+  const uint32_t sQ = base, sP = base + TILE_BYTES + 4 * HTILE_BYTES;
+  auto sK = [&](int b) { return base + TILE_BYTES + (2 * b) * HTILE_BYTES; };
+  auto sV = [&](int b) { return base + TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
+  __nv_bfloat16* xch = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * TILE_BYTES + 4 * HTILE_BYTES);   // [2][128]
+  float* xsum = reinterpret_cast<float*>(smem_raw + TILE_BYTES);                                        // aliases K/V at the end
+  const uint32_t bars = base + 2 * TILE_BYTES + 4 * HTILE_BYTES + 512;
   const uint32_t bar_q = bars, bar_s = bars + 8, bar_o = bars + 16, tmem_slot = bars + 40;
   auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
 
@@ -78,28 +79,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   const int q0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * S;
-  const int n_kv = (S + AT - 1) / AT;
+  const int n_kv = (S + BT - 1) / BT;
 
   if (tid == 0) {
     mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_kv(0), 1); mbar_init(bar_kv(1), 1);
     fence_barrier_init();
-    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const uint32_t tS = tmem_base + lane_off + half * 64, tO = tmem_base + lane_off + 128 + half * 32;
+  const uint32_t tS = tmem_base + lane_off + half * 32, tO = tmem_base + lane_off + 64 + half * 32;
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, TILE_BYTES);
-    tma_load_2d(sQ, &tm_qkv, bar_q, h * 64, row0 + q0);
-    mbar_expect_tx(bar_kv(0), 2 * TILE_BYTES);
-    tma_load_2d(sK(0), &tm_qkv, bar_kv(0), (H + h) * 64, row0);
-    tma_load_2d(sV(0), &tm_qkv, bar_kv(0), (2 * H + h) * 64, row0);
+    tma_load_2d(sQ, &tm_q, bar_q, h * 64, row0 + q0);
+    mbar_expect_tx(bar_kv(0), 2 * HTILE_BYTES);
+    tma_load_2d(sK(0), &tm_kv, bar_kv(0), (H + h) * 64, row0);
+    tma_load_2d(sV(0), &tm_kv, bar_kv(0), (2 * H + h) * 64, row0);
   }
 
   float o_acc[32];
@@ -111,44 +112,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
     const int buf = j & 1;
     if (tid == 0) {
       if (j + 1 < n_kv) {   // prefetch next K/V tile (its buffer was released by bar_o of iteration j-1)
-        mbar_expect_tx(bar_kv(buf ^ 1), 2 * TILE_BYTES);
-        tma_load_2d(sK(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * AT);
-        tma_load_2d(sV(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * AT);
+        mbar_expect_tx(bar_kv(buf ^ 1), 2 * HTILE_BYTES);
+        tma_load_2d(sK(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * BT);
+        tma_load_2d(sV(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * BT);
       }
       if (j == 0) mbar_wait(bar_q, 0);
       mbar_wait(bar_kv(buf), (j >> 1) & 1);
       tc_fence_after();
-      mma_qk(tmem_base, sQ, sK(buf));
+      mma_ab_t(tmem_base, sQ, sK(buf));
       tc_commit(bar_s);
     }
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
-    const int kv_valid = S - j * AT - half * 64;   // own columns >= kv_valid are padding
-    uint32_t r0[32], r1[32];
-    tmem_ld32(tS, r0);
-    tmem_ld32(tS + 32, r1);
+    const int kv_valid = S - j * BT - half * 32;   // own columns >= kv_valid are padding (last tile only)
+    uint32_t r[32];
+    tmem_ld32(tS, r);
     tc_wait_ld();
     float mx = -INFINITY;
+    if (kv_valid >= 32) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      if (e < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[e]));
-      if (32 + e < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[e]));
+      for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) if (e < kv_valid) mx = fmaxf(mx, __uint_as_float(r[e]));
     }
-    xch[half * 128 + row] = mx;
+    // exchange the two half-row maxima rounded UP to bf16: both threads of a row then use the identical reference
+    // value (any upper bound of the true maximum keeps exp2 <= 1; the lse below stays exact).
+    xch[half * 128 + row] = __float2bfloat16_ru(mx);
     __syncthreads();
-    mx = fmaxf(xch[row], xch[128 + row]);
+    mx = fmaxf(__bfloat162float(xch[row]), __bfloat162float(xch[128 + row]));
     const float m_new = fmaxf(m_run, mx * c);
     const float alpha = exp2f(m_run - m_new);
     float rs = 0.f;
-    {
-      float p[32];
+    float p[32];
+    if (kv_valid >= 32) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) { p[e] = (e < kv_valid) ? exp2f(__uint_as_float(r0[e]) * c - m_new) : 0.f; rs += p[e]; }
-      store_p_chunk(sP, row, half * 64, p);
+      for (int e = 0; e < 32; ++e) { p[e] = exp2f(__uint_as_float(r[e]) * c - m_new); rs += p[e]; }
+    } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) { p[e] = (32 + e < kv_valid) ? exp2f(__uint_as_float(r1[e]) * c - m_new) : 0.f; rs += p[e]; }
-      store_p_chunk(sP, row, half * 64 + 32, p);
+      for (int e = 0; e < 32; ++e) { p[e] = (e < kv_valid) ? exp2f(__uint_as_float(r[e]) * c - m_new) : 0.f; rs += p[e]; }
     }
+    store_p_chunk(sP, row, half * 32, p);
     l_run = l_run * alpha + rs;
     m_run = m_new;
     fence_proxy_async_smem();
@@ -156,21 +160,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_pv(tmem_base + 128, sP, sV(buf), false);
+      mma_p_t(tmem_base + 64, sP, sV(buf), false);
       tc_commit(bar_o);
     }
     mbar_wait(bar_o, j & 1);
     tc_fence_after();
-    tmem_ld32(tO, r0);
+    tmem_ld32(tO, r);
     tc_wait_ld();
 #pragma unroll
-    for (int e = 0; e < 32; ++e) o_acc[e] = o_acc[e] * alpha + __uint_as_float(r0[e]);
+    for (int e = 0; e < 32; ++e) o_acc[e] = o_acc[e] * alpha + __uint_as_float(r[e]);
     tc_fence_before();
   }
 
-  xch[256 + half * 128 + row] = l_run;
+  __syncthreads();                      // every MMA has completed (bar_o of the last iteration): K/V smem is free
+  xsum[half * 128 + row] = l_run;
   __syncthreads();
-  const float l_tot = xch[256 + row] + xch[256 + 128 + row];
+  const float l_tot = xsum[row] + xsum[128 + row];
   const int q = q0 + row;
   if (q < S) {
     const float inv = 1.0f / l_tot;
@@ -187,7 +192,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, int S, int H, float 
     if (half == 0) lse[(static_cast<size_t>(b) * H + h) * S + q] = m_run + log2f(l_tot);
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 // =================================================================================================
@@ -212,21 +217,24 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
 }
 
 // =================================================================================================
-// backward, part 1: dQ   (CTA per (q tile, head, clip); loops over kv tiles)
+// backward, part 1: dQ.  CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles.
+// TMEM: S [0,64) | dP [64,128) | dQ [128,192) (256 allocated) -> 2 CTAs / SM.  smem 80 KB.
+// Rows q >= S and kv >= S: garbage rows only pollute their own (never stored) output rows, so only the
+// reduction (column) index is masked, and only in the last tile.
 // =================================================================================================
-constexpr int DQ_SMEM = 8 * TILE_BYTES + 64;   // Q, dO, K0, V0, K1, V1, dS(2)
+constexpr int DQ_SMEM = 2 * TILE_BYTES + 4 * HTILE_BYTES + TILE_BYTES + 64;   // Q, dO, K0,V0,K1,V1, dS
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, int S, int H,
-                   float c, float scale, const float* __restrict__ lse, const float* __restrict__ delta,
-                   __nv_bfloat16* __restrict__ dqkv) {
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                   const __grid_constant__ CUtensorMap tm_do, int S, int H, float c, float scale,
+                   const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   check_align(base);
-  const uint32_t sQ = base, sdO = base + TILE_BYTES, sdS = base + 6 * TILE_BYTES;
-  auto sK = [&](int b) { return base + (2 + 2 * b) * TILE_BYTES; };
-  auto sV = [&](int b) { return base + (3 + 2 * b) * TILE_BYTES; };
-  const uint32_t bars = base + 8 * TILE_BYTES;
+  const uint32_t sQ = base, sdO = base + TILE_BYTES, sdS = base + 2 * TILE_BYTES + 4 * HTILE_BYTES;
+  auto sK = [&](int b) { return base + 2 * TILE_BYTES + (2 * b) * HTILE_BYTES; };
+  auto sV = [&](int b) { return base + 2 * TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
+  const uint32_t bars = base + 3 * TILE_BYTES + 4 * HTILE_BYTES;
   const uint32_t bar_q = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
   auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
 
@@ -234,22 +242,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   const int q0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * S;
-  const int n_kv = (S + AT - 1) / AT;
+  const int n_kv = (S + BT - 1) / BT;
 
   if (tid == 0) {
     mbar_init(bar_q, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1); mbar_init(bar_kv(0), 1); mbar_init(bar_kv(1), 1);
     fence_barrier_init();
-    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do);
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const uint32_t tS = tmem_base + lane_off + half * 64, tdP = tmem_base + lane_off + 128 + half * 64;
-  const uint32_t tdQ = tmem_base + lane_off + 256 + half * 32;
+  const uint32_t tS = tmem_base + lane_off + half * 32, tdP = tmem_base + lane_off + 64 + half * 32;
+  const uint32_t tdQ = tmem_base + lane_off + 128 + half * 32;
 
   const int q = q0 + row;
   const bool q_ok = q < S;
@@ -258,55 +266,55 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, 2 * TILE_BYTES);
-    tma_load_2d(sQ, &tm_qkv, bar_q, h * 64, row0 + q0);
+    tma_load_2d(sQ, &tm_q, bar_q, h * 64, row0 + q0);
     tma_load_2d(sdO, &tm_do, bar_q, h * 64, row0 + q0);
-    mbar_expect_tx(bar_kv(0), 2 * TILE_BYTES);
-    tma_load_2d(sK(0), &tm_qkv, bar_kv(0), (H + h) * 64, row0);
-    tma_load_2d(sV(0), &tm_qkv, bar_kv(0), (2 * H + h) * 64, row0);
+    mbar_expect_tx(bar_kv(0), 2 * HTILE_BYTES);
+    tma_load_2d(sK(0), &tm_kv, bar_kv(0), (H + h) * 64, row0);
+    tma_load_2d(sV(0), &tm_kv, bar_kv(0), (2 * H + h) * 64, row0);
     mbar_wait(bar_q, 0);
     mbar_wait(bar_kv(0), 0);
     tc_fence_after();
-    mma_qk(tmem_base, sQ, sK(0));            // S  = Q K^T
-    mma_qk(tmem_base + 128, sdO, sV(0));     // dP = dO V^T
+    mma_ab_t(tmem_base, sQ, sK(0));            // S  = Q K^T
+    mma_ab_t(tmem_base + 64, sdO, sV(0));      // dP = dO V^T
     tc_commit(bar_12);
   }
 
   for (int j = 0; j < n_kv; ++j) {
     const int buf = j & 1;
-    mbar_wait(bar_12, j & 1);   // also covers MMA3 of iteration j-1 (tensor pipe is in-order)
+    mbar_wait(bar_12, j & 1);   // also covers the dQ MMA of iteration j-1 (tensor pipe is in-order)
     tc_fence_after();
     if (tid == 0 && j + 1 < n_kv) {
-      mbar_expect_tx(bar_kv(buf ^ 1), 2 * TILE_BYTES);
-      tma_load_2d(sK(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * AT);
-      tma_load_2d(sV(buf ^ 1), &tm_qkv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * AT);
+      mbar_expect_tx(bar_kv(buf ^ 1), 2 * HTILE_BYTES);
+      tma_load_2d(sK(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * BT);
+      tma_load_2d(sV(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * BT);
     }
-    const int kv_valid = S - j * AT - half * 64;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tS + c0, rs);
-      tmem_ld32(tdP + c0, rp);
-      tc_wait_ld();
-      float ds[32];
+    const int kv_valid = S - j * BT - half * 32;
+    uint32_t rs[32], rp[32];
+    tmem_ld32(tS, rs);
+    tmem_ld32(tdP, rp);
+    tc_wait_ld();
+    float ds[32];
+    if (kv_valid >= 32) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const bool ok = q_ok && (c0 + e < kv_valid);
-        const float p = ok ? exp2f(__uint_as_float(rs[e]) * c - my_lse) : 0.f;
-        ds[e] = ok ? p * (__uint_as_float(rp[e]) - my_delta) : 0.f;
-      }
-      store_p_chunk(sdS, row, half * 64 + c0, ds);
+      for (int e = 0; e < 32; ++e)
+        ds[e] = exp2f(__uint_as_float(rs[e]) * c - my_lse) * (__uint_as_float(rp[e]) - my_delta);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        ds[e] = (e < kv_valid) ? exp2f(__uint_as_float(rs[e]) * c - my_lse) * (__uint_as_float(rp[e]) - my_delta) : 0.f;
     }
+    store_p_chunk(sdS, row, half * 32, ds);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_pv(tmem_base + 256, sdS, sK(buf), j != 0);          // dQ += dS K
+      mma_p_t(tmem_base + 128, sdS, sK(buf), j != 0);          // dQ += dS K
       if (j + 1 < n_kv) {
         mbar_wait(bar_kv(buf ^ 1), ((j + 1) >> 1) & 1);
         tc_fence_after();
-        mma_qk(tmem_base, sQ, sK(buf ^ 1));
-        mma_qk(tmem_base + 128, sdO, sV(buf ^ 1));
+        mma_ab_t(tmem_base, sQ, sK(buf ^ 1));
+        mma_ab_t(tmem_base + 64, sdO, sV(buf ^ 1));
         tc_commit(bar_12);
       } else {
         tc_commit(bar_fin);
@@ -334,26 +342,28 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // =================================================================================================
-// backward, part 2: dK, dV   (CTA per (kv tile, head, clip); loops over q tiles)
+// backward, part 2: dK, dV.  CTA = 128 kv rows of one (clip, head); streams 64-row Q/dO tiles.
+// TMEM: S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256) -> 2 CTAs / SM.  smem 97 KB.
 // =================================================================================================
-constexpr int DKV_SMEM = 10 * TILE_BYTES + 2048 + 64;   // K, V, Q0, dO0, Q1, dO1, P^T(2), dS^T(2), lse/delta x2
+constexpr int DKV_SMEM = 2 * TILE_BYTES + 4 * HTILE_BYTES + 2 * TILE_BYTES + 1024 + 64;   // K,V, Q0,dO0,Q1,dO1, P^T, dS^T, stats
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, int S, int H,
-                    float c, float scale, const float* __restrict__ lse, const float* __restrict__ delta,
-                    __nv_bfloat16* __restrict__ dqkv) {
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
+                    const __grid_constant__ CUtensorMap tm_do, int S, int H, float c, float scale,
+                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   check_align(base);
-  const uint32_t sK = base, sV = base + TILE_BYTES, sP = base + 6 * TILE_BYTES, sdS = base + 8 * TILE_BYTES;
-  auto sQ = [&](int b) { return base + (2 + 2 * b) * TILE_BYTES; };
-  auto sdO = [&](int b) { return base + (3 + 2 * b) * TILE_BYTES; };
-  float* vec = reinterpret_cast<float*>(smem_raw + 10 * TILE_BYTES);   // [2 buffers][lse 128 | delta 128]
-  const uint32_t bars = base + 10 * TILE_BYTES + 2048;
+  const uint32_t sK = base, sV = base + TILE_BYTES;
+  const uint32_t sP = base + 2 * TILE_BYTES + 4 * HTILE_BYTES, sdS = sP + TILE_BYTES;
+  auto sQ = [&](int b) { return base + 2 * TILE_BYTES + (2 * b) * HTILE_BYTES; };
+  auto sdO = [&](int b) { return base + 2 * TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
+  float* vec = reinterpret_cast<float*>(smem_raw + 4 * TILE_BYTES + 4 * HTILE_BYTES);   // [2 buffers][lse 64 | delta 64]
+  const uint32_t bars = base + 4 * TILE_BYTES + 4 * HTILE_BYTES + 1024;
   const uint32_t bar_kv = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
   auto bar_q = [&](int b) { return bars + 24 + 8 * b; };
 
@@ -361,87 +371,91 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   const int kv0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * S;
-  const int n_q = (S + AT - 1) / AT;
+  const int n_q = (S + BT - 1) / BT;
 
   if (tid == 0) {
     mbar_init(bar_kv, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1); mbar_init(bar_q(0), 1); mbar_init(bar_q(1), 1);
     fence_barrier_init();
-    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do);
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const uint32_t tS = tmem_base + lane_off + half * 64, tdP = tmem_base + lane_off + 128 + half * 64;
+  const uint32_t tS = tmem_base + lane_off + half * 32, tdP = tmem_base + lane_off + 64 + half * 32;
 
   const int kv = kv0 + row;
   const bool kv_ok = kv < S;
 
   if (tid == 0) {
     mbar_expect_tx(bar_kv, 2 * TILE_BYTES);
-    tma_load_2d(sK, &tm_qkv, bar_kv, (H + h) * 64, row0 + kv0);
-    tma_load_2d(sV, &tm_qkv, bar_kv, (2 * H + h) * 64, row0 + kv0);
-    mbar_expect_tx(bar_q(0), 2 * TILE_BYTES);
-    tma_load_2d(sQ(0), &tm_qkv, bar_q(0), h * 64, row0);
+    tma_load_2d(sK, &tm_kv, bar_kv, (H + h) * 64, row0 + kv0);
+    tma_load_2d(sV, &tm_kv, bar_kv, (2 * H + h) * 64, row0 + kv0);
+    mbar_expect_tx(bar_q(0), 2 * HTILE_BYTES);
+    tma_load_2d(sQ(0), &tm_q, bar_q(0), h * 64, row0);
     tma_load_2d(sdO(0), &tm_do, bar_q(0), h * 64, row0);
     mbar_wait(bar_kv, 0);
     mbar_wait(bar_q(0), 0);
     tc_fence_after();
-    mma_qk(tmem_base, sK, sQ(0));             // S^T  = K Q^T
-    mma_qk(tmem_base + 128, sV, sdO(0));      // dP^T = V dO^T
+    mma_ab_t(tmem_base, sK, sQ(0));             // S^T  = K Q^T
+    mma_ab_t(tmem_base + 64, sV, sdO(0));       // dP^T = V dO^T
     tc_commit(bar_12);
   }
 
   for (int i = 0; i < n_q; ++i) {
     const int buf = i & 1;
-    {   // per-column (q) statistics of this q tile: threads 0-127 fetch lse, 128-255 fetch delta
-      const int qq = i * AT + (tid & 127);
-      const float* src = tid < 128 ? lse : delta;
-      vec[buf * 256 + tid] = qq < S ? src[(static_cast<size_t>(b) * H + h) * S + qq] : 0.f;
+    if (tid < 128) {   // per-column (q) statistics of this q tile: threads 0-63 fetch lse, 64-127 fetch delta
+      const int qq = i * BT + (tid & 63);
+      const float* src = tid < 64 ? lse : delta;
+      vec[buf * 128 + tid] = qq < S ? src[(static_cast<size_t>(b) * H + h) * S + qq] : 0.f;
     }
-    mbar_wait(bar_12, i & 1);    // also covers MMA3/4 of iteration i-1
+    mbar_wait(bar_12, i & 1);    // also covers the dV/dK MMAs of iteration i-1
     tc_fence_after();
     __syncthreads();             // vec[] visible
     if (tid == 0 && i + 1 < n_q) {
-      mbar_expect_tx(bar_q(buf ^ 1), 2 * TILE_BYTES);
-      tma_load_2d(sQ(buf ^ 1), &tm_qkv, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * AT);
-      tma_load_2d(sdO(buf ^ 1), &tm_do, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * AT);
+      mbar_expect_tx(bar_q(buf ^ 1), 2 * HTILE_BYTES);
+      tma_load_2d(sQ(buf ^ 1), &tm_q, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * BT);
+      tma_load_2d(sdO(buf ^ 1), &tm_do, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * BT);
     }
-    const int q_valid = S - i * AT - half * 64;
-    const float* lse_s = vec + buf * 256 + half * 64;
-    const float* del_s = lse_s + 128;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tS + c0, rs);
-      tmem_ld32(tdP + c0, rp);
-      tc_wait_ld();
-      float p[32];
+    const int q_valid = S - i * BT - half * 32;
+    const float* lse_s = vec + buf * 128 + half * 32;
+    const float* del_s = lse_s + 64;
+    uint32_t rs[32], rp[32];
+    tmem_ld32(tS, rs);
+    tmem_ld32(tdP, rp);
+    tc_wait_ld();
+    float p[32];
+    if (q_valid >= 32) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const bool ok = kv_ok && (c0 + e < q_valid);
-        p[e] = ok ? exp2f(__uint_as_float(rs[e]) * c - lse_s[c0 + e]) : 0.f;
-      }
-      store_p_chunk(sP, row, half * 64 + c0, p);
+      for (int e = 0; e < 32; ++e) p[e] = exp2f(__uint_as_float(rs[e]) * c - lse_s[e]);
+    } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) p[e] = p[e] * (__uint_as_float(rp[e]) - del_s[c0 + e]);
-      store_p_chunk(sdS, row, half * 64 + c0, p);
+      for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? exp2f(__uint_as_float(rs[e]) * c - lse_s[e]) : 0.f;
     }
+    store_p_chunk(sP, row, half * 32, p);
+    if (q_valid >= 32) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) p[e] *= (__uint_as_float(rp[e]) - del_s[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? p[e] * (__uint_as_float(rp[e]) - del_s[e]) : 0.f;
+    }
+    store_p_chunk(sdS, row, half * 32, p);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_pv(tmem_base + 256, sP, sdO(buf), i != 0);       // dV += P^T dO
-      mma_pv(tmem_base + 320, sdS, sQ(buf), i != 0);       // dK += dS^T Q
+      mma_p_t(tmem_base + 128, sP, sdO(buf), i != 0);       // dV += P^T dO
+      mma_p_t(tmem_base + 192, sdS, sQ(buf), i != 0);       // dK += dS^T Q
       if (i + 1 < n_q) {
         mbar_wait(bar_q(buf ^ 1), ((i + 1) >> 1) & 1);
         tc_fence_after();
-        mma_qk(tmem_base, sK, sQ(buf ^ 1));
-        mma_qk(tmem_base + 128, sV, sdO(buf ^ 1));
+        mma_ab_t(tmem_base, sK, sQ(buf ^ 1));
+        mma_ab_t(tmem_base + 64, sV, sdO(buf ^ 1));
         tc_commit(bar_12);
       } else {
         tc_commit(bar_fin);
@@ -453,7 +467,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   {   // half 0 writes dV, half 1 writes dK (64 columns each)
     __nv_bfloat16* dst = dqkv + static_cast<size_t>(row0 + kv) * (3 * H * 64) + ((half == 0 ? 2 * H : H) + h) * 64;
     const float sc = half == 0 ? 1.0f : scale;
-    const uint32_t tsrc = tmem_base + lane_off + (half == 0 ? 256 : 320);
+    const uint32_t tsrc = tmem_base + lane_off + (half == 0 ? 128 : 192);
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t r[32];
@@ -474,7 +488,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 int get_tmap(CUtensorMap* out, const void* p, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);  // gemm.cu
@@ -488,8 +502,10 @@ extern "C" {
 int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_bf16* out, float* lse, void* stream) {
   MOFO_CHECK_ARG(qkv && out && lse, "attn_fwd: null pointer");
   MOFO_CHECK_ARG(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
-  CUtensorMap tm;
-  int rc = get_tmap(&tm, qkv, static_cast<uint64_t>(B) * S, 3ull * H * 64, 3ull * H * 64, AT);
+  CUtensorMap tq, tkv;
+  int rc = get_tmap(&tq, qkv, static_cast<uint64_t>(B) * S, 3ull * H * 64, 3ull * H * 64, AT);
+  if (rc) return rc;
+  rc = get_tmap(&tkv, qkv, static_cast<uint64_t>(B) * S, 3ull * H * 64, 3ull * H * 64, BT);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -497,8 +513,8 @@ int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_b
     attr_set = true;
   }
   dim3 grid((S + AT - 1) / AT, H, B);
-  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, S, H, scale * 1.4426950408889634f,
-                                                                            reinterpret_cast<__nv_bfloat16*>(out), lse);
+  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      tq, tkv, S, H, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(out), lse);
   MOFO_LAUNCH_CHECK("attn_fwd_kernel");
   return MOFO_OK;
 }
@@ -508,10 +524,15 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
   MOFO_CHECK_ARG(qkv && out && dout && lse && dqkv && delta, "attn_bwd: null pointer");
   MOFO_CHECK_ARG(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attn_bwd: bad shape B=%d S=%d H=%d", B, S, H);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CUtensorMap tq, td;
-  int rc = get_tmap(&tq, qkv, static_cast<uint64_t>(B) * S, 3ull * H * 64, 3ull * H * 64, AT);
+  const uint64_t rows = static_cast<uint64_t>(B) * S;
+  CUtensorMap tq128, tq64, td128, td64;
+  int rc = get_tmap(&tq128, qkv, rows, 3ull * H * 64, 3ull * H * 64, AT);
   if (rc) return rc;
-  rc = get_tmap(&td, dout, static_cast<uint64_t>(B) * S, 1ull * H * 64, 1ull * H * 64, AT);
+  rc = get_tmap(&tq64, qkv, rows, 3ull * H * 64, 3ull * H * 64, BT);
+  if (rc) return rc;
+  rc = get_tmap(&td128, dout, rows, 1ull * H * 64, 1ull * H * 64, AT);
+  if (rc) return rc;
+  rc = get_tmap(&td64, dout, rows, 1ull * H * 64, 1ull * H * 64, BT);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -519,15 +540,16 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
     MOFO_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
     attr_set = true;
   }
-  const int rows = B * S;
-  attn_delta_kernel<<<(rows * H + 127) / 128, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out),
-                                                           reinterpret_cast<const __nv_bfloat16*>(dout), rows, S, H, delta);
+  attn_delta_kernel<<<(static_cast<int>(rows) * H + 127) / 128, 128, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), static_cast<int>(rows), S, H, delta);
   MOFO_LAUNCH_CHECK("attn_delta_kernel");
   dim3 grid((S + AT - 1) / AT, H, B);
   const float c = scale * 1.4426950408889634f;
-  attn_bwd_dq_kernel<<<grid, ATT_THREADS, DQ_SMEM, s>>>(tq, td, S, H, c, scale, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv));
+  attn_bwd_dq_kernel<<<grid, ATT_THREADS, DQ_SMEM, s>>>(tq128, tq64, td128, S, H, c, scale, lse, delta,
+                                                        reinterpret_cast<__nv_bfloat16*>(dqkv));
   MOFO_LAUNCH_CHECK("attn_bwd_dq_kernel");
-  attn_bwd_dkv_kernel<<<grid, ATT_THREADS, DKV_SMEM, s>>>(tq, td, S, H, c, scale, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv));
+  attn_bwd_dkv_kernel<<<grid, ATT_THREADS, DKV_SMEM, s>>>(tq128, tq64, td64, S, H, c, scale, lse, delta,
+                                                          reinterpret_cast<__nv_bfloat16*>(dqkv));
   MOFO_LAUNCH_CHECK("attn_bwd_dkv_kernel");
   return MOFO_OK;
 }
