@@ -105,9 +105,12 @@ int mofo_gemm_tn(const mofo_bf16* A, int lda, const mofo_bf16* B, int ldb, int M
 /* mofo_gemm_wgrad: dW[N,K] += dY[M,N]^T · X[M,K]   (f32 accumulate into dW with red.global.add; dW must hold the
  * running sum, e.g. a zeroed slice of the gradient arena).  Replaces the weight-gradient GEMM of every nn.Linear /
  * the Conv3d patch embedding in autograd's backward (utils.py:354 scale(loss).backward()).
- * dY, X row-major bf16; reduction runs over rows, split across CTAs.  N % 8 == 0, K % 8 == 0. */
+ * dY, X row-major bf16; reduction runs over rows, split across CTAs.  N % 8 == 0, K % 8 == 0.
+ * dbias (may be NULL): f32 [N], dbias[n] += sum_m dY[m,n] (the layer's bias gradient) computed in the same pass;
+ * columns n in [dbias_skip_lo, dbias_skip_hi) are left untouched (the K third of the qkv bias, which is the constant 0
+ * of modeling_finetune.py:82-84 and has no parameter). */
 int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, int M, int N, int K, float* dW,
-                    int ldw, void* stream);
+                    int ldw, float* dbias, int dbias_skip_lo, int dbias_skip_hi, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (4) Fused multi-head attention, head_dim 64 (every registry model, modeling_pretrain.py:268-338).
@@ -127,14 +130,18 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
  * group_rows = N_mask, in_group_rows = N, offset = N - N_mask; modeling_pretrain.py:156).
  * fwd: y bf16 [M,D] (dense), mean/rstd f32 [M].
  * bwd: dx = LN'(dy) (+ dres[row] if dres != NULL) written to dx_f32 / dx_bf16 at the mapped x rows (either may be
- *      NULL); dgamma/dbeta f32 [D] are accumulated with atomics (caller zeroes them).
+ *      NULL); dgamma/dbeta f32 [D] are accumulated (+=).  ws: caller-provided scratch of
+ *      mofo_layernorm_bwd_ws_floats(D) floats, zero-filled once before its first use (the kernel leaves it ready for
+ *      the next call; one ws per stream): 16 accumulator rows for the CTA partial sums + a ticket counter; the last
+ *      CTA folds them into dgamma/dbeta.
  */
+int64_t mofo_layernorm_bwd_ws_floats(int D);
 int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int D, float eps,
                        int group_rows, int in_group_rows, int in_row_offset, mofo_bf16* y, float* mean, float* rstd,
                        void* stream);
 int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                        const float* dres, int M, int D, int group_rows, int in_group_rows, int in_row_offset,
-                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, void* stream);
+                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, float* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (6) Decoder input assembly, masked rows (modeling_pretrain.py:260-263): for each clip b and masked slot j,

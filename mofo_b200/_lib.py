@@ -27,11 +27,12 @@ SIGNATURES = {
     "mofo_mask_indices": ([_P, _I, _I, _I, _P, _P, _P, _P], C.c_int),
     "mofo_gather_tubes": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_gemm_tn": ([_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P, _I, _P], C.c_int),
-    "mofo_gemm_wgrad": ([_P, _I, _P, _I, _I, _I, _I, _P, _I, _P], C.c_int),
+    "mofo_gemm_wgrad": ([_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P], C.c_int),
     "mofo_attn_fwd": ([_P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
     "mofo_attn_bwd": ([_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
     "mofo_layernorm_fwd": ([_P, _P, _P, _I, _I, _F, _I, _I, _I, _P, _P, _P, _P], C.c_int),
-    "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
+    "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
+    "mofo_layernorm_bwd_ws_floats": ([_I], C.c_int64),
     "mofo_decoder_assemble_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_decoder_assemble_bwd": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
     "mofo_target_mse": ([_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P], C.c_int),
@@ -187,14 +188,14 @@ def gemm_tn(A, Bm, epilogue, out0, out1=None, bias=None, resid=None, aux=None, p
     return out0
 
 
-def gemm_wgrad(dY, X, dW, M=None):
-    """dW[N,K] += dY[M,N]^T @ X[M,K]  (dW f32, accumulated)."""
+def gemm_wgrad(dY, X, dW, M=None, dbias=None, skip=(0, 0)):
+    """dW[N,K] += dY[M,N]^T @ X[M,K]  (dW f32, accumulated); optionally dbias[N] += colsum(dY) outside skip=[lo,hi)."""
     M = dY.shape[0] if M is None else M
     N, K = dY.shape[1], X.shape[1]
     assert dY.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dW.dtype == torch.float32
     assert dY.stride(1) == 1 and X.stride(1) == 1 and dW.stride(-1) == 1 and dW.numel() == N * K
-    _check(load().mofo_gemm_wgrad(_ptr(dY), dY.stride(0), _ptr(X), X.stride(0), M, N, K, _ptr(dW), K, _stream()),
-           "mofo_gemm_wgrad")
+    _check(load().mofo_gemm_wgrad(_ptr(dY), dY.stride(0), _ptr(X), X.stride(0), M, N, K, _ptr(dW), K, _ptr(dbias),
+                                  skip[0], skip[1], _stream()), "mofo_gemm_wgrad")
     return dW
 
 
@@ -217,13 +218,27 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, M, D, eps=1e-6, group_rows=0, i
     return y
 
 
+_ln_ws = {}
+
+
+def layernorm_bwd_ws(D, device):
+    """Zero-initialised scratch for mofo_layernorm_bwd (per device, stream and D)."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream, D)
+    ws = _ln_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(int(load().mofo_layernorm_bwd_ws_floats(D)), dtype=torch.float32, device=device)
+        _ln_ws[key] = ws
+    return ws
+
+
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres, M, D, dx_f32, dx_bf16, dgamma, dbeta, group_rows=0,
                   in_group_rows=0, in_row_offset=0):
     g = group_rows if group_rows > 0 else M
     ig = in_group_rows if in_group_rows > 0 else M
+    ws = layernorm_bwd_ws(D, x.device)
     _check(load().mofo_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), M, D, g, ig,
-                                     in_row_offset, _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _stream()),
-           "mofo_layernorm_bwd")
+                                     in_row_offset, _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _ptr(ws),
+                                     _stream()), "mofo_layernorm_bwd")
 
 
 def decoder_assemble_fwd(mask_token, pos, msk_idx, B, n_vis, n_msk, Dd, x_full):

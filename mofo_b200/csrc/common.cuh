@@ -40,7 +40,7 @@ int cuda_fail(cudaError_t e, const char* what);
 
 #define MOFO_LAUNCH_CHECK(name)                                              \
   do {                                                                       \
-    cudaError_t _e = cudaPeekAtLastError();                                  \
+    cudaError_t _e = cudaGetLastError();                                     \
     if (_e != cudaSuccess) return ::mofo::cuda_fail(_e, "launch " name);     \
   } while (0)
 

@@ -1,13 +1,14 @@
 // tcgen05 / TMEM / TMA GEMM kernels for the dense layers of the MOFO pretraining step.
 //
 //   gemm_tn_kernel    C[M,N] = epi(A[M,K] · B[N,K]^T)   persistent, warp-specialised:
-//                       warp 4 = TMA producer, warp 5 = tcgen05.mma issuer (+TMEM owner),
-//                       warps 0-3 = epilogue (TMEM -> registers -> fused epilogue -> global).
+//                       warp 8 = TMA producer, warp 9 = tcgen05.mma issuer (+TMEM owner),
+//                       warps 0-7 = epilogue (TMEM -> registers -> fused epilogue -> smem staging -> coalesced global).
 //                     128 x BN output tiles (BN = 128/192/256), BLOCK_K = 64 (one 128-byte swizzle row),
 //                     multi-stage smem ring, two TMEM accumulators so the epilogue of tile i overlaps the
 //                     main loop of tile i+1.
 //   gemm_wgrad_kernel dW[N,K] += dY[M,N]^T · X[M,K]     both operands MN-major (reduction over rows),
-//                     split over M across CTAs, fp32 red.add into the gradient arena.
+//                     split over M across CTAs, row-coalesced fp32 red.add into the gradient arena; the bias
+//                     gradient (column sums of dY) rides along as one extra N=16 MMA against a ones tile.
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -39,9 +40,25 @@ struct EpiParams {
   int ldo1;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-form GELU (nn.GELU default).  erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution):
+// one MUFU.RCP + one MUFU.EX2 + 7 FMA-class ops instead of libdevice erff's branchy ~25; the epilogue is
+// instruction-bound, so this is worth ~2x on the fc1 / fc2-dgrad GEMMs.  e = exp(-x^2/2) is shared with the pdf term.
+__device__ __forceinline__ void erf_parts(float x, float& erf_v, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  e = __expf(-z * z);
+  erf_v = copysignf(fmaf(-poly, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float er, e;
+  erf_parts(x, er, e);
+  return 0.5f * x * (1.0f + er);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  float er, e;
+  erf_parts(x, er, e);
+  return fmaf(x * 0.3989422804014327f, e, 0.5f * (1.0f + er));
 }
 
 // ---- per-warp staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7) ---------------------------
@@ -312,14 +329,14 @@ struct WgCfg {
   static constexpr int B_BYTES = (BNW / 64) * 64 * 128;   // BNW/64 panels
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BNW == 128 ? 6 : 4;
-  static constexpr int TMEM_COLS = BNW == 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = BNW == 256 ? 512 : 256;   // accumulator + 16 columns for the bias-gradient MMA
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
 template <int BNW>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
-                  float* __restrict__ dW, int ldw, int kb_per_split) {
+                  float* __restrict__ dW, int ldw, int kb_per_split, float* __restrict__ dbias, int skip_lo, int skip_hi) {
   using Cfg = WgCfg<BNW>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -340,11 +357,19 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   const int kb0 = blockIdx.y * kb_per_split;
   const int kb1 = min(kblocks_total, kb0 + kb_per_split);
   const int nkb = kb1 - kb0;   // >= 1 by construction of the grid
+  // bias gradient = column sums of dY = dY^T · 1: one extra N=16 MMA per K-step against an all-ones tile, issued by
+  // the CTAs of the first k-tile only.  The ones tile (16 reduction rows x 128 B) aliases the epilogue staging area,
+  // which is not touched before the last MMA has completed.
+  const bool do_bias = dbias != nullptr && k_blk == 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
+  }
+  if (do_bias && threadIdx.x < 128) {
+    sts128(stg_base + threadIdx.x * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
+    fence_proxy_async_smem();
   }
   if (warp == EPI_WARPS && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmX); }
   if (warp == EPI_WARPS + 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -382,6 +407,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
           const uint64_t adesc = umma_desc_mnmajor(smem_a(stage) + k * 2048, 8192);
           const uint64_t bdesc = umma_desc_mnmajor(smem_b(stage) + k * 2048, 8192);
           umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          if (do_bias)
+            umma_bf16(tmem_base + BNW, adesc, umma_desc_mnmajor(stg_base, 8192), umma_idesc_bf16(128, 16, 1, 1),
+                      (i | k) != 0 ? 1u : 0u);
         }
         tc_commit(empty_bar(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -396,6 +424,13 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
     tc_fence_after();
     const int n_base = n_blk * 128 + quarter * 32;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    if (do_bias && grp == 0) {
+      uint32_t r[32];
+      tmem_ld32(taddr + BNW, r);
+      tc_wait_ld();
+      const int n = n_base + lane;
+      if (n < N && !(n >= skip_lo && n < skip_hi)) atomicAdd(dbias + n, __uint_as_float(r[0]));
+    }
 #pragma unroll 1
     for (int ch = grp; ch < BNW / 32; ch += 2) {
       const int k0 = k_blk * BNW + ch * 32;
@@ -493,7 +528,8 @@ static int dispatch_bn(int bn, const CUtensorMap& tA, const CUtensorMap& tB, int
 }
 
 template <int BNW>
-static int launch_wgrad(const CUtensorMap& tY, const CUtensorMap& tX, int M, int N, int K, float* dW, int ldw, cudaStream_t s) {
+static int launch_wgrad(const CUtensorMap& tY, const CUtensorMap& tX, int M, int N, int K, float* dW, int ldw, float* dbias,
+                        int skip_lo, int skip_hi, cudaStream_t s) {
   using Cfg = WgCfg<BNW>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -508,7 +544,7 @@ static int launch_wgrad(const CUtensorMap& tY, const CUtensorMap& tX, int M, int
   const int kb_per_split = (kblocks + splits - 1) / splits;
   splits = (kblocks + kb_per_split - 1) / kb_per_split;
   dim3 grid(tiles, splits);
-  gemm_wgrad_kernel<BNW><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tY, tX, M, N, K, dW, ldw, kb_per_split);
+  gemm_wgrad_kernel<BNW><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tY, tX, M, N, K, dW, ldw, kb_per_split, dbias, skip_lo, skip_hi);
   MOFO_LAUNCH_CHECK("gemm_wgrad_kernel");
   return MOFO_OK;
 }
@@ -559,7 +595,7 @@ int mofo_gemm_tn(const mofo_bf16* A, int lda, const mofo_bf16* B, int ldb, int M
 }
 
 int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, int M, int N, int K, float* dW, int ldw,
-                    void* stream) {
+                    float* dbias, int dbias_skip_lo, int dbias_skip_hi, void* stream) {
   MOFO_CHECK_ARG(dY && X && dW, "gemm_wgrad: null pointer");
   MOFO_CHECK_ARG(M > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, "gemm_wgrad: M=%d N=%d K=%d (need N%%8==0, K%%8==0)", M, N, K);
   MOFO_CHECK_ARG(ldy >= N && ldx >= K && ldy % 8 == 0 && ldx % 8 == 0 && ldw >= K, "gemm_wgrad: bad leading dimensions");
@@ -569,9 +605,9 @@ int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, i
   rc = get_tmap(&tX, X, M, K, ldx, 64);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (K % 256 == 0) return launch_wgrad<256>(tY, tX, M, N, K, dW, ldw, s);
-  if (K % 192 == 0) return launch_wgrad<192>(tY, tX, M, N, K, dW, ldw, s);
-  return launch_wgrad<128>(tY, tX, M, N, K, dW, ldw, s);
+  if (K % 256 == 0) return launch_wgrad<256>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
+  if (K % 192 == 0) return launch_wgrad<192>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
+  return launch_wgrad<128>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
 }
 
 }  // extern "C"

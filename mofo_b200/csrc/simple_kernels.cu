@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(192) gather_tubes_kernel(const float* __restri
 // (5) LayerNorm
 // =================================================================================================
 constexpr int LN_MAX_CHUNKS = 8;  // D <= 1024 (float4 chunk per lane per iteration)
+constexpr int LN_SLOTS = 16;      // accumulator rows for the parameter-gradient partials of layernorm_bwd
 
 __device__ __forceinline__ size_t map_row(int m, int group_rows, int in_group_rows, int in_row_offset) {
   return static_cast<size_t>(m / group_rows) * in_group_rows + in_row_offset + (m % group_rows);
@@ -233,8 +234,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres, int M, int D,
     int group_rows, int in_group_rows, int in_row_offset, float* __restrict__ dx_f32,
-    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ ws) {
   extern __shared__ float red[];  // [warps][2*D]
+  __shared__ int s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int nch = D >> 2;
   float4 dg[NCH], db[NCH];
@@ -295,11 +297,33 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     }
   }
   __syncthreads();
+  // CTA partials are spread over LN_SLOTS accumulator rows in ws (16x less atomic contention per address than adding
+  // into dgamma/dbeta directly); the last CTA to arrive (ticket counter in ws[0]) folds the rows into dgamma/dbeta
+  // and re-zeroes them for the next call.
+  float* slots = ws + 4;
+  float* my_slot = slots + static_cast<size_t>(blockIdx.x % LN_SLOTS) * 2 * D;
   for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
     float s = 0.f;
     for (int w2 = 0; w2 < warps; ++w2) s += red[static_cast<size_t>(w2) * 2 * D + c];
-    if (c < D) atomicAdd(dgamma + c, s);
-    else atomicAdd(dbeta + (c - D), s);
+    atomicAdd(my_slot + c, s);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(reinterpret_cast<unsigned int*>(ws), 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+      float v[LN_SLOTS];
+#pragma unroll
+      for (int g = 0; g < LN_SLOTS; ++g) v[g] = __ldcg(slots + static_cast<size_t>(g) * 2 * D + c);
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < LN_SLOTS; ++g) { s += v[g]; slots[static_cast<size_t>(g) * 2 * D + c] = 0.f; }
+      if (c < D) dgamma[c] += s;
+      else dbeta[c - D] += s;
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws) = 0u;
   }
 }
 
@@ -603,10 +627,12 @@ int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, in
   return MOFO_OK;
 }
 
+int64_t mofo_layernorm_bwd_ws_floats(int D) { return static_cast<int64_t>(LN_SLOTS) * 2 * D + 4; }
+
 int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                        const float* dres, int M, int D, int group_rows, int in_group_rows, int in_row_offset,
-                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, void* stream) {
-  MOFO_CHECK_ARG(dy && x && gamma && mean && rstd && dgamma && dbeta, "layernorm_bwd: null pointer");
+                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, float* ws, void* stream) {
+  MOFO_CHECK_ARG(dy && x && gamma && mean && rstd && dgamma && dbeta && ws, "layernorm_bwd: null pointer");
   MOFO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_CHUNKS && group_rows > 0, "layernorm_bwd: unsupported M=%d D=%d", M, D);
   const int warps = 8;
   int grid = (M + warps - 1) / warps;
@@ -616,11 +642,11 @@ int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, 
   const int nch = (D + 127) / 128;
 #define MOFO_LN_BWD(NCH)                                                                                               \
   do {                                                                                                                 \
-    if (smem > 48 * 1024)                                                                                              \
+    if (smem + 1024 > 48 * 1024)                                                                                       \
       MOFO_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     layernorm_bwd_kernel<NCH><<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(                          \
         reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, M, D, group_rows, in_group_rows,       \
-        in_row_offset, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta);                              \
+        in_row_offset, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, ws);                          \
   } while (0)
   if (nch <= 1) MOFO_LN_BWD(1);
   else if (nch == 2) MOFO_LN_BWD(2);

@@ -208,7 +208,7 @@ class _Runner:
     def _make_arena(self):
         params = dict(self.m.named_parameters())
         order, stage_of, n_stages = self.backward_order()
-        total = sum((params[n].numel() + 3) // 4 * 4 for n in order)     # 16-byte aligned slices
+        total = sum((params[n].numel() + 3) // 4 * 4 * (2 if n.endswith(".attn.q_bias") else 1) for n in order)  # 16-B aligned
         arena = torch.zeros(total, dtype=torch.float32, device=self.device)
         views, off = {}, 0
         stage_end = [0] * n_stages
@@ -216,6 +216,8 @@ class _Runner:
             p = params[n]
             views[n] = arena[off:off + p.numel()].view(p.shape)
             off += (p.numel() + 3) // 4 * 4
+            if n.endswith(".attn.q_bias"):
+                off += (p.numel() + 3) // 4 * 4       # always-zero gap: [q_bias | gap | v_bias] is one [3D] window
             stage_end[stage_of[n]] = off
         self.stage_end = stage_end
         return arena, views
@@ -337,30 +339,28 @@ class _Runner:
         h2 = self.buf(pre + ".h2", (M, D), bf); mean2 = self.buf(pre + ".mean2", (M,), f32); rstd2 = self.buf(pre + ".rstd2", (M,), f32)
         u = self.buf(pre + ".u", (M, Dh), bf); a = self.buf(pre + ".a", (M, Dh), bf)
         # fc2
-        _lib.gemm_wgrad(dxA16, a, g[name + ".mlp.fc2.weight"])
-        _lib.colsum_bf16(dxA16, M, D, g[name + ".mlp.fc2.bias"])
+        _lib.gemm_wgrad(dxA16, a, g[name + ".mlp.fc2.weight"], dbias=g[name + ".mlp.fc2.bias"])
         du = self.buf("bwd.du", (M, Dh), bf)
         _lib.gemm_tn(dxA16, wc[pre + ".fc2"][1], _lib.EPI_GELU_BWD_BF16, du, aux=u)
         # fc1
-        _lib.gemm_wgrad(du, h2, g[name + ".mlp.fc1.weight"])
-        _lib.colsum_bf16(du, M, Dh, g[name + ".mlp.fc1.bias"])
+        _lib.gemm_wgrad(du, h2, g[name + ".mlp.fc1.weight"], dbias=g[name + ".mlp.fc1.bias"])
         dh = self.buf("bwd.dh", (M, D), bf)
         _lib.gemm_tn(du, wc[pre + ".fc1"][1], _lib.EPI_PLAIN_BF16, dh)
         # norm2 (+ residual gradient)
         _lib.layernorm_bwd(dh, xm, blk.norm2.weight, mean2, rstd2, dxA, M, D, dxB, dxB16, g[name + ".norm2.weight"],
                            g[name + ".norm2.bias"])
         # proj
-        _lib.gemm_wgrad(dxB16, o, g[name + ".attn.proj.weight"])
-        _lib.colsum_bf16(dxB16, M, D, g[name + ".attn.proj.bias"])
+        _lib.gemm_wgrad(dxB16, o, g[name + ".attn.proj.weight"], dbias=g[name + ".attn.proj.bias"])
         do = self.buf("bwd.do", (M, D), bf)
         _lib.gemm_tn(dxB16, wc[pre + ".proj"][1], _lib.EPI_PLAIN_BF16, do)
         # attention
         dqkv = self.buf("bwd.dqkv", (M, 3 * D), bf); delta = self.buf("bwd.delta", (B, H, S), f32)
         _lib.attn_bwd(qkv, o, do, lse, B, S, H, blk.attn.scale, dqkv, delta)
         # qkv
-        _lib.gemm_wgrad(dqkv, h1, g[name + ".attn.qkv.weight"])
-        _lib.colsum_bf16(dqkv[:, :D], M, D, g[name + ".attn.q_bias"])
-        _lib.colsum_bf16(dqkv[:, 2 * D:], M, D, g[name + ".attn.v_bias"])
+        # q_bias / v_bias gradients: column sums of dqkv[:, :D] and dqkv[:, 2D:], written through a [3D] window whose
+        # first D floats are q_bias.grad and whose last D floats are v_bias.grad (see _make_arena: a D-float gap sits
+        # between them in the arena so the window is contiguous); the K third is skipped.
+        _lib.gemm_wgrad(dqkv, h1, g[name + ".attn.qkv.weight"], dbias=g[name + ".attn.q_bias"], skip=(D, 2 * D))
         _lib.gemm_tn(dqkv, wc[pre + ".qkv"][1], _lib.EPI_PLAIN_BF16, dh)
         # norm1 (+ residual gradient)
         _lib.layernorm_bwd(dh, x_in, blk.norm1.weight, mean1, rstd1, dxB, M, D, dxA, dxA16, g[name + ".norm1.weight"],
@@ -379,8 +379,7 @@ class _Runner:
         C = m.decoder.num_classes
         # head
         hd = self.buf("dec.hd", (B * Nm, Dd), bf)
-        _lib.gemm_wgrad(dpred, hd, g["decoder.head.weight"])
-        _lib.colsum_bf16(dpred, B * Nm, C, g["decoder.head.bias"])
+        _lib.gemm_wgrad(dpred, hd, g["decoder.head.weight"], dbias=g["decoder.head.bias"])
         dhd = self.buf("bwd.dhd", (B * Nm, Dd), bf)
         _lib.gemm_tn(dpred, wc["head"][1], _lib.EPI_PLAIN_BF16, dhd)
         # decoder.norm on the masked rows; visible rows receive zero gradient from the head
@@ -418,8 +417,7 @@ class _Runner:
                 stage_done(stage)
         # patch embedding (no input gradient)
         A_pe = self.buf("A_pe", (B * Nv, 1536), bf)
-        _lib.gemm_wgrad(exA16, A_pe, g["encoder.patch_embed.proj.weight"])
-        _lib.colsum_bf16(exA16, B * Nv, D, g["encoder.patch_embed.proj.bias"])
+        _lib.gemm_wgrad(exA16, A_pe, g["encoder.patch_embed.proj.weight"], dbias=g["encoder.patch_embed.proj.bias"])
         if stage_done is not None:
             stage_done(last_stage)
 

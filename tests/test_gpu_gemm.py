@@ -97,6 +97,16 @@ def test_gemm_wgrad(lib, M, N, K):
     assert e < 2e-5, f"wgrad rel err {e}"
     lib.gemm_wgrad(dY, X, dW)          # accumulates
     assert rel(dW, 2 * ref) < 2e-5
+    # fused bias gradient (column sums of dY), with a skipped column window like the qkv bias
+    dW.zero_()
+    db = torch.zeros(N, device="cuda")
+    lo, hi = (N // 3, 2 * N // 3) if N % 3 == 0 else (0, 0)
+    lib.gemm_wgrad(dY, X, dW, dbias=db, skip=(lo, hi))
+    want = dY.float().sum(0)
+    want[lo:hi] = 0
+    assert rel(dW, ref) < 2e-5
+    assert rel(db, want) < 2e-5, f"dbias rel err {rel(db, want)}"
+    assert db[lo:hi].abs().max().item() == 0 if hi > lo else True
 
 
 def test_gemm_rejects_bad_args(lib):
