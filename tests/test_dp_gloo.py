@@ -1,0 +1,117 @@
+"""Host-side logic of the data-parallel path on CPU: world_size-2 gloo processes drive mofo_b200.dp.GradSync over an
+arena laid out exactly as the model lays it out (backward-completion order, stage boundaries), and the result must be
+the rank-sum of every slice with the 1/world factor folded in.  No GPU and no kernel is involved."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mofo_b200.dp import GradSync
+        from mofo_b200.modeling_pretrain import create_model
+        torch.manual_seed(0)
+        model = create_model("pretrain_mae_small_patch16_224", decoder_depth=4)
+        runner = model._runner
+        runner.device = torch.device("cpu")
+        arena, views = runner._make_arena()
+        stage_end = runner.stage_end
+        order, stage_of, n_stages = runner.backward_order()
+        assert stage_end == sorted(stage_end) and stage_end[-1] == arena.numel()
+        # every parameter lives wholly inside its stage's slice
+        lo = [0] + stage_end[:-1]
+        for n in order:
+            v = views[n]
+            off = (v.data_ptr() - arena.data_ptr()) // 4
+            k = stage_of[n]
+            assert lo[k] <= off and off + v.numel() <= stage_end[k], n
+        sync = GradSync()
+        assert sync.world == world and abs(sync.grad_scale - 1.0 / world) < 1e-12
+        g = torch.Generator().manual_seed(100 + rank)
+        local = torch.randn(arena.numel(), generator=g)
+        arena.copy_(local * sync.grad_scale)            # the loss gradient carries the 1/world factor
+        sync.begin(arena, stage_end)
+        calls = []
+        for k in range(n_stages):                        # the order the backward pass reports stages
+            sync.stage_done(k)
+            calls.append(sync.prev_end)
+        sync.finish()
+        assert calls == stage_end and sync.launched == n_stages
+        expect = sum(torch.randn(arena.numel(), generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
+        err = (arena - expect).abs().max().item()
+        # a stage that never reports is still flushed by finish()
+        arena.copy_(local * sync.grad_scale)
+        sync.begin(arena, stage_end)
+        sync.stage_done(0)
+        sync.finish()
+        err2 = (arena - expect).abs().max().item()
+        q.put((rank, err, err2, None))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, None, None, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradsync_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err, err2, tb in res:
+        assert tb is None, tb
+        assert err < 1e-6 and err2 < 1e-6, (rank, err, err2)
+
+
+def test_single_process_sync_is_a_noop():
+    from mofo_b200.dp import GradSync
+    s = GradSync()
+    a = torch.arange(10, dtype=torch.float32)
+    s.begin(a, [4, 10])
+    s.stage_done(0); s.stage_done(1); s.finish()
+    assert s.world == 1 and s.grad_scale == 1.0 and torch.equal(a, torch.arange(10, dtype=torch.float32))
+
+
+def test_state_dict_schema_matches_reference_layout():
+    """state_dict keys / shapes / order equal the reference's (oracle.param_shapes is pinned to it by the golden test)."""
+    from mofo_b200.modeling_pretrain import create_model
+    from oracle import model_oracle as mdl
+    for name, cfg in mdl.CONFIGS.items():
+        if "large" in name:
+            continue
+        m = create_model(name, pretrained=False, drop_path_rate=0.0, drop_block_rate=None, decoder_depth=4)
+        sd = m.state_dict()
+        want = mdl.param_shapes(cfg)
+        assert list(sd.keys()) == list(want.keys())
+        assert all(tuple(sd[k].shape) == tuple(want[k]) for k in want)
+        assert m.encoder.patch_embed.patch_size == (16, 16)
+        assert m.no_weight_decay() == {'pos_embed', 'cls_token', 'mask_token'}
+        assert not any(k.endswith("pos_embed") for k in sd)          # tables are not buffers (modeling_pretrain.py:42)
+
+
+def test_model_refuses_cpu_inputs():
+    from mofo_b200.modeling_pretrain import create_model
+    m = create_model("pretrain_mae_small_patch16_224", decoder_depth=4)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 16, 224, 224), torch.zeros(1, 1568, dtype=torch.bool))
