@@ -222,8 +222,8 @@ _ln_ws = {}
 
 
 def layernorm_bwd_ws(D, device):
-    """Zero-initialised scratch for mofo_layernorm_bwd (per device, stream and D)."""
-    key = (str(device), torch.cuda.current_stream(device).cuda_stream, D)
+    """Zero-initialised scratch for mofo_layernorm_bwd (per device and D; calls on one device are stream-ordered)."""
+    key = (str(device), D)
     ws = _ln_ws.get(key)
     if ws is None:
         ws = torch.zeros(int(load().mofo_layernorm_bwd_ws_floats(D)), dtype=torch.float32, device=device)

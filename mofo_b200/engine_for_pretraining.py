@@ -44,6 +44,42 @@ def build_labels(videos, msk_idx, normalize_target=True):
     return out.view(B, n, 1536)
 
 
+class _CudaPrefetcher:
+    """Wraps the data loader: the H2D copies of batch i+1 (pinned host memory -> device, `non_blocking`) are issued on
+    a copy stream while step i computes, so `videos.to(device)` (engine_for_pretraining.py:239-240) costs no step time
+    when the host keeps up.  Yields batches whose tensors already live on `device`."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, device
+        self.quiet = getattr(loader, "quiet", False)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _load(self, it, stream):
+        try:
+            videos, bbox, mask = next(it)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(stream):
+            videos = videos.to(self.device, non_blocking=True)
+            mask = mask.to(self.device, non_blocking=True)
+        return videos, bbox, mask
+
+    def __iter__(self):
+        stream = torch.cuda.Stream(device=self.device)
+        it = iter(self.loader)
+        nxt = self._load(it, stream)
+        while nxt is not None:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_stream(stream)
+            videos, bbox, mask = nxt
+            videos.record_stream(cur)
+            mask.record_stream(cur)
+            nxt = self._load(it, stream)          # overlaps with the step the caller is about to run
+            yield videos, bbox, mask
+
+
 def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer: torch.optim.Optimizer,
                        device: torch.device, epoch: int, loss_scaler, max_norm: float = 0, patch_size: int = 16,
                        normlize_target: bool = True, log_writer=None, lr_scheduler=None, start_steps=None,
@@ -61,6 +97,8 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
     sync = GradSync() if fused else None
     start_steps = start_steps or 0
 
+    if torch.device(device).type == "cuda":
+        data_loader = _CudaPrefetcher(data_loader, torch.device(device))
     for step, batch in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
         it = start_steps + step                                                         # :230
         if lr_schedule_values is not None or wd_schedule_values is not None:

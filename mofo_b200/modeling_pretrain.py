@@ -161,6 +161,10 @@ class _Runner:
         self.scratch_arena = None
         self.enc_group = 4          # encoder blocks per gradient-sync stage
         self.stage_end = None
+        self.graphs = {}            # (B, Nv, Nm, normalize, grad_scale) -> [CUDAGraph per sync stage] | None (capture failed)
+        self.static_in = {}         # (B, Nv, Nm, T, size) -> (videos, vis_idx, msk_idx) device buffers the graphs read
+        self.graph_pool = None
+        self.force_cast = False
 
     # ---- memory -------------------------------------------------------------------------------------------
     def buf(self, name, shape, dtype):
@@ -176,6 +180,7 @@ class _Runner:
             self.device = device
             self.bufs.clear(); self.wcache.clear(); self.wversion = None
             self.arena = None; self.arena_views = None; self.scratch_arena = None
+            self.graphs.clear(); self.static_in.clear(); self.graph_pool = None
             m = self.m
             self.pos_enc = m.encoder_pos_embed[0].to(device).contiguous()
             self.pos_dec = m.pos_embed[0].to(device).contiguous()
@@ -237,7 +242,7 @@ class _Runner:
     def prepare_weights(self):
         m = self.m
         version = tuple(p._version for p in m.parameters())
-        if version == self.wversion:
+        if version == self.wversion and not self.force_cast:
             return
         self.wversion = version
         wc = self.wcache
@@ -422,6 +427,106 @@ class _Runner:
             stage_done(last_stage)
 
 
+    # ---- fused step: eager launch sequence and its CUDA-graph replay ------------------------------------
+    def step_eager(self, videos, vis_idx, msk_idx, normalize_target, grad_scale, zero_grad, stage_done):
+        pred = self.forward(videos, vis_idx, msk_idx)
+        arena = self.grad_arena()
+        if zero_grad:
+            arena.zero_()
+        B, Nv, Nm = self.shape
+        lp = self.buf("loss_partials", (B * Nm,), torch.float32)
+        loss = self.buf("loss", (1,), torch.float32)
+        dpred = self.buf("dpred", (B * Nm, self.m.decoder.num_classes), torch.bfloat16)
+        _lib.target_mse(videos, msk_idx, pred, lp, loss, dpred, normalize_target, grad_scale)
+        self.backward(dpred, self.arena_views, stage_done)
+        return loss
+
+    def static_inputs(self, B, Nv, Nm, frames, size):
+        """Device buffers the captured graphs read their inputs from (the engine's prefetcher copies H2D straight
+        into them; any other caller's tensors are copied in by ``step_graphed``)."""
+        key = (B, Nv, Nm, frames, size)
+        t = self.static_in.get(key)
+        if t is None:
+            t = (torch.empty(B, 3, frames, size, size, dtype=torch.float32, device=self.device),
+                 torch.empty(B, Nv, dtype=torch.int32, device=self.device),
+                 torch.empty(B, Nm, dtype=torch.int32, device=self.device))
+            self.static_in[key] = t
+        return t
+
+    def step_graphed(self, videos, vis_idx, msk_idx, normalize_target, grad_scale, stage_done):
+        """Replays the whole fused step (weight casts, forward, arena zeroing, target + MSE, backward) as CUDA graphs,
+        one per gradient-sync stage, so a step costs a handful of launches instead of ~360.  ``stage_done(k)`` is
+        invoked between the segments exactly as in the eager sequence (NCCL all-reduces stay eager launches)."""
+        B, _, frames, size, _ = videos.shape
+        Nv, Nm = vis_idx.shape[1], msk_idx.shape[1]
+        sv, si, sm = self.static_inputs(B, Nv, Nm, frames, size)
+        if videos.data_ptr() != sv.data_ptr():
+            sv.copy_(videos, non_blocking=True)
+        if vis_idx.data_ptr() != si.data_ptr():
+            si.copy_(vis_idx, non_blocking=True)
+        if msk_idx.data_ptr() != sm.data_ptr():
+            sm.copy_(msk_idx, non_blocking=True)
+        arena = self.grad_arena()                              # (re)attaches the p.grad views
+        key = (B, Nv, Nm, frames, size, bool(normalize_target), float(grad_scale), arena.data_ptr())
+        graphs = self.graphs.get(key, "missing")
+        if graphs == "missing":
+            self.step_eager(sv, si, sm, normalize_target, grad_scale, True, None)   # warm-up: allocations, attributes
+            graphs = self._capture(sv, si, sm, normalize_target, grad_scale)
+            self.graphs[key] = graphs
+        if graphs is None:                                     # capture unavailable: same kernels, launched one by one
+            return self.step_eager(sv, si, sm, normalize_target, grad_scale, True, stage_done)
+        self.shape = (B, Nv, Nm)
+        for k, (g, n_kernels) in enumerate(graphs):
+            g.replay()
+            _lib.launch_count += n_kernels                     # kernels of ours inside the replayed segment
+            if stage_done is not None:
+                stage_done(k)
+        return self.buf("loss", (1,), torch.float32)
+
+    def _capture(self, sv, si, sm, normalize_target, grad_scale):
+        dev = self.device
+        if self.graph_pool is None:
+            self.graph_pool = torch.cuda.graph_pool_handle()
+        graphs = []
+        cur = {"g": None, "n0": 0}
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        n_stages = len(self.stage_end)
+
+        def begin():
+            cur["g"] = torch.cuda.CUDAGraph()
+            cur["n0"] = _lib.launch_count
+            cur["g"].capture_begin(pool=self.graph_pool)
+
+        def boundary(k):
+            cur["g"].capture_end()
+            graphs.append((cur["g"], _lib.launch_count - cur["n0"]))
+            cur["g"] = None
+            if k + 1 < n_stages:
+                begin()
+
+        self.force_cast = True
+        try:
+            with torch.cuda.stream(stream):
+                begin()
+                self.step_eager(sv, si, sm, normalize_target, grad_scale, True, boundary)
+            torch.cuda.current_stream(dev).wait_stream(stream)
+            assert cur["g"] is None and len(graphs) == n_stages
+            return graphs
+        except Exception as e:                                  # pragma: no cover - depends on driver / torch build
+            import warnings
+            warnings.warn(f"mofo_b200: CUDA graph capture failed ({e!r}); launching kernels individually")
+            try:
+                if cur["g"] is not None:
+                    cur["g"].capture_end()
+            except Exception:
+                pass
+            torch.cuda.synchronize(dev)
+            return None
+        finally:
+            self.force_cast = False
+
+
 class _ForwardFn(torch.autograd.Function):
     """pred = model(x, mask) with the manual kernel backward (drop-in autograd path)."""
 
@@ -482,6 +587,7 @@ class PretrainVisionTransformer(nn.Module):
         for i, blk in enumerate(self.decoder.blocks):
             blk._mofo_name = f"decoder.blocks.{i}"
         self._runner = _Runner(self)
+        self.use_cuda_graph = True      # replay the fused step as CUDA graphs (pretrain_step only)
         self._n_msk = None
         self._bad_rows = None
 
@@ -547,18 +653,11 @@ class PretrainVisionTransformer(nn.Module):
         if vis_idx is None:
             vis_idx, msk_idx = self.indices_from_mask(mask)
         r = self._runner
+        r._ensure_device(videos.device)
         with torch.no_grad():
-            pred = r.forward(videos, vis_idx, msk_idx)
-            arena = r.grad_arena()
-            if zero_grad:
-                arena.zero_()
-            B, Nv, Nm = r.shape
-            lp = r.buf("loss_partials", (B * Nm,), torch.float32)
-            loss = r.buf("loss", (1,), torch.float32)
-            dpred = r.buf("dpred", (B * Nm, self.decoder.num_classes), torch.bfloat16)
-            _lib.target_mse(videos, msk_idx, pred, lp, loss, dpred, normalize_target, grad_scale)
-            r.backward(dpred, r.arena_views, stage_done)
-        return loss
+            if self.use_cuda_graph and zero_grad:
+                return r.step_graphed(videos, vis_idx, msk_idx, normalize_target, grad_scale, stage_done)
+            return r.step_eager(videos, vis_idx, msk_idx, normalize_target, grad_scale, zero_grad, stage_done)
 
 
 # ----------------------------------------------------------------------------------------------------------
