@@ -12,7 +12,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmofo_sm100.so")
+LIB_PATH = os.environ.get("MOFO_B200_LIB", os.path.join(HERE, "libmofo_sm100.so"))
 
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PLAIN_BF16, EPI_GELU_BWD_BF16, EPI_BIAS_POS_F32 = range(6)
 
