@@ -1,8 +1,9 @@
 // tcgen05 / TMEM / TMA GEMM kernels for the dense layers of the MOFO pretraining step.
 //
 //   gemm_tn_kernel    C[M,N] = epi(A[M,K] · B[N,K]^T)   persistent, warp-specialised:
-//                       warp 8 = TMA producer, warp 9 = tcgen05.mma issuer (+TMEM owner),
-//                       warps 0-7 = epilogue (TMEM -> registers -> fused epilogue -> smem staging -> coalesced global).
+//                       warp 16 = TMA producer, warp 17 = tcgen05.mma issuer (+TMEM owner),
+//                       warps 0-15 = epilogue (TMEM -> registers -> fused epilogue -> smem staging -> coalesced global;
+//                       the epilogue's second input is prefetched one chunk ahead).
 //                     128 x BN output tiles (BN = 128/192/256), BLOCK_K = 64 (one 128-byte swizzle row),
 //                     multi-stage smem ring, two TMEM accumulators so the epilogue of tile i overlaps the
 //                     main loop of tile i+1.
@@ -20,10 +21,13 @@ namespace mofo {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 8;                       // warps 0-7: epilogue; warp 8: TMA producer; warp 9: MMA issuer
+constexpr int EPI_WARPS = 16;                      // warps 0-15: epilogue; warp 16: TMA producer; warp 17: MMA issuer
 constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;
 constexpr int A_TILE_BYTES = BM * BK * 2;          // 16 KB
-constexpr int STAGING_BYTES = EPI_WARPS * 4096;    // per epilogue warp: 32 rows x 128 B
+constexpr int STAGING_BYTES = EPI_WARPS * 2048;    // per epilogue warp: 32 rows x 64 B
+constexpr int WG_EPI_WARPS = 8;                    // wgrad kernel: warps 0-7 epilogue, 8 producer, 9 MMA
+constexpr int WG_THREADS = (WG_EPI_WARPS + 2) * 32;
+constexpr int WG_STAGING_BYTES = WG_EPI_WARPS * 4096;
 
 struct EpiParams {
   const float* bias;
@@ -40,33 +44,29 @@ struct EpiParams {
   int ldo1;
 };
 
-// erf-form GELU (nn.GELU default).  erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution):
-// one MUFU.RCP + one MUFU.EX2 + 7 FMA-class ops instead of libdevice erff's branchy ~25; the epilogue is
-// instruction-bound, so this is worth ~2x on the fc1 / fc2-dgrad GEMMs.  e = exp(-x^2/2) is shared with the pdf term.
+// erf-form GELU (nn.GELU default).  erf by Abramowitz-Stegun 7.1.25 (3-term, |abs err| <= 2.5e-5, below bf16
+// resolution of the outputs it feeds): one MUFU.RCP + one MUFU.EX2 + a handful of FMA-class ops instead of
+// libdevice erff's branchy ~25.  The epilogue is instruction-bound, so every instruction per element counts.
+// e = exp(-x^2/2) is shared with the pdf term of the derivative.
 __device__ __forceinline__ void erf_parts(float x, float& erf_v, float& e) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  e = __expf(-z * z);
+  const float t = __fdividef(1.0f, fmaf(0.47047f, z, 1.0f));
+  const float poly = t * fmaf(t, fmaf(t, 0.7478556f, -0.0958798f), 0.3480242f);
+  e = exp2f(-1.4426950408889634f * z * z);
   erf_v = copysignf(fmaf(-poly, e, 1.0f), x);
 }
 __device__ __forceinline__ float gelu_erf(float x) {
   float er, e;
   erf_parts(x, er, e);
-  return 0.5f * x * (1.0f + er);
+  const float hx = 0.5f * x;
+  return fmaf(hx, er, hx);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float er, e;
   erf_parts(x, er, e);
-  return fmaf(x * 0.3989422804014327f, e, 0.5f * (1.0f + er));
+  return fmaf(x * 0.3989422804014327f, e, fmaf(0.5f, er, 0.5f));
 }
 
-// ---- per-warp staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7) ---------------------------
-// "own row" access: thread `lane` touches row `lane`;  "cooperative" access: instruction i touches rows 4i..4i+3,
-// 8 lanes per row -> every global instruction covers 4 full 128-byte lines.  Both patterns are bank-conflict free.
-__device__ __forceinline__ uint32_t stg_addr(uint32_t stg, int row, int chunk) {
-  return stg + static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
-}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -75,56 +75,98 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// wgrad staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7)
+__device__ __forceinline__ uint32_t stg_addr(uint32_t stg, int row, int chunk) {
+  return stg + static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
+}
+// ---- gemm_tn per-warp staging tile: 32 rows x 64 B (32 bf16 or 16 f32 output columns per row) ------------------
+// 16-byte chunks XOR-swizzled by ((row >> 1) & 3): conflict-free both for "own row" accesses (thread `lane` touches
+// row `lane`) and for "cooperative" accesses (instruction i touches rows 8i..8i+7, 4 lanes per row), so every global
+// instruction of the epilogue moves 8 full 64-byte row segments.
+__device__ __forceinline__ uint32_t stg64(uint32_t stg, int row, int chunk) {
+  return stg + static_cast<uint32_t>(row) * 64u + (static_cast<uint32_t>(chunk ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 
-// cooperative global -> staging: rows row_base..+31 of a row-major matrix, 128 bytes per row starting where
-// `rowptr(grow)` points (rows >= M and chunks >= valid_chunks are zero filled).
+// cooperative 64-byte-row access: 4 instructions cover 32 rows; lane -> (row 8i + lane/4, chunk lane%4)
 template <typename RowPtr>
-__device__ __forceinline__ void coop_load(uint32_t stg, int lane, int row_base, int M, int valid_chunks, RowPtr rowptr) {
+__device__ __forceinline__ void coop_fetch(uint4 (&pre)[4], int lane, int row_base, int M, int valid_chunks, RowPtr rowptr) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = 4 * i + (lane >> 3), chunk = lane & 7;
-    const int grow = row_base + row;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (grow < M && chunk < valid_chunks) v = __ldg(reinterpret_cast<const uint4*>(rowptr(grow)) + chunk);
-    sts128(stg_addr(stg, row, chunk), v);
+  for (int i = 0; i < 4; ++i) {
+    const int grow = row_base + 8 * i + (lane >> 2), chunk = lane & 3;
+    pre[i] = make_uint4(0, 0, 0, 0);
+    if (grow < M && chunk < valid_chunks) pre[i] = __ldg(reinterpret_cast<const uint4*>(rowptr(grow)) + chunk);
   }
+}
+__device__ __forceinline__ void coop_stage(uint32_t stg, int lane, const uint4 (&pre)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sts128(stg64(stg, 8 * i + (lane >> 2), lane & 3), pre[i]);
 }
 template <typename RowPtr>
 __device__ __forceinline__ void coop_store(uint32_t stg, int lane, int row_base, int M, int valid_chunks, RowPtr rowptr) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = 4 * i + (lane >> 3), chunk = lane & 7;
+  for (int i = 0; i < 4; ++i) {
+    const int row = 8 * i + (lane >> 2), chunk = lane & 3;
     const int grow = row_base + row;
-    if (grow < M && chunk < valid_chunks) *(reinterpret_cast<uint4*>(rowptr(grow)) + chunk) = lds128(stg_addr(stg, row, chunk));
+    if (grow < M && chunk < valid_chunks) *(reinterpret_cast<uint4*>(rowptr(grow)) + chunk) = lds128(stg64(stg, row, chunk));
   }
 }
 
-// One warp, one chunk of 128 output bytes per row (64 bf16 or 32 f32 columns) starting at column n0.
-// `taddr` already points at this warp's TMEM lanes and the chunk's first accumulator column.
+template <int EPI>
+struct EpiTraits {
+  static constexpr bool F32_OUT = (EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32);
+  static constexpr int COLS = F32_OUT ? 16 : 32;                 // 64 output bytes per row per chunk
+  static constexpr bool HAS_BIAS = (EPI == MOFO_EPI_BIAS_BF16 || EPI == MOFO_EPI_BIAS_GELU_BF16 ||
+                                    EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32);
+  static constexpr bool HAS_OPERAND = (EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32 ||
+                                       EPI == MOFO_EPI_GELU_BWD_BF16);   // a second [M,N] input read by the epilogue
+};
+
+// global -> registers prefetch of the epilogue's additive / multiplicative operand for one chunk
+template <int EPI>
+__device__ __forceinline__ void operand_fetch(const EpiParams& ep, uint4 (&pre)[4], int lane, int row_base, int M, int n0, int N) {
+  using T = EpiTraits<EPI>;
+  const int rem = N - n0;
+  const int valid_chunks = rem >= T::COLS ? 4 : (T::F32_OUT ? rem / 4 : rem / 8);
+  if (EPI == MOFO_EPI_BIAS_RESID_F32)
+    coop_fetch(pre, lane, row_base, M, valid_chunks, [&](int g) { return ep.resid + static_cast<size_t>(g) * ep.ldr + n0; });
+  else if (EPI == MOFO_EPI_BIAS_POS_F32)
+    coop_fetch(pre, lane, row_base, M, valid_chunks, [&](int g) { return ep.pos + static_cast<size_t>(ep.row_idx[g]) * N + n0; });
+  else if (EPI == MOFO_EPI_GELU_BWD_BF16)
+    coop_fetch(pre, lane, row_base, M, valid_chunks, [&](int g) { return ep.aux + static_cast<size_t>(g) * ep.ldaux + n0; });
+}
+
+// One warp, one chunk (64 output bytes per row) starting at column n0; `taddr` = this warp's TMEM lanes + chunk column.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, uint32_t stg, int lane, int row_base, int M, int n0,
-                                               int N, uint32_t taddr) {
-  constexpr bool F32_OUT = (EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32);
-  constexpr int COLS = F32_OUT ? 32 : 64;
-  constexpr bool HAS_BIAS = (EPI == MOFO_EPI_BIAS_BF16 || EPI == MOFO_EPI_BIAS_GELU_BF16 ||
-                             EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32);
+                                               int N, uint32_t taddr, const uint4 (&pre)[4]) {
+  using T = EpiTraits<EPI>;
+  constexpr int COLS = T::COLS;
   const int rem = N - n0;                                   // > 0
-  const int valid_chunks = rem >= COLS ? 8 : (F32_OUT ? rem / 4 : rem / 8);
+  const int valid_chunks = rem >= COLS ? 4 : (T::F32_OUT ? rem / 4 : rem / 8);
   float v[COLS];
-  {
+  if (COLS == 32) {
     uint32_t r[32];
     tmem_ld32(taddr, r);
     tc_wait_ld();
 #pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-    if (COLS == 64) {
-      tmem_ld32(taddr + 32, r);
-      tc_wait_ld();
+    for (int e = 0; e < 32; ++e) v[e % COLS] = __uint_as_float(r[e]);
+  } else {
+    uint32_t r[16];
+    tmem_ld16(taddr, r);
+    tc_wait_ld();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) v[(COLS == 64 ? 32 : 0) + e] = __uint_as_float(r[e]);
-    }
+    for (int e = 0; e < 16; ++e) v[e % COLS] = __uint_as_float(r[e]);
   }
-  if (HAS_BIAS && ep.bias) {
+  if (T::HAS_BIAS && ep.bias) {
 #pragma unroll
     for (int c = 0; c < COLS / 4; ++c) {
       if (n0 + c * 4 < N) {
@@ -138,35 +180,31 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, uint32_t stg
                ? static_cast<size_t>(grow / ep.group_rows) * ep.out_group_rows + (grow % ep.group_rows)
                : static_cast<size_t>(grow);
   };
-  if (F32_OUT) {
-    // additive f32 operand (residual stream or gathered position row), staged for coalesced access
-    if (EPI == MOFO_EPI_BIAS_RESID_F32)
-      coop_load(stg, lane, row_base, M, valid_chunks, [&](int g) { return ep.resid + static_cast<size_t>(g) * ep.ldr + n0; });
-    else
-      coop_load(stg, lane, row_base, M, valid_chunks, [&](int g) { return ep.pos + static_cast<size_t>(ep.row_idx[g]) * N + n0; });
+  if (T::HAS_OPERAND) {            // transpose the prefetched operand rows to "own row" through the staging tile
+    coop_stage(stg, lane, pre);
     __syncwarp();
+  }
+  if (T::F32_OUT) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 q = lds128(stg_addr(stg, lane, c));
+    for (int c = 0; c < 4; ++c) {
+      const uint4 q = lds128(stg64(stg, lane, c));
       v[c * 4 + 0] += __uint_as_float(q.x); v[c * 4 + 1] += __uint_as_float(q.y);
       v[c * 4 + 2] += __uint_as_float(q.z); v[c * 4 + 3] += __uint_as_float(q.w);
     }
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      sts128(stg_addr(stg, lane, c), make_uint4(__float_as_uint(v[c * 4]), __float_as_uint(v[c * 4 + 1]),
-                                                 __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3])));
+    for (int c = 0; c < 4; ++c)
+      sts128(stg64(stg, lane, c), make_uint4(__float_as_uint(v[c * 4]), __float_as_uint(v[c * 4 + 1]),
+                                              __float_as_uint(v[c * 4 + 2]), __float_as_uint(v[c * 4 + 3])));
     __syncwarp();
     coop_store(stg, lane, row_base, M, valid_chunks,
                [&](int g) { return reinterpret_cast<float*>(ep.out0) + out_row(g) * ep.ldo0 + n0; });
     __syncwarp();
   } else {
     if (EPI == MOFO_EPI_GELU_BWD_BF16) {
-      coop_load(stg, lane, row_base, M, valid_chunks, [&](int g) { return ep.aux + static_cast<size_t>(g) * ep.ldaux + n0; });
-      __syncwarp();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 a = lds128(stg_addr(stg, lane, c));
+      for (int c = 0; c < 4; ++c) {
+        const uint4 a = lds128(stg64(stg, lane, c));
         v[c * 8 + 0] *= gelu_erf_grad(bf16_lo(a.x)); v[c * 8 + 1] *= gelu_erf_grad(bf16_hi(a.x));
         v[c * 8 + 2] *= gelu_erf_grad(bf16_lo(a.y)); v[c * 8 + 3] *= gelu_erf_grad(bf16_hi(a.y));
         v[c * 8 + 4] *= gelu_erf_grad(bf16_lo(a.z)); v[c * 8 + 5] *= gelu_erf_grad(bf16_hi(a.z));
@@ -174,26 +212,27 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, uint32_t stg
       }
       __syncwarp();
     }
-    if (EPI == MOFO_EPI_BIAS_GELU_BF16) {
-      // the pre-activation is rounded to bf16 first (what F.linear returns under autocast); GELU acts on that
+    uint32_t packed[COLS / 2];
 #pragma unroll
-      for (int e = 0; e < COLS; ++e) v[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
-    }
+    for (int e = 0; e < COLS / 2; ++e) packed[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      sts128(stg_addr(stg, lane, c), make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
-                                                 pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16(v[c * 8 + 6], v[c * 8 + 7])));
+    for (int c = 0; c < 4; ++c)
+      sts128(stg64(stg, lane, c), make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]));
     __syncwarp();
     coop_store(stg, lane, row_base, M, valid_chunks,
                [&](int g) { return reinterpret_cast<__nv_bfloat16*>(ep.out0) + static_cast<size_t>(g) * ep.ldo0 + n0; });
     __syncwarp();
     if (EPI == MOFO_EPI_BIAS_GELU_BF16) {
+      // GELU acts on the bf16-rounded pre-activation (what F.linear returns under autocast)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float u[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) u[e] = gelu_erf(v[c * 8 + e]);
-        sts128(stg_addr(stg, lane, c), make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7])));
+        for (int e = 0; e < 4; ++e) {
+          u[2 * e] = gelu_erf(bf16_lo(packed[c * 4 + e]));
+          u[2 * e + 1] = gelu_erf(bf16_hi(packed[c * 4 + e]));
+        }
+        sts128(stg64(stg, lane, c), make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7])));
       }
       __syncwarp();
       coop_store(stg, lane, row_base, M, valid_chunks,
@@ -275,12 +314,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          const uint64_t adesc = umma_desc_kmajor(smem_a(stage)), bdesc = umma_desc_kmajor(smem_b(stage));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = umma_desc_kmajor(smem_a(stage) + k * 32);
-            const uint64_t bdesc = umma_desc_kmajor(smem_b(stage) + k * 32);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           tc_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -290,23 +326,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {  // ===== epilogue warps: quarter = TMEM lane group, grp = which chunks of the tile =====
-    constexpr bool F32_OUT = (EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32);
-    constexpr int COLS = F32_OUT ? 32 : 64;
+    using T = EpiTraits<EPI>;
+    constexpr int COLS = T::COLS;
+    constexpr int NCHUNK = BN / COLS;
     const int quarter = warp & 3, grp = warp >> 2;
-    const uint32_t stg = stg_base + warp * 4096;
+    const uint32_t stg = stg_base + warp * 2048;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row_base = m_blk * BM + quarter * 32;
+      uint4 pre[4];
+      if (T::HAS_OPERAND && n_blk * BN + grp * COLS < N)          // first chunk's operand: overlaps the tile's main loop
+        operand_fetch<EPI>(ep, pre, lane, row_base, M, n_blk * BN + grp * COLS, N);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row_base = m_blk * BM + quarter * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int ch = grp; ch < BN / COLS; ch += 2) {
+      for (int ch = grp; ch < NCHUNK; ch += EPI_WARPS / 4) {
         const int n0 = n_blk * BN + ch * COLS;
         if (n0 >= N) break;
-        epilogue_chunk<EPI>(ep, stg, lane, row_base, M, n0, N, taddr + ch * COLS);
+        uint4 cur[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = pre[i];
+        const int n_next = n0 + (EPI_WARPS / 4) * COLS;
+        if (T::HAS_OPERAND && ch + EPI_WARPS / 4 < NCHUNK && n_next < N)
+          operand_fetch<EPI>(ep, pre, lane, row_base, M, n_next, N);   // next chunk's operand in flight during this one
+        epilogue_chunk<EPI>(ep, stg, lane, row_base, M, n0, N, taddr + ch * COLS, cur);
       }
       tc_fence_before();
       __syncwarp();
@@ -330,11 +376,11 @@ struct WgCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BNW == 128 ? 6 : 4;
   static constexpr int TMEM_COLS = BNW == 256 ? 512 : 256;   // accumulator + 16 columns for the bias-gradient MMA
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + WG_STAGING_BYTES + 1024 + 256;
 };
 
 template <int BNW>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
                   float* __restrict__ dW, int ldw, int kb_per_split, float* __restrict__ dbias, int skip_lo, int skip_hi) {
   using Cfg = WgCfg<BNW>;
@@ -342,7 +388,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = stg_base + STAGING_BYTES;
+  const uint32_t bar_base = stg_base + WG_STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
@@ -371,15 +417,15 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
     sts128(stg_base + threadIdx.x * 16, make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u));
     fence_proxy_async_smem();
   }
-  if (warp == EPI_WARPS && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmX); }
-  if (warp == EPI_WARPS + 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == WG_EPI_WARPS && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmX); }
+  if (warp == WG_EPI_WARPS + 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == EPI_WARPS) {
+  if (warp == WG_EPI_WARPS) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -394,7 +440,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == EPI_WARPS + 1) {
+  } else if (warp == WG_EPI_WARPS + 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);
       int stage = 0;
@@ -456,7 +502,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == EPI_WARPS + 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == WG_EPI_WARPS + 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -544,7 +590,7 @@ static int launch_wgrad(const CUtensorMap& tY, const CUtensorMap& tX, int M, int
   const int kb_per_split = (kblocks + splits - 1) / splits;
   splits = (kblocks + kb_per_split - 1) / kb_per_split;
   dim3 grid(tiles, splits);
-  gemm_wgrad_kernel<BNW><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tY, tX, M, N, K, dW, ldw, kb_per_split, dbias, skip_lo, skip_hi);
+  gemm_wgrad_kernel<BNW><<<grid, WG_THREADS, Cfg::SMEM_BYTES, s>>>(tY, tX, M, N, K, dW, ldw, kb_per_split, dbias, skip_lo, skip_hi);
   MOFO_LAUNCH_CHECK("gemm_wgrad_kernel");
   return MOFO_OK;
 }

@@ -183,6 +183,7 @@ __device__ __forceinline__ size_t map_row(int m, int group_rows, int in_group_ro
   return static_cast<size_t>(m / group_rows) * in_group_rows + in_row_offset + (m % group_rows);
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int M, int D, float eps,
                                                             int group_rows, int in_group_rows, int in_row_offset,
@@ -193,17 +194,17 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   if (m >= M) return;
   const int nch = D >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + map_row(m, group_rows, in_group_rows, in_row_offset) * D);
-  float4 v[LN_MAX_CHUNKS];
+  float4 v[NCH];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     int ch = lane + i * 32;
     if (ch < nch) { v[i] = xr[ch]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
   }
   const float mu = warp_sum(s) / D;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     int ch = lane + i * 32;
     if (ch < nch) {
       float a = v[i].x - mu, b2 = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   if (lane == 0) { mean[m] = mu; rstd[m] = rs; }
   uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(m) * D);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     int ch = lane + i * 32;
     if (ch < nch) {
       float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // warp per row, grid-stride over rows; per-lane register partials of dgamma/dbeta, reduced through shared
 // memory per CTA and accumulated with one atomicAdd per column per CTA.
 template <int NCH>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(
+__global__ void __launch_bounds__(256, (NCH <= 3 ? 3 : 2)) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres, int M, int D,
     int group_rows, int in_group_rows, int in_row_offset, float* __restrict__ dx_f32,
@@ -248,8 +249,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const float4* xr = reinterpret_cast<const float4*>(x + xrow * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(m) * D);
     const float mu = mean[m], rs = rstd[m];
-    float4 xh[NCH], g[NCH];
+    float4 xh[NCH], g[NCH], rres[NCH];
     float s1 = 0.f, s2 = 0.f;
+    if (dres) {   // issued together with x / dy: one global-latency phase per row instead of two
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        int ch = lane + i * 32;
+        if (ch < nch) rres[i] = reinterpret_cast<const float4*>(dres + xrow * D)[ch];
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       int ch = lane + i * 32;
@@ -274,10 +282,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
       if (ch < nch) {
         float4 o = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
                                rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
-        if (dres) {
-          float4 r = reinterpret_cast<const float4*>(dres + xrow * D)[ch];
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
+        if (dres) { o.x += rres[i].x; o.y += rres[i].y; o.z += rres[i].z; o.w += rres[i].w; }
         if (dx_f32) reinterpret_cast<float4*>(dx_f32 + xrow * D)[ch] = o;
         if (dx_bf16) {
           uint2 p; p.x = pack_bf16(o.x, o.y); p.y = pack_bf16(o.z, o.w);
@@ -621,8 +626,17 @@ int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, in
                        int in_group_rows, int in_row_offset, mofo_bf16* y, float* mean, float* rstd, void* stream) {
   MOFO_CHECK_ARG(x && gamma && beta && y && mean && rstd, "layernorm_fwd: null pointer");
   MOFO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_CHUNKS && group_rows > 0, "layernorm_fwd: unsupported M=%d D=%d", M, D);
-  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, gamma, beta, M, D, eps, group_rows, in_group_rows, in_row_offset, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd);
+  const int nch = (D + 127) / 128;
+#define MOFO_LN_FWD(NCH)                                                                                     \
+  layernorm_fwd_kernel<NCH><<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(                     \
+      x, gamma, beta, M, D, eps, group_rows, in_group_rows, in_row_offset, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd)
+  if (nch <= 1) MOFO_LN_FWD(1);
+  else if (nch == 2) MOFO_LN_FWD(2);
+  else if (nch == 3) MOFO_LN_FWD(3);
+  else if (nch == 4) MOFO_LN_FWD(4);
+  else if (nch <= 6) MOFO_LN_FWD(6);
+  else MOFO_LN_FWD(8);
+#undef MOFO_LN_FWD
   MOFO_LAUNCH_CHECK("layernorm_fwd_kernel");
   return MOFO_OK;
 }
