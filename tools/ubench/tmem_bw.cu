@@ -1,0 +1,56 @@
+// Microbenchmark: tcgen05.ld (32x32b.x32) throughput per SM as a function of the number of reading warps.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__global__ void k(int iters, long long* cycles, uint32_t* sink) {
+  __shared__ uint32_t slot;
+  int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t r[32];
+    tmem_ld32(base + ((i * 32 + (warp >> 2) * 64) & 511 & ~31), r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc ^= r[e];
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+  if (acc == 0x12345) sink[threadIdx.x] = acc;
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"(512u) : "memory");
+}
+int main() {
+  long long* d; uint32_t* s; cudaMalloc(&d, 8); cudaMalloc(&s, 4096);
+  for (int warps : {4, 8, 16}) {
+    int iters = 4096;
+    k<<<148, warps * 32>>>(iters, d, s); cudaDeviceSynchronize();
+    k<<<148, warps * 32>>>(iters, d, s);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+    double bytes = (double)iters * warps * 32 * 32 * 4;
+    printf("warps %2d: %lld cycles, %.1f B/clk/SM (err %d)\n", warps, c, bytes / c, (int)e);
+  }
+  return 0;
+}
