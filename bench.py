@@ -55,10 +55,11 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -67,7 +68,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
@@ -78,7 +79,12 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.06]
+        window = "timed region"
+        if len(inside) < 3:            # very short timed region: widen to the surrounding (equally loaded) warm-up / legs
+            inside = [r for t, r in self.rows if self.t0 is not None and self.t0 - 1.0 <= t <= self.t1 + 1.0]
+            window = "timed region +-1 s (region shorter than the sampling period)"
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -88,7 +94,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -193,7 +199,8 @@ def run_ours(args):
     model = mp.create_model(args.model, pretrained=False, drop_path_rate=0.0, drop_block_rate=None, decoder_depth=4).to(dev)
     model.train()
     lr = 1.5e-4 * B * world / 256                         # run_mae_pretraining_BB.py:219-223
-    opt = torch.optim.AdamW(param_groups(model), lr=lr, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+    from mofo_b200.optim_factory import FusedAdamW
+    opt = FusedAdamW(param_groups(model), lr=lr, betas=(0.9, 0.95), weight_decay=0.05).attach(model)
     scaler = U.NativeScalerWithGradNormCount()
     gen = mg.TubeMaskingGenerator_BB((8, 14, 14), 0.9, 0.75, device=dev)
     mean = torch.tensor((0.485, 0.456, 0.406), device=dev)[None, :, None, None, None]
@@ -224,7 +231,7 @@ def run_ours(args):
         loss = model.pretrain_step(vid, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=True, grad_scale=sync.grad_scale,
                                    zero_grad=True, stage_done=sync.stage_done)
         sync.finish()
-        scaler(loss, opt, clip_grad=0, parameters=None, arena=arena)
+        scaler(loss, opt, clip_grad=0, parameters=None, arena=arena, loss_guard=True)
         return loss
 
     def barrier():
@@ -232,24 +239,26 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                   # started before warm-up: nvidia-smi needs ~0.3 s to produce its first row
     for i in range(args.warmup):
         loss = device_step(i)
     barrier()
     assert torch.isfinite(loss).item(), "non-finite loss in warm-up"
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+
     launches0 = _lib.launch_count
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.t0 = time.time()
     e0.record()
     for i in range(args.steps):
         loss = device_step(args.warmup + i)
     e1.record()
     barrier()
+    sampler.t1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -272,6 +281,7 @@ def run_ours(args):
     n_gemm, gemm_ms, gemm_flops = ktimer.summary()
     ms_instrumented = e2.elapsed_time(e3)
     model.use_cuda_graph = True
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the public engine API with HOST (pinned) batches; H2D + loss D2H inside the timed region ----------
     e2e = None
@@ -332,7 +342,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": f"inputs larger than L2: {POOL} rotating {B * 3 * 16 * 224 * 224 * 4 >> 20} MiB batches per GPU",
-                       "optimizer": "torch AdamW(fused) on fp32 masters (SURVEY §8f-1: optimizer kernel is a 'next' row)",
+                       "optimizer": "mofo_b200.optim_factory.FusedAdamW: one mofo_adamw_step kernel over the flat fp32 arenas, also "
+                                    "emitting the bf16 W / W^T operand copies (SURVEY §8f-1)",
                        "launch": "fused step replayed as 4 CUDA graphs (one per gradient-sync stage); roofline leg launches kernels individually"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "final_loss": final_loss,
             "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05, all fused-epilogue instances)",

@@ -40,6 +40,7 @@ SIGNATURES = {
     "mofo_pack_qkv_bias": ([_P, _P, _I, _P, _P], C.c_int),
     "mofo_colsum_bf16": ([_P, _I, _I, _I, _P, _P], C.c_int),
     "mofo_sq_norm_f32": ([_P, _L, _P, _P], C.c_int),
+    "mofo_adamw_step": ([_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P], C.c_int),
 }
 
 
@@ -279,3 +280,9 @@ def colsum_bf16(X, M, N, out):
 
 def sq_norm_f32(x, out):
     _check(load().mofo_sq_norm_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "mofo_sq_norm_f32")
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, w16, segs, tiles, hyper, clip_coef=None, loss_guard=None):
+    _check(load().mofo_adamw_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(w16), _ptr(segs),
+                                  _ptr(tiles), tiles.shape[0], _ptr(hyper), _ptr(clip_coef), _ptr(loss_guard), _stream()),
+           "mofo_adamw_step")

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmofo_sm100.so")
-SOURCES = ["runtime.cu", "simple_kernels.cu", "gemm.cu", "attention.cu"]
+SOURCES = ["runtime.cu", "simple_kernels.cu", "gemm.cu", "attention.cu", "optimizer.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "mofo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]

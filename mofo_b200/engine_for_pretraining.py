@@ -120,11 +120,22 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
             loss = core.pretrain_step(videos, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=normlize_target,
                                       grad_scale=sync.grad_scale, zero_grad=True, stage_done=sync.stage_done)
             sync.finish()
-            loss_value = loss.item()                                                    # :306 (the step's D2H read)
-            if not math.isfinite(loss_value):
-                print("Loss is {}, stopping training".format(loss_value))
-                sys.exit(1)
-            grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=core.parameters(), arena=arena)
+            if getattr(optimizer, "fused_mofo", False):
+                # the fused optimizer skips the update on the device when the loss is not finite, so the whole step
+                # (incl. the parameter update) is enqueued before the single host read of the loss
+                optimizer.attach(core)
+                grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=core.parameters(), arena=arena,
+                                        loss_guard=True)
+                loss_value = loss.item()                                                # :306 (the step's D2H read)
+                if not math.isfinite(loss_value):
+                    print("Loss is {}, stopping training".format(loss_value))
+                    sys.exit(1)
+            else:
+                loss_value = loss.item()
+                if not math.isfinite(loss_value):
+                    print("Loss is {}, stopping training".format(loss_value))
+                    sys.exit(1)
+                grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=core.parameters(), arena=arena)
         else:
             vis_idx, msk_idx = core.indices_from_mask(bool_masked_pos)
             with torch.no_grad():

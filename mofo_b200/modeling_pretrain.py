@@ -165,6 +165,7 @@ class _Runner:
         self.static_in = {}         # (B, Nv, Nm, T, size) -> (videos, vis_idx, msk_idx) device buffers the graphs read
         self.graph_pool = None
         self.force_cast = False
+        self.external_weights = False   # bf16 operand copies maintained by mofo_b200.optim_factory.FusedAdamW
 
     # ---- memory -------------------------------------------------------------------------------------------
     def buf(self, name, shape, dtype):
@@ -239,10 +240,22 @@ class _Runner:
         return self.arena
 
     # ---- weights ------------------------------------------------------------------------------------------
+    def adopt_external_weights(self, wcache, qkvbias):
+        """Called by FusedAdamW.attach: from now on the optimizer kernel rewrites the bf16 W / W^T copies in place after
+        every update (and the packed qkv bias is a window of the parameter arena), so ``prepare_weights`` only has to
+        re-cast when something else modified the fp32 parameters (e.g. ``load_state_dict``)."""
+        self.wcache = dict(wcache)
+        for k, v in qkvbias.items():
+            self.bufs[(k, tuple(v.shape), torch.float32)] = v
+        self.external_weights = True
+        self.external_qkvbias = set(qkvbias)
+        self.wversion = None
+        self.graphs.clear()
+
     def prepare_weights(self):
         m = self.m
         version = tuple(p._version for p in m.parameters())
-        if version == self.wversion and not self.force_cast:
+        if version == self.wversion and not (self.force_cast and not self.external_weights):
             return
         self.wversion = version
         wc = self.wcache
@@ -264,8 +277,9 @@ class _Runner:
                 cast(pre + ".proj", blk.attn.proj.weight)
                 cast(pre + ".fc1", blk.mlp.fc1.weight)
                 cast(pre + ".fc2", blk.mlp.fc2.weight)
-                qb = self.buf(pre + ".qkvbias", (3 * blk.attn.q_bias.numel(),), torch.float32)
-                _lib.pack_qkv_bias(blk.attn.q_bias.detach(), blk.attn.v_bias.detach(), qb)
+                if not (self.external_weights and (pre + ".qkvbias") in self.external_qkvbias):
+                    qb = self.buf(pre + ".qkvbias", (3 * blk.attn.q_bias.numel(),), torch.float32)
+                    _lib.pack_qkv_bias(blk.attn.q_bias.detach(), blk.attn.v_bias.detach(), qb)
         cast("e2d", m.encoder_to_decoder.weight)
         cast("head", m.decoder.head.weight)
 
@@ -485,8 +499,6 @@ class _Runner:
 
     def _capture(self, sv, si, sm, normalize_target, grad_scale):
         dev = self.device
-        if self.graph_pool is None:
-            self.graph_pool = torch.cuda.graph_pool_handle()
         graphs = []
         cur = {"g": None, "n0": 0}
         stream = torch.cuda.Stream(device=dev)
@@ -496,7 +508,7 @@ class _Runner:
         def begin():
             cur["g"] = torch.cuda.CUDAGraph()
             cur["n0"] = _lib.launch_count
-            cur["g"].capture_begin(pool=self.graph_pool)
+            cur["g"].capture_begin()       # private pool per segment: nothing is allocated while capturing
 
         def boundary(k):
             cur["g"].capture_end()

@@ -161,7 +161,7 @@ class NativeScalerWithGradNormCount:
         self._scale = 1.0
 
     def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True,
-                 arena=None):
+                 arena=None, loss_guard=False):
         """``arena``: the model's flat gradient arena when the gradients were produced by the fused step (the engine
         passes it); otherwise ``loss.backward()`` runs autograd through the model's kernel backward."""
         if arena is None:
@@ -176,8 +176,14 @@ class NativeScalerWithGradNormCount:
             assert parameters is not None
             parameters = list(parameters)
             norm = get_grad_norm_(parameters)
+        coef = None
         if clip_grad is not None and clip_grad > 0:          # engine passes max_norm (0 = off, as in the reference CLI)
-            coef = torch.clamp(clip_grad / (norm + 1e-6), max=1.0)
+            coef = torch.clamp(clip_grad / (norm + 1e-6), max=1.0).reshape(1)
+        if getattr(optimizer, "fused_mofo", False):
+            # one kernel: clip coefficient and the non-finite-loss guard are applied on the device
+            optimizer.step(clip_coef=coef, loss_guard=loss.detach().reshape(-1)[:1] if loss_guard else None)
+            return norm
+        if coef is not None:
             if arena is not None:
                 arena.mul_(coef)
             else:
