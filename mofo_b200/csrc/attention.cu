@@ -26,6 +26,12 @@ __device__ __forceinline__ void check_align(uint32_t base) {
   }
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {   // single FMNMX3 on sm_100
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // write 32 consecutive columns [c0, c0+32) (c0 = 0 or 32) of row `row` of a [128 x 64] bf16 K-major SW128 tile
 __device__ __forceinline__ void store_p_chunk(uint32_t tile_base, int row, int c0, const float (&v)[32]) {
   const int chunk0 = c0 >> 3;
@@ -56,9 +62,28 @@ __device__ __forceinline__ void mma_p_t(uint32_t d_tmem, uint32_t p_tile, uint32
 
 // =================================================================================================
 // forward: CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles (double buffered).
-// TMEM: S [0,64) | O_part [64,128).  smem 64.6 KB -> up to 3 CTAs / SM.
+// TMEM: S [0,64) | O [64,128).  smem 64.6 KB -> 3 CTAs / SM.
+// O accumulates in TMEM across the kv tiles (tcgen05.mma accumulate), so the threads never read it back inside the
+// loop.  The exponent reference m_ref is updated lazily: only when the running row maximum exceeds it by more than
+// 2^8 is the O row (and the row sum) rescaled in TMEM (tcgen05.ld / .st), which happens in the first tile(s) only;
+// otherwise p = exp2(t - m_ref) may exceed 1 (<= 256), harmless in bf16 / fp32.  The final lse is exact.
+// Per iteration there is ONE tensor-pipe round trip: thread 0 issues P(j)V(j) and S(j+1) back to back and the
+// single commit of S(j+1) also covers P(j)V(j) (the tensor pipe executes in order).
 // =================================================================================================
 constexpr int FWD_SMEM = TILE_BYTES + 4 * HTILE_BYTES + TILE_BYTES + 512 + 64;   // Q, K0,V0,K1,V1, P, max xchg, barriers
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 3)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int S, int H,
@@ -72,7 +97,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __nv_bfloat16* xch = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * TILE_BYTES + 4 * HTILE_BYTES);   // [2][128]
   float* xsum = reinterpret_cast<float*>(smem_raw + TILE_BYTES);                                        // aliases K/V at the end
   const uint32_t bars = base + 2 * TILE_BYTES + 4 * HTILE_BYTES + 512;
-  const uint32_t bar_q = bars, bar_s = bars + 8, bar_o = bars + 16, tmem_slot = bars + 40;
+  const uint32_t bar_q = bars, bar_s = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
   auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -82,7 +107,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int n_kv = (S + BT - 1) / BT;
 
   if (tid == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_kv(0), 1); mbar_init(bar_kv(1), 1);
+    mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_fin, 1); mbar_init(bar_kv(0), 1); mbar_init(bar_kv(1), 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
   }
@@ -101,96 +126,117 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_expect_tx(bar_kv(0), 2 * HTILE_BYTES);
     tma_load_2d(sK(0), &tm_kv, bar_kv(0), (H + h) * 64, row0);
     tma_load_2d(sV(0), &tm_kv, bar_kv(0), (2 * H + h) * 64, row0);
+    if (n_kv > 1) {
+      mbar_expect_tx(bar_kv(1), 2 * HTILE_BYTES);
+      tma_load_2d(sK(1), &tm_kv, bar_kv(1), (H + h) * 64, row0 + BT);
+      tma_load_2d(sV(1), &tm_kv, bar_kv(1), (2 * H + h) * 64, row0 + BT);
+    }
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_kv(0), 0);
+    tc_fence_after();
+    mma_ab_t(tmem_base, sQ, sK(0));                 // S(0)
+    tc_commit(bar_s);
   }
 
-  float o_acc[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) o_acc[e] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;   // l_run: partial row sum over this thread's columns
+  float m_ref = -INFINITY, l_run = 0.f;             // l_run: partial row sum over this thread's columns
 
   for (int j = 0; j < n_kv; ++j) {
     const int buf = j & 1;
-    if (tid == 0) {
-      if (j + 1 < n_kv) {   // prefetch next K/V tile (its buffer was released by bar_o of iteration j-1)
-        mbar_expect_tx(bar_kv(buf ^ 1), 2 * HTILE_BYTES);
-        tma_load_2d(sK(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * BT);
-        tma_load_2d(sV(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * BT);
-      }
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv(buf), (j >> 1) & 1);
-      tc_fence_after();
-      mma_ab_t(tmem_base, sQ, sK(buf));
-      tc_commit(bar_s);
-    }
-    mbar_wait(bar_s, j & 1);
+    mbar_wait(bar_s, j & 1);                        // S(j) ready; also: P(j-1)V(j-1) done -> P tile and K/V buffer buf^1 free
     tc_fence_after();
-    const int kv_valid = S - j * BT - half * 32;   // own columns >= kv_valid are padding (last tile only)
+    if (tid == 0 && j >= 1 && j + 1 < n_kv) {       // refill the buffer tile j-1 used with tile j+1
+      mbar_expect_tx(bar_kv(buf ^ 1), 2 * HTILE_BYTES);
+      tma_load_2d(sK(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * BT);
+      tma_load_2d(sV(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * BT);
+    }
+    const int kv_valid = S - j * BT - half * 32;    // own columns >= kv_valid are padding (last tile only)
     uint32_t r[32];
     tmem_ld32(tS, r);
     tc_wait_ld();
     float mx = -INFINITY;
     if (kv_valid >= 32) {
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+      for (int e = 0; e < 32; e += 8) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m4[k] = fmax3(m4[k], __uint_as_float(r[e + 2 * k]), __uint_as_float(r[e + 2 * k + 1]));
+      }
+      mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
     } else {
 #pragma unroll
       for (int e = 0; e < 32; ++e) if (e < kv_valid) mx = fmaxf(mx, __uint_as_float(r[e]));
     }
-    // exchange the two half-row maxima rounded UP to bf16: both threads of a row then use the identical reference
-    // value (any upper bound of the true maximum keeps exp2 <= 1; the lse below stays exact).
+    // the two half-row maxima are exchanged rounded UP to bf16: both threads of a row then take identical decisions
     xch[half * 128 + row] = __float2bfloat16_ru(mx);
     __syncthreads();
-    mx = fmaxf(__bfloat162float(xch[row]), __bfloat162float(xch[128 + row]));
-    const float m_new = fmaxf(m_run, mx * c);
-    const float alpha = exp2f(m_run - m_new);
+    mx = fmaxf(__bfloat162float(xch[row]), __bfloat162float(xch[128 + row])) * c;
+    // lazy exponent reference: move it (and rescale l and the O row) only when the maximum grew by more than 2^8
+    const bool bump = mx > m_ref + 8.0f;            // always true in the first tile (m_ref = -inf)
+    if (__any_sync(0xffffffffu, bump) && j > 0) {
+      const float alpha = bump ? exp2f(m_ref - mx) : 1.0f;
+      uint32_t o[32];
+      tmem_ld32(tO, o);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+      tmem_st32(tO, o);
+      l_run *= alpha;
+    }
+    if (bump) m_ref = mx;
     float rs = 0.f;
     float p[32];
     if (kv_valid >= 32) {
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 32; ++e) { p[e] = exp2f(__uint_as_float(r[e]) * c - m_new); rs += p[e]; }
+      for (int e = 0; e < 32; ++e) { p[e] = exp2f(__uint_as_float(r[e]) * c - m_ref); s4[e & 3] += p[e]; }
+      rs = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) { p[e] = (e < kv_valid) ? exp2f(__uint_as_float(r[e]) * c - m_new) : 0.f; rs += p[e]; }
+      for (int e = 0; e < 32; ++e) { p[e] = (e < kv_valid) ? exp2f(__uint_as_float(r[e]) * c - m_ref) : 0.f; rs += p[e]; }
     }
     store_p_chunk(sP, row, half * 32, p);
-    l_run = l_run * alpha + rs;
-    m_run = m_new;
+    l_run += rs;
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_p_t(tmem_base + 64, sP, sV(buf), false);
-      tc_commit(bar_o);
+      mma_p_t(tmem_base + 64, sP, sV(buf), j != 0);            // O += P(j) V(j)
+      if (j + 1 < n_kv) {
+        mbar_wait(bar_kv(buf ^ 1), ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        mma_ab_t(tmem_base, sQ, sK(buf ^ 1));                   // S(j+1)
+        tc_commit(bar_s);
+      } else {
+        tc_commit(bar_fin);
+      }
     }
-    mbar_wait(bar_o, j & 1);
-    tc_fence_after();
-    tmem_ld32(tO, r);
-    tc_wait_ld();
-#pragma unroll
-    for (int e = 0; e < 32; ++e) o_acc[e] = o_acc[e] * alpha + __uint_as_float(r[e]);
-    tc_fence_before();
   }
 
-  __syncthreads();                      // every MMA has completed (bar_o of the last iteration): K/V smem is free
+  mbar_wait(bar_fin, 0);                // every MMA has completed: O is final, K/V smem is free
+  tc_fence_after();
   xsum[half * 128 + row] = l_run;
   __syncthreads();
   const float l_tot = xsum[row] + xsum[128 + row];
+  uint32_t o[32];
+  tmem_ld32(tO, o);
+  tc_wait_ld();
   const int q = q0 + row;
   if (q < S) {
     const float inv = 1.0f / l_tot;
     __nv_bfloat16* dst = out + (static_cast<size_t>(row0 + q) * H + h) * 64 + half * 32;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      uint4 o;
-      o.x = pack_bf16(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
-      o.y = pack_bf16(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
-      o.z = pack_bf16(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
-      o.w = pack_bf16(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
-      reinterpret_cast<uint4*>(dst)[g] = o;
+      uint4 v;
+      v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+      v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+      v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+      v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+      reinterpret_cast<uint4*>(dst)[g] = v;
     }
-    if (half == 0) lse[(static_cast<size_t>(b) * H + h) * S + q] = m_run + log2f(l_tot);
+    if (half == 0) lse[(static_cast<size_t>(b) * H + h) * S + q] = m_ref + log2f(l_tot);
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
@@ -427,21 +473,25 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     tmem_ld32(tS, rs);
     tmem_ld32(tdP, rp);
     tc_wait_ld();
-    float p[32];
+    float p[32], st[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(st + 4 * g) = reinterpret_cast<const float4*>(lse_s)[g];
     if (q_valid >= 32) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) p[e] = exp2f(__uint_as_float(rs[e]) * c - lse_s[e]);
+      for (int e = 0; e < 32; ++e) p[e] = exp2f(__uint_as_float(rs[e]) * c - st[e]);
     } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? exp2f(__uint_as_float(rs[e]) * c - lse_s[e]) : 0.f;
+      for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? exp2f(__uint_as_float(rs[e]) * c - st[e]) : 0.f;
     }
     store_p_chunk(sP, row, half * 32, p);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(st + 4 * g) = reinterpret_cast<const float4*>(del_s)[g];
     if (q_valid >= 32) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) p[e] *= (__uint_as_float(rp[e]) - del_s[e]);
+      for (int e = 0; e < 32; ++e) p[e] *= (__uint_as_float(rp[e]) - st[e]);
     } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? p[e] * (__uint_as_float(rp[e]) - del_s[e]) : 0.f;
+      for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? p[e] * (__uint_as_float(rp[e]) - st[e]) : 0.f;
     }
     store_p_chunk(sdS, row, half * 32, p);
     fence_proxy_async_smem();
