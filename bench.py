@@ -311,8 +311,35 @@ def run_ours(args):
         c0.record(); db.copy_(hb, non_blocking=True); c1.record(); torch.cuda.synchronize()
         h2d_gbps = hb.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
         del hb, db
+        def run_epoch(loader):
+            eng.train_one_epoch_BB(model, loader, opt, dev, 0, scaler, max_norm=0, patch_size=16, normlize_target=True, start_steps=0)
+
+        def timed_epoch(make_loader):
+            run_epoch(make_loader(max(3, args.warmup)))
+            loader = make_loader(args.steps)
+            barrier()
+            t0 = time.perf_counter()
+            run_epoch(loader)
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return dt.item()
+
+        # extension: the host ships raw uint8 clips, ToTorchFormatTensor+GroupNormalize run on the GPU
+        class HostLoaderU8(HostLoader):
+            def __init__(self, n):
+                self.n = n
+                gcpu = torch.Generator().manual_seed(77 + rank)
+                self.batches = []
+                for i in range(2):
+                    _, bb, words = pool[i]
+                    mask = gen.generate_batch(bb, words)[0]
+                    u8 = torch.randint(0, 256, (B, 3, 16, 224, 224), dtype=torch.uint8, generator=gcpu).pin_memory()
+                    self.batches.append((u8, bb.long().cpu()[:, None, :].expand(B, 16, 4).contiguous(), mask.double().cpu().pin_memory()))
+        dt_u8 = timed_epoch(HostLoaderU8)
         loader = HostLoader(max(3, args.warmup))
-        eng.train_one_epoch_BB(model, loader, opt, dev, 0, scaler, max_norm=0, patch_size=16, normlize_target=True, start_steps=0)
+        run_epoch(loader)
         loader = HostLoader(args.steps)
         barrier()
         t0 = time.perf_counter()
@@ -327,7 +354,9 @@ def run_ours(args):
                "ms_per_step": 1e3 * dt.item() / args.steps, "h2d_pinned_gbps": h2d_gbps,
                "h2d_ms_per_step_at_that_rate": vid_bytes / h2d_gbps / 1e6,
                "api": "mofo_b200.engine_for_pretraining.train_one_epoch_BB, pinned fp32 clips + f64 masks per step "
-                      "(H2D of batch i+1 overlaps step i on a copy stream)"}
+                      "(H2D of batch i+1 overlaps step i on a copy stream)",
+               "uint8_input": {"value": B * world * args.steps / dt_u8, "unit": "clips/s", "h2d_bytes_per_step": vid_bytes // 4 + B * 1568 * 8,
+                               "note": "same engine call fed raw uint8 clips (1 B/sample); normalisation on the GPU (mofo_normalize_u8)"}}
 
     if rank != 0:
         if world > 1:

@@ -182,6 +182,13 @@ int mofo_colsum_bf16(const mofo_bf16* X, int ldx, int M, int N, float* out, void
 int mofo_sq_norm_f32(const float* x, int64_t n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * (8b) On-GPU input normalisation (first piece): uint8 clip [B,3,frames,size,size] (NCTHW) ->
+ * f32 (x/255 - mean_c)/std_c with the ImageNet constants, bit-identical to ToTorchFormatTensor(div=True) +
+ * GroupNormalize (datasets.py:44-50, transforms.py:346-382).  Lets the host ship 1 byte per sample instead of 4.
+ */
+int mofo_normalize_u8(const uint8_t* clip_u8, int B, int frames, int size, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * (9) Fused AdamW over the flat arenas.  Replaces torch.optim.AdamW.step() as created by
  * optim_factory.create_optimizer (optim_factory.py:126-127) and driven by utils.py:355-364 (clip + step), plus the
  * per-step fp32->bf16 operand casts.  params / grads / exp_avg / exp_avg_sq are f32 arenas with identical layout.

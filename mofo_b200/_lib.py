@@ -40,6 +40,7 @@ SIGNATURES = {
     "mofo_pack_qkv_bias": ([_P, _P, _I, _P, _P], C.c_int),
     "mofo_colsum_bf16": ([_P, _I, _I, _I, _P, _P], C.c_int),
     "mofo_sq_norm_f32": ([_P, _L, _P, _P], C.c_int),
+    "mofo_normalize_u8": ([_P, _I, _I, _I, _P, _P], C.c_int),
     "mofo_adamw_step": ([_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P], C.c_int),
 }
 
@@ -286,3 +287,11 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, w16, segs, tiles, hyper, clip
     _check(load().mofo_adamw_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(w16), _ptr(segs),
                                   _ptr(tiles), tiles.shape[0], _ptr(hyper), _ptr(clip_coef), _ptr(loss_guard), _stream()),
            "mofo_adamw_step")
+
+
+def normalize_u8(clip_u8, out):
+    """uint8 [B,3,T,H,W] -> ImageNet-normalised f32 (same shape), on the current stream."""
+    B, Cc, frames, size, _ = clip_u8.shape
+    assert Cc == 3 and clip_u8.dtype == torch.uint8 and clip_u8.is_contiguous() and out.dtype == torch.float32
+    _check(load().mofo_normalize_u8(_ptr(clip_u8), B, frames, size, _ptr(out), _stream()), "mofo_normalize_u8")
+    return out

@@ -543,6 +543,29 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
+// uint8 NCTHW clip -> ImageNet-normalised f32 (ToTorchFormatTensor(div=True) + GroupNormalize, datasets.py:44-50):
+// v = float(x) / 255; out = (v - mean_c) / std_c, with the same two roundings per step as the torch ops.
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
+                                                           int64_t n16, int64_t plane16) {
+  const float mean_c[3] = {0.485f, 0.456f, 0.406f}, std_c[3] = {0.229f, 0.224f, 0.225f};
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>((i / plane16) % 3);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float4* o = reinterpret_cast<float4*>(out) + 4 * i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 r;
+      r.x = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(w[k] & 0xffu), 255.0f), mean_c[c]), std_c[c]);
+      r.y = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>((w[k] >> 8) & 0xffu), 255.0f), mean_c[c]), std_c[c]);
+      r.z = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>((w[k] >> 16) & 0xffu), 255.0f), mean_c[c]), std_c[c]);
+      r.w = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(w[k] >> 24), 255.0f), mean_c[c]), std_c[c]);
+      o[k] = r;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) sq_norm_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
   __shared__ float sh[8];
   float s = 0.f;
@@ -735,6 +758,17 @@ int mofo_colsum_bf16(const mofo_bf16* X, int ldx, int M, int N, float* out, void
   dim3 grid((N + 255) / 256, (M + rows_per_cta - 1) / rows_per_cta);
   colsum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(X), ldx, M, N, rows_per_cta, out);
   MOFO_LAUNCH_CHECK("colsum_bf16_kernel");
+  return MOFO_OK;
+}
+
+int mofo_normalize_u8(const uint8_t* clip_u8, int B, int frames, int size, float* out, void* stream) {
+  MOFO_CHECK_ARG(clip_u8 && out && B > 0 && frames > 0 && size > 0, "normalize_u8: bad argument");
+  const int64_t plane = static_cast<int64_t>(frames) * size * size;
+  MOFO_CHECK_ARG(plane % 16 == 0 && (reinterpret_cast<uintptr_t>(clip_u8) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "normalize_u8: frames*size*size must be a multiple of 16 and buffers 16-byte aligned");
+  const int64_t n16 = static_cast<int64_t>(B) * 3 * plane / 16;
+  normalize_u8_kernel<<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(clip_u8, out, n16, plane / 16);
+  MOFO_LAUNCH_CHECK("normalize_u8_kernel");
   return MOFO_OK;
 }
 

@@ -138,6 +138,8 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
                 grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=core.parameters(), arena=arena)
         else:
             vis_idx, msk_idx = core.indices_from_mask(bool_masked_pos)
+            if videos.dtype == torch.uint8:
+                videos = _lib.normalize_u8(videos.contiguous(), torch.empty(videos.shape, dtype=torch.float32, device=videos.device))
             with torch.no_grad():
                 labels = build_labels(videos.float().contiguous(), msk_idx, normlize_target)
             outputs = model(videos, bool_masked_pos)

@@ -661,11 +661,18 @@ class PretrainVisionTransformer(nn.Module):
         """One fused pass: forward, target + MSE (engine_for_pretraining.py:258-304) and backward.  Gradients are
         accumulated into the flat arena (``p.grad`` views).  Returns the loss as a 1-element CUDA tensor (no sync)."""
         self._require_cuda(videos)
-        videos = videos.float().contiguous()
-        if vis_idx is None:
-            vis_idx, msk_idx = self.indices_from_mask(mask)
         r = self._runner
         r._ensure_device(videos.device)
+        if vis_idx is None:
+            vis_idx, msk_idx = self.indices_from_mask(mask)
+        if videos.dtype == torch.uint8:
+            # raw uint8 clip (NCTHW): ToTorchFormatTensor + GroupNormalize on the GPU, written straight into the buffer
+            # the step's graphs read (mofo_normalize_u8); the host ships 1 byte per sample instead of 4
+            B, _, frames, size, _ = videos.shape
+            sv = r.static_inputs(B, vis_idx.shape[1], msk_idx.shape[1], frames, size)[0]
+            videos = _lib.normalize_u8(videos.contiguous(), sv)
+        else:
+            videos = videos.float().contiguous()
         with torch.no_grad():
             if self.use_cuda_graph and zero_grad:
                 return r.step_graphed(videos, vis_idx, msk_idx, normalize_target, grad_scale, stage_done)

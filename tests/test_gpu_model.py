@@ -146,3 +146,9 @@ def test_training_reduces_loss_and_matches_oracle_trajectory():
     final = model.pretrain_step(vid.cuda(), mask.cuda()).item()
     assert final < ref_losses[0] * 0.98
     assert abs(stats["loss"] - float(np.mean(ref_losses))) < 2e-2 * float(np.mean(ref_losses)), (stats["loss"], np.mean(ref_losses))
+
+
+def test_vit_large_c4_step_matches_oracle():
+    """BASELINE.json configs[3] architecture (pretrain_videomae_large_patch16_224, decoder depth 4), 1 clip."""
+    rep, *_ = compare(mdl.CONFIGS["pretrain_videomae_large_patch16_224"], B=1)
+    check(rep)

@@ -212,3 +212,30 @@ def test_helpers(lib):
     o = torch.zeros(1, device="cuda")
     lib.sq_norm_f32(x, o)
     assert abs(o.item() - (x.double() ** 2).sum().item()) < 1e-4 * o.item()
+
+
+def test_normalize_u8_bit_exact_and_step_equivalence(lib):
+    """uint8 input path: bit-identical to ToTorchFormatTensor(div=True) + GroupNormalize (datasets.py:44-50) on CPU."""
+    g = torch.Generator().manual_seed(4)
+    u8 = torch.randint(0, 256, (2, 3, 16, 64, 64), dtype=torch.uint8, generator=g)
+    out = torch.empty(u8.shape, dtype=torch.float32, device="cuda")
+    lib.normalize_u8(u8.cuda(), out)
+    mean = torch.tensor((0.485, 0.456, 0.406))[None, :, None, None, None]
+    std = torch.tensor((0.229, 0.224, 0.225))[None, :, None, None, None]
+    ref = u8.float().div(255).sub_(mean).div_(std)
+    assert torch.equal(out.cpu(), ref)
+    # the fused step gives the same loss for the raw uint8 clip and for its normalised fp32 version
+    from functools import partial
+    from mofo_b200 import modeling_pretrain as mp
+    from oracle import model_oracle as mdl
+    cfg = mdl.tiny_config(img=64, frames=16)
+    m = mp.PretrainVisionTransformer(img_size=64, patch_size=16, encoder_embed_dim=cfg.enc_dim, encoder_depth=cfg.enc_depth,
+                                     encoder_num_heads=cfg.enc_heads, decoder_embed_dim=cfg.dec_dim, decoder_depth=cfg.dec_depth,
+                                     decoder_num_heads=cfg.dec_heads, mlp_ratio=4, qkv_bias=True,
+                                     norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    m.load_state_dict(mdl.random_state_dict(cfg, seed=2, perturb=0.05)); m.cuda()
+    masks = np.stack([mo.tube_mask_bb([[8, 8, 40, 40]] * 16, mo.mt19937_words(b, 300), cfg.grid)[0] for b in range(2)])
+    mask = torch.from_numpy(masks).bool().cuda()
+    l_u8 = m.pretrain_step(u8.cuda(), mask).item()
+    l_f32 = m.pretrain_step(ref.cuda(), mask).item()
+    assert l_u8 == l_f32
