@@ -264,11 +264,12 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
 
 // =================================================================================================
 // backward, part 1: dQ.  CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles.
-// TMEM: S [0,64) | dP [64,128) | dQ [128,192) (256 allocated) -> 2 CTAs / SM.  smem 80 KB.
+// TMEM: S [0,64) | dP [64,128) | dQ [128,192) (256 allocated) -> 2 CTAs / SM.  smem 112 KB (4-stage K/V ring).
 // Rows q >= S and kv >= S: garbage rows only pollute their own (never stored) output rows, so only the
 // reduction (column) index is masked, and only in the last tile.
 // =================================================================================================
-constexpr int DQ_SMEM = 2 * TILE_BYTES + 4 * HTILE_BYTES + TILE_BYTES + 64;   // Q, dO, K0,V0,K1,V1, dS
+constexpr int DQ_NST = 4;                                                       // K/V ring depth (prefetch distance 3)
+constexpr int DQ_SMEM = 2 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES + TILE_BYTES + 64;   // Q, dO, K/V ring, dS
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
@@ -277,11 +278,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   check_align(base);
-  const uint32_t sQ = base, sdO = base + TILE_BYTES, sdS = base + 2 * TILE_BYTES + 4 * HTILE_BYTES;
+  const uint32_t sQ = base, sdO = base + TILE_BYTES, sdS = base + 2 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES;
   auto sK = [&](int b) { return base + 2 * TILE_BYTES + (2 * b) * HTILE_BYTES; };
   auto sV = [&](int b) { return base + 2 * TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
-  const uint32_t bars = base + 3 * TILE_BYTES + 4 * HTILE_BYTES;
-  const uint32_t bar_q = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
+  const uint32_t bars = base + 3 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES;
+  const uint32_t bar_q = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 56;
   auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -289,9 +290,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int q0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * S;
   const int n_kv = (S + BT - 1) / BT;
+  auto load_kv = [&](int t) {      // thread 0: tile t -> ring stage t % DQ_NST
+    const int st = t % DQ_NST;
+    mbar_expect_tx(bar_kv(st), 2 * HTILE_BYTES);
+    tma_load_2d(sK(st), &tm_kv, bar_kv(st), (H + h) * 64, row0 + t * BT);
+    tma_load_2d(sV(st), &tm_kv, bar_kv(st), (2 * H + h) * 64, row0 + t * BT);
+  };
 
   if (tid == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1); mbar_init(bar_kv(0), 1); mbar_init(bar_kv(1), 1);
+    mbar_init(bar_q, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1);
+    for (int st = 0; st < DQ_NST; ++st) mbar_init(bar_kv(st), 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do);
   }
@@ -314,9 +322,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     mbar_expect_tx(bar_q, 2 * TILE_BYTES);
     tma_load_2d(sQ, &tm_q, bar_q, h * 64, row0 + q0);
     tma_load_2d(sdO, &tm_do, bar_q, h * 64, row0 + q0);
-    mbar_expect_tx(bar_kv(0), 2 * HTILE_BYTES);
-    tma_load_2d(sK(0), &tm_kv, bar_kv(0), (H + h) * 64, row0);
-    tma_load_2d(sV(0), &tm_kv, bar_kv(0), (2 * H + h) * 64, row0);
+    for (int t = 0; t < DQ_NST - 1 && t < n_kv; ++t) load_kv(t);
     mbar_wait(bar_q, 0);
     mbar_wait(bar_kv(0), 0);
     tc_fence_after();
@@ -326,14 +332,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
 
   for (int j = 0; j < n_kv; ++j) {
-    const int buf = j & 1;
-    mbar_wait(bar_12, j & 1);   // also covers the dQ MMA of iteration j-1 (tensor pipe is in-order)
+    const int buf = j % DQ_NST, nbuf = (j + 1) % DQ_NST;
+    mbar_wait(bar_12, j & 1);   // also covers the dQ MMA of iteration j-1 (tensor pipe is in-order) -> stage (j-1)%NST is free
     tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {
-      mbar_expect_tx(bar_kv(buf ^ 1), 2 * HTILE_BYTES);
-      tma_load_2d(sK(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * BT);
-      tma_load_2d(sV(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * BT);
-    }
+    if (tid == 0 && j + DQ_NST - 1 < n_kv) load_kv(j + DQ_NST - 1);
     const int kv_valid = S - j * BT - half * 32;
     uint32_t rs[32], rp[32];
     tmem_ld32(tS, rs);
@@ -357,10 +359,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_after();
       mma_p_t(tmem_base + 128, sdS, sK(buf), j != 0);          // dQ += dS K
       if (j + 1 < n_kv) {
-        mbar_wait(bar_kv(buf ^ 1), ((j + 1) >> 1) & 1);
+        mbar_wait(bar_kv(nbuf), ((j + 1) / DQ_NST) & 1);
         tc_fence_after();
-        mma_ab_t(tmem_base, sQ, sK(buf ^ 1));
-        mma_ab_t(tmem_base + 64, sdO, sV(buf ^ 1));
+        mma_ab_t(tmem_base, sQ, sK(nbuf));
+        mma_ab_t(tmem_base + 64, sdO, sV(nbuf));
         tc_commit(bar_12);
       } else {
         tc_commit(bar_fin);
@@ -393,9 +395,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 // =================================================================================================
 // backward, part 2: dK, dV.  CTA = 128 kv rows of one (clip, head); streams 64-row Q/dO tiles.
-// TMEM: S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256) -> 2 CTAs / SM.  smem 97 KB.
+// TMEM: S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256) -> 2 CTAs / SM.  smem 112.6 KB (3-stage Q/dO ring).
 // =================================================================================================
-constexpr int DKV_SMEM = 2 * TILE_BYTES + 4 * HTILE_BYTES + 2 * TILE_BYTES + 1024 + 64;   // K,V, Q0,dO0,Q1,dO1, P^T, dS^T, stats
+constexpr int DKV_NST = 3;                                                            // Q/dO ring depth (prefetch distance 2)
+constexpr int DKV_SMEM = 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 2 * TILE_BYTES + 512 + 64;   // K,V, Q/dO ring, P^T, dS^T, stats
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
@@ -405,12 +408,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
   const uint32_t base = smem_u32(smem_raw);
   check_align(base);
   const uint32_t sK = base, sV = base + TILE_BYTES;
-  const uint32_t sP = base + 2 * TILE_BYTES + 4 * HTILE_BYTES, sdS = sP + TILE_BYTES;
+  const uint32_t sP = base + 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES, sdS = sP + TILE_BYTES;
   auto sQ = [&](int b) { return base + 2 * TILE_BYTES + (2 * b) * HTILE_BYTES; };
   auto sdO = [&](int b) { return base + 2 * TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
-  float* vec = reinterpret_cast<float*>(smem_raw + 4 * TILE_BYTES + 4 * HTILE_BYTES);   // [2 buffers][lse 64 | delta 64]
-  const uint32_t bars = base + 4 * TILE_BYTES + 4 * HTILE_BYTES + 1024;
-  const uint32_t bar_kv = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
+  float* vec = reinterpret_cast<float*>(smem_raw + 4 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES);   // [lse 64 | delta 64]
+  const uint32_t bars = base + 4 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 512;
+  const uint32_t bar_kv = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 56;
   auto bar_q = [&](int b) { return bars + 24 + 8 * b; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -418,9 +421,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
   const int kv0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * S;
   const int n_q = (S + BT - 1) / BT;
+  auto load_q = [&](int t) {       // thread 0: q tile t -> ring stage t % DKV_NST
+    const int st = t % DKV_NST;
+    mbar_expect_tx(bar_q(st), 2 * HTILE_BYTES);
+    tma_load_2d(sQ(st), &tm_q, bar_q(st), h * 64, row0 + t * BT);
+    tma_load_2d(sdO(st), &tm_do, bar_q(st), h * 64, row0 + t * BT);
+  };
 
   if (tid == 0) {
-    mbar_init(bar_kv, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1); mbar_init(bar_q(0), 1); mbar_init(bar_q(1), 1);
+    mbar_init(bar_kv, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1);
+    for (int st = 0; st < DKV_NST; ++st) mbar_init(bar_q(st), 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do);
   }
@@ -440,9 +450,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     mbar_expect_tx(bar_kv, 2 * TILE_BYTES);
     tma_load_2d(sK, &tm_kv, bar_kv, (H + h) * 64, row0 + kv0);
     tma_load_2d(sV, &tm_kv, bar_kv, (2 * H + h) * 64, row0 + kv0);
-    mbar_expect_tx(bar_q(0), 2 * HTILE_BYTES);
-    tma_load_2d(sQ(0), &tm_q, bar_q(0), h * 64, row0);
-    tma_load_2d(sdO(0), &tm_do, bar_q(0), h * 64, row0);
+    for (int t = 0; t < DKV_NST - 1 && t < n_q; ++t) load_q(t);
     mbar_wait(bar_kv, 0);
     mbar_wait(bar_q(0), 0);
     tc_fence_after();
@@ -451,23 +459,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     tc_commit(bar_12);
   }
 
+  // per-column (q) statistics: threads 0-63 fetch lse, 64-127 fetch delta, one tile AHEAD into a register, so the
+  // global-load latency never sits between the MMA hand-off and the softmax recompute
+  const float* stat_src = (tid < 64 ? lse : delta) + (static_cast<size_t>(b) * H + h) * S;
+  float stat_next = (tid < 128 && (tid & 63) < S) ? stat_src[tid & 63] : 0.f;
   for (int i = 0; i < n_q; ++i) {
-    const int buf = i & 1;
-    if (tid < 128) {   // per-column (q) statistics of this q tile: threads 0-63 fetch lse, 64-127 fetch delta
-      const int qq = i * BT + (tid & 63);
-      const float* src = tid < 64 ? lse : delta;
-      vec[buf * 128 + tid] = qq < S ? src[(static_cast<size_t>(b) * H + h) * S + qq] : 0.f;
+    const int buf = i % DKV_NST, nbuf = (i + 1) % DKV_NST;
+    if (tid < 128) {   // vec[] was last read before the second __syncthreads of iteration i-1
+      vec[tid] = stat_next;
+      const int qq = (i + 1) * BT + (tid & 63);
+      stat_next = qq < S ? stat_src[qq] : 0.f;
     }
-    mbar_wait(bar_12, i & 1);    // also covers the dV/dK MMAs of iteration i-1
+    mbar_wait(bar_12, i & 1);    // also covers the dV/dK MMAs of iteration i-1 -> ring stage (i-1)%NST is free
     tc_fence_after();
     __syncthreads();             // vec[] visible
-    if (tid == 0 && i + 1 < n_q) {
-      mbar_expect_tx(bar_q(buf ^ 1), 2 * HTILE_BYTES);
-      tma_load_2d(sQ(buf ^ 1), &tm_q, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * BT);
-      tma_load_2d(sdO(buf ^ 1), &tm_do, bar_q(buf ^ 1), h * 64, row0 + (i + 1) * BT);
-    }
+    if (tid == 0 && i + DKV_NST - 1 < n_q) load_q(i + DKV_NST - 1);
     const int q_valid = S - i * BT - half * 32;
-    const float* lse_s = vec + buf * 128 + half * 32;
+    const float* lse_s = vec + half * 32;
     const float* del_s = lse_s + 64;
     uint32_t rs[32], rp[32];
     tmem_ld32(tS, rs);
@@ -502,10 +510,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
       mma_p_t(tmem_base + 128, sP, sdO(buf), i != 0);       // dV += P^T dO
       mma_p_t(tmem_base + 192, sdS, sQ(buf), i != 0);       // dK += dS^T Q
       if (i + 1 < n_q) {
-        mbar_wait(bar_q(buf ^ 1), ((i + 1) >> 1) & 1);
+        mbar_wait(bar_q(nbuf), ((i + 1) / DKV_NST) & 1);
         tc_fence_after();
-        mma_ab_t(tmem_base, sK, sQ(buf ^ 1));
-        mma_ab_t(tmem_base + 64, sV, sdO(buf ^ 1));
+        mma_ab_t(tmem_base, sK, sQ(nbuf));
+        mma_ab_t(tmem_base + 64, sV, sdO(nbuf));
         tc_commit(bar_12);
       } else {
         tc_commit(bar_fin);
