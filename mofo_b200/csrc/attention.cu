@@ -5,7 +5,8 @@
 // All three kernels use 128 threads: thread r owns TMEM lane r = one row of the 128-row tile, so the
 // softmax needs no cross-thread reduction.  Thread 0 additionally issues TMA loads and tcgen05.mma.
 //   S = Q K^T and friends:  both operands K-major SW128 tiles [128 rows x 64 d] straight from TMA.
-//   P V / dS K / P^T dO ...: A = bf16 tile written by the threads into a K-major SW128 layout,
+//   P V / dS K / P^T dO ...: A = bf16 operand written by the threads straight into TENSOR MEMORY (tcgen05.st over their
+//                            own fp32 accumulator columns; tcgen05.mma with A in TMEM), so it never touches shared memory;
 //                            B = the same TMA tile re-read as an MN-major operand (rows = reduction index).
 // Everything is kept in the log2 domain: t = s * scale * log2(e), p = exp2(t - lse2).
 #include "../../include/mofo_b200.h"
@@ -60,9 +61,44 @@ __device__ __forceinline__ void mma_p_t(uint32_t d_tmem, uint32_t p_tile, uint32
   for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 128 * k, idesc, (accumulate || k != 0) ? 1u : 0u);
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// D[128 x 64] (+)= P[128 x 64 bf16, in TMEM: lane = row, column k/2 holds elements (k, k+1)] · T[64 x 64] (MN-major smem)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The bf16 operand is written by the threads over their OWN fp32 accumulator columns: the thread pair of a row owns
+// fp32 columns [0,32) and [32,64) of a 64-column region and stores its 32 bf16 values (16 packed columns) at region
+// columns [0,16) resp. [32,48).  K-steps of 16 elements therefore start at columns {0, 8, 32, 40}.
+__device__ __forceinline__ void mma_ptmem_t(uint32_t d_tmem, uint32_t p_tmem, uint32_t t_tile, bool accumulate) {
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+  const uint64_t b0 = umma_desc_mnmajor(t_tile, 8192);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16_ts(d_tmem, p_tmem + (k >> 1) * 32 + (k & 1) * 8, b0 + 128 * k, idesc, (accumulate || k != 0) ? 1u : 0u);
+}
+__device__ __forceinline__ void tmem_store_bf16_row(uint32_t taddr, const float (&v)[32]) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+  tmem_st16(taddr, pk);
+}
 // =================================================================================================
 // forward: CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles (double buffered).
-// TMEM: S [0,64) | O [64,128).  smem 64.6 KB -> 3 CTAs / SM.
+// TMEM: S [0,64) (P aliases it) | O [64,128).  smem 48.6 KB, 3 CTAs / SM.
 // O accumulates in TMEM across the kv tiles (tcgen05.mma accumulate), so the threads never read it back inside the
 // loop.  The exponent reference m_ref is updated lazily: only when the running row maximum exceeds it by more than
 // 2^8 is the O row (and the row sum) rescaled in TMEM (tcgen05.ld / .st), which happens in the first tile(s) only;
@@ -70,7 +106,7 @@ __device__ __forceinline__ void mma_p_t(uint32_t d_tmem, uint32_t p_tile, uint32
 // Per iteration there is ONE tensor-pipe round trip: thread 0 issues P(j)V(j) and S(j+1) back to back and the
 // single commit of S(j+1) also covers P(j)V(j) (the tensor pipe executes in order).
 // =================================================================================================
-constexpr int FWD_SMEM = TILE_BYTES + 4 * HTILE_BYTES + TILE_BYTES + 512 + 64;   // Q, K0,V0,K1,V1, P, max xchg, barriers
+constexpr int FWD_SMEM = TILE_BYTES + 4 * HTILE_BYTES + 512 + 64;   // Q, K0,V0,K1,V1, max xchg, barriers
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -91,12 +127,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   check_align(base);
-  const uint32_t sQ = base, sP = base + TILE_BYTES + 4 * HTILE_BYTES;
+  const uint32_t sQ = base;
   auto sK = [&](int b) { return base + TILE_BYTES + (2 * b) * HTILE_BYTES; };
   auto sV = [&](int b) { return base + TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
-  __nv_bfloat16* xch = reinterpret_cast<__nv_bfloat16*>(smem_raw + 2 * TILE_BYTES + 4 * HTILE_BYTES);   // [2][128]
-  float* xsum = reinterpret_cast<float*>(smem_raw + TILE_BYTES);                                        // aliases K/V at the end
-  const uint32_t bars = base + 2 * TILE_BYTES + 4 * HTILE_BYTES + 512;
+  __nv_bfloat16* xch = reinterpret_cast<__nv_bfloat16*>(smem_raw + TILE_BYTES + 4 * HTILE_BYTES);   // [2][128]
+  float* xsum = reinterpret_cast<float*>(smem_raw + TILE_BYTES);                                    // aliases K/V at the end
+  const uint32_t bars = base + TILE_BYTES + 4 * HTILE_BYTES + 512;
   const uint32_t bar_q = bars, bar_s = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 40;
   auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
 
@@ -194,14 +230,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 32; ++e) { p[e] = (e < kv_valid) ? exp2f(__uint_as_float(r[e]) * c - m_ref) : 0.f; rs += p[e]; }
     }
-    store_p_chunk(sP, row, half * 32, p);
+    {   // P (bf16) goes to TMEM over this thread's own S columns (already in registers): no smem tile, no proxy fence
+      tmem_store_bf16_row(tmem_base + lane_off + half * 32, p);
+    }
     l_run += rs;
-    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_p_t(tmem_base + 64, sP, sV(buf), j != 0);            // O += P(j) V(j)
+      mma_ptmem_t(tmem_base + 64, tmem_base, sV(buf), j != 0);   // O += P(j) V(j), P read from TMEM
       if (j + 1 < n_kv) {
         mbar_wait(bar_kv(buf ^ 1), ((j + 1) >> 1) & 1);
         tc_fence_after();
@@ -264,12 +301,12 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
 
 // =================================================================================================
 // backward, part 1: dQ.  CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles.
-// TMEM: S [0,64) | dP [64,128) | dQ [128,192) (256 allocated) -> 2 CTAs / SM.  smem 112 KB (4-stage K/V ring).
+// TMEM: S [0,64) | dP [64,128) | dQ [128,192) (256 allocated) -> 2 CTAs / SM.  smem 96 KB (4-stage K/V ring); dS aliases S in TMEM.
 // Rows q >= S and kv >= S: garbage rows only pollute their own (never stored) output rows, so only the
 // reduction (column) index is masked, and only in the last tile.
 // =================================================================================================
 constexpr int DQ_NST = 4;                                                       // K/V ring depth (prefetch distance 3)
-constexpr int DQ_SMEM = 2 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES + TILE_BYTES + 64;   // Q, dO, K/V ring, dS
+constexpr int DQ_SMEM = 2 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES + 64;   // Q, dO, K/V ring
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
@@ -278,10 +315,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   check_align(base);
-  const uint32_t sQ = base, sdO = base + TILE_BYTES, sdS = base + 2 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES;
+  const uint32_t sQ = base, sdO = base + TILE_BYTES;
   auto sK = [&](int b) { return base + 2 * TILE_BYTES + (2 * b) * HTILE_BYTES; };
   auto sV = [&](int b) { return base + 2 * TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
-  const uint32_t bars = base + 3 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES;
+  const uint32_t bars = base + 2 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES;
   const uint32_t bar_q = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 56;
   auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
 
@@ -351,13 +388,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int e = 0; e < 32; ++e)
         ds[e] = (e < kv_valid) ? exp2f(__uint_as_float(rs[e]) * c - my_lse) * (__uint_as_float(rp[e]) - my_delta) : 0.f;
     }
-    store_p_chunk(sdS, row, half * 32, ds);
-    fence_proxy_async_smem();
+    tmem_store_bf16_row(tS, ds);                               // dS (bf16) over this thread's own S columns
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_p_t(tmem_base + 128, sdS, sK(buf), j != 0);          // dQ += dS K
+      mma_ptmem_t(tmem_base + 128, tmem_base, sK(buf), j != 0);  // dQ += dS K, dS read from TMEM
       if (j + 1 < n_kv) {
         mbar_wait(bar_kv(nbuf), ((j + 1) / DQ_NST) & 1);
         tc_fence_after();
@@ -395,10 +431,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
 // =================================================================================================
 // backward, part 2: dK, dV.  CTA = 128 kv rows of one (clip, head); streams 64-row Q/dO tiles.
-// TMEM: S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256) -> 2 CTAs / SM.  smem 112.6 KB (3-stage Q/dO ring).
+// TMEM: S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256) -> 2 CTAs / SM.  smem 96.6 KB (4-stage Q/dO ring); P^T / dS^T alias S^T / dP^T in TMEM.
 // =================================================================================================
-constexpr int DKV_NST = 3;                                                            // Q/dO ring depth (prefetch distance 2)
-constexpr int DKV_SMEM = 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 2 * TILE_BYTES + 512 + 64;   // K,V, Q/dO ring, P^T, dS^T, stats
+constexpr int DKV_NST = 4;                                                            // Q/dO ring depth (prefetch distance 3)
+constexpr int DKV_SMEM = 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 512 + 64;   // K,V, Q/dO ring, stats
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
@@ -408,11 +444,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
   const uint32_t base = smem_u32(smem_raw);
   check_align(base);
   const uint32_t sK = base, sV = base + TILE_BYTES;
-  const uint32_t sP = base + 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES, sdS = sP + TILE_BYTES;
   auto sQ = [&](int b) { return base + 2 * TILE_BYTES + (2 * b) * HTILE_BYTES; };
   auto sdO = [&](int b) { return base + 2 * TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
-  float* vec = reinterpret_cast<float*>(smem_raw + 4 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES);   // [lse 64 | delta 64]
-  const uint32_t bars = base + 4 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 512;
+  float* vec = reinterpret_cast<float*>(smem_raw + 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES);   // [lse 64 | delta 64]
+  const uint32_t bars = base + 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 512;
   const uint32_t bar_kv = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 56;
   auto bar_q = [&](int b) { return bars + 24 + 8 * b; };
 
@@ -491,7 +526,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
 #pragma unroll
       for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? exp2f(__uint_as_float(rs[e]) * c - st[e]) : 0.f;
     }
-    store_p_chunk(sP, row, half * 32, p);
+    tmem_store_bf16_row(tS, p);                                // P^T over this thread's own S^T columns
 #pragma unroll
     for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(st + 4 * g) = reinterpret_cast<const float4*>(del_s)[g];
     if (q_valid >= 32) {
@@ -501,14 +536,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
 #pragma unroll
       for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? p[e] * (__uint_as_float(rp[e]) - st[e]) : 0.f;
     }
-    store_p_chunk(sdS, row, half * 32, p);
-    fence_proxy_async_smem();
+    tmem_store_bf16_row(tdP, p);                               // dS^T over this thread's own dP^T columns
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_p_t(tmem_base + 128, sP, sdO(buf), i != 0);       // dV += P^T dO
-      mma_p_t(tmem_base + 192, sdS, sQ(buf), i != 0);       // dK += dS^T Q
+      mma_ptmem_t(tmem_base + 128, tmem_base, sdO(buf), i != 0);       // dV += P^T dO   (A from TMEM)
+      mma_ptmem_t(tmem_base + 192, tmem_base + 64, sQ(buf), i != 0);   // dK += dS^T Q   (A from TMEM)
       if (i + 1 < n_q) {
         mbar_wait(bar_q(nbuf), ((i + 1) / DKV_NST) & 1);
         tc_fence_after();
