@@ -77,11 +77,13 @@ int mofo_gather_tubes(const float* video, const int32_t* idx, int B, int n_idx, 
  *   with B = W^T (bf16 copy kept by the caller), the input-gradient GEMMs of their backward.
  * Epilogues (aux pointers may be NULL when unused):
  *   BIAS_BF16       out0 bf16 = acc + bias[n]
- *   BIAS_GELU_BF16  out0 bf16 = acc + bias[n] (pre-activation, kept for backward); out1 bf16 = gelu_erf(out0)
- *                   (Mlp.forward fc1 + nn.GELU, modeling_finetune.py:45-46)
+ *   BIAS_GELU_BF16  u = bf16(acc + bias[n]) (the pre-activation F.linear returns under autocast);
+ *                   out1 bf16 = gelu_erf(u)  (Mlp.forward fc1 + nn.GELU, modeling_finetune.py:45-46);
+ *                   out0 bf16 = gelu_erf'(u) (kept for backward in place of u: same erf/exp evaluation, so the
+ *                   backward epilogue is a single multiply)
  *   BIAS_RESID_F32  out0 f32 = acc + bias[n] + resid[m,n]  (residual add of Block.forward, :218-219)
  *   PLAIN_BF16      out0 bf16 = acc
- *   GELU_BWD_BF16   out0 bf16 = acc * gelu_erf'(aux_bf16[m,n])   (backward through nn.GELU)
+ *   GELU_BWD_BF16   out0 bf16 = acc * aux_bf16[m,n], aux = the gelu_erf'(u) saved by BIAS_GELU_BF16 (backward through nn.GELU)
  *   BIAS_POS_F32    out0 f32 [row' , n] = acc + bias[n] + pos[row_idx[m], n]; row' = (m / group_rows) *
  *                   out_group_rows + m % group_rows.  With bias = patch-embed bias this is "+ pos_embed" then the
  *                   visible gather (modeling_pretrain.py:85-90); with bias = NULL, group_rows = N_vis,

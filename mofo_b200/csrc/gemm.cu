@@ -10,6 +10,8 @@
 //   gemm_wgrad_kernel dW[N,K] += dY[M,N]^T · X[M,K]     both operands MN-major (reduction over rows),
 //                     split over M across CTAs, row-coalesced fp32 red.add into the gradient arena; the bias
 //                     gradient (column sums of dY) rides along as one extra N=16 MMA against a ones tile.
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -201,44 +203,55 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, uint32_t stg
                [&](int g) { return reinterpret_cast<float*>(ep.out0) + out_row(g) * ep.ldo0 + n0; });
     __syncwarp();
   } else {
-    if (EPI == MOFO_EPI_GELU_BWD_BF16) {
+    if (EPI == MOFO_EPI_GELU_BWD_BF16) {      // aux holds gelu'(u) saved by the forward epilogue: one multiply per element
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint4 a = lds128(stg64(stg, lane, c));
-        v[c * 8 + 0] *= gelu_erf_grad(bf16_lo(a.x)); v[c * 8 + 1] *= gelu_erf_grad(bf16_hi(a.x));
-        v[c * 8 + 2] *= gelu_erf_grad(bf16_lo(a.y)); v[c * 8 + 3] *= gelu_erf_grad(bf16_hi(a.y));
-        v[c * 8 + 4] *= gelu_erf_grad(bf16_lo(a.z)); v[c * 8 + 5] *= gelu_erf_grad(bf16_hi(a.z));
-        v[c * 8 + 6] *= gelu_erf_grad(bf16_lo(a.w)); v[c * 8 + 7] *= gelu_erf_grad(bf16_hi(a.w));
+        v[c * 8 + 0] *= bf16_lo(a.x); v[c * 8 + 1] *= bf16_hi(a.x);
+        v[c * 8 + 2] *= bf16_lo(a.y); v[c * 8 + 3] *= bf16_hi(a.y);
+        v[c * 8 + 4] *= bf16_lo(a.z); v[c * 8 + 5] *= bf16_hi(a.z);
+        v[c * 8 + 6] *= bf16_lo(a.w); v[c * 8 + 7] *= bf16_hi(a.w);
       }
       __syncwarp();
     }
     uint32_t packed[COLS / 2];
+    if (EPI == MOFO_EPI_BIAS_GELU_BF16) {
+      // GELU acts on the bf16-rounded pre-activation u (what F.linear returns under autocast).  One erf/exp evaluation
+      // yields both gelu(u) (out1, feeds fc2) and gelu'(u) (out0, kept for backward instead of u itself).
+      uint32_t dpacked[COLS / 2];
 #pragma unroll
-    for (int e = 0; e < COLS / 2; ++e) packed[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+      for (int e = 0; e < COLS / 2; ++e) {
+        const uint32_t ub = pack_bf16(v[2 * e], v[2 * e + 1]);
+        const float u0 = bf16_lo(ub), u1 = bf16_hi(ub);
+        float er0, e0, er1, e1;
+        erf_parts(u0, er0, e0);
+        erf_parts(u1, er1, e1);
+        const float h0 = 0.5f * u0, h1 = 0.5f * u1;
+        packed[e] = pack_bf16(fmaf(h0, er0, h0), fmaf(h1, er1, h1));
+        dpacked[e] = pack_bf16(fmaf(u0 * 0.3989422804014327f, e0, fmaf(0.5f, er0, 0.5f)),
+                               fmaf(u1 * 0.3989422804014327f, e1, fmaf(0.5f, er1, 0.5f)));
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts128(stg64(stg, lane, c), make_uint4(dpacked[c * 4], dpacked[c * 4 + 1], dpacked[c * 4 + 2], dpacked[c * 4 + 3]));
+      __syncwarp();
+      coop_store(stg, lane, row_base, M, valid_chunks,
+                 [&](int g) { return reinterpret_cast<__nv_bfloat16*>(ep.out0) + static_cast<size_t>(g) * ep.ldo0 + n0; });
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int e = 0; e < COLS / 2; ++e) packed[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       sts128(stg64(stg, lane, c), make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]));
     __syncwarp();
-    coop_store(stg, lane, row_base, M, valid_chunks,
-               [&](int g) { return reinterpret_cast<__nv_bfloat16*>(ep.out0) + static_cast<size_t>(g) * ep.ldo0 + n0; });
-    __syncwarp();
-    if (EPI == MOFO_EPI_BIAS_GELU_BF16) {
-      // GELU acts on the bf16-rounded pre-activation (what F.linear returns under autocast)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float u[8];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          u[2 * e] = gelu_erf(bf16_lo(packed[c * 4 + e]));
-          u[2 * e + 1] = gelu_erf(bf16_hi(packed[c * 4 + e]));
-        }
-        sts128(stg64(stg, lane, c), make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7])));
-      }
-      __syncwarp();
-      coop_store(stg, lane, row_base, M, valid_chunks,
-                 [&](int g) { return reinterpret_cast<__nv_bfloat16*>(ep.out1) + static_cast<size_t>(g) * ep.ldo1 + n0; });
-      __syncwarp();
+    {
+      __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(EPI == MOFO_EPI_BIAS_GELU_BF16 ? ep.out1 : ep.out0);
+      const int ldo = EPI == MOFO_EPI_BIAS_GELU_BF16 ? ep.ldo1 : ep.ldo0;
+      coop_store(stg, lane, row_base, M, valid_chunks, [&](int g) { return outp + static_cast<size_t>(g) * ldo + n0; });
     }
+    __syncwarp();
   }
 }
 
@@ -548,6 +561,8 @@ static int launch_tn(const CUtensorMap& tA, const CUtensorMap& tB, int M, int N,
 }
 
 static int pick_bn(int M, int N) {
+  static const int forced = [] { const char* e = getenv("MOFO_FORCE_BN"); return e ? atoi(e) : 0; }();   // tuning aid
+  if (forced == 128 || ((forced == 192 || forced == 256) && N >= forced)) return forced;
   const int sms = sm_count();
   const int num_m = (M + BM - 1) / BM;
   int best = 128;

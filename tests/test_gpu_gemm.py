@@ -44,22 +44,22 @@ def test_gemm_tn_fused_epilogues(lib, M, N, K):
     A = torch.randn(M, K, device="cuda").bfloat16(); B = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device="cuda")
     ref = A.float() @ B.float().t()
-    # bias + GELU (two outputs)
-    u = torch.empty(M, N, dtype=torch.bfloat16, device="cuda"); a = torch.empty_like(u)
-    lib.gemm_tn(A, B, lib.EPI_BIAS_GELU_BF16, u, out1=a, bias=bias)
-    assert rel(u, ref + bias) < 6e-3
-    assert rel(a, torch.nn.functional.gelu(u.float())) < 6e-3
+    # bias + GELU: out1 = gelu(u), out0 = gelu'(u) with u = bf16(acc + bias)
+    dg = torch.empty(M, N, dtype=torch.bfloat16, device="cuda"); a = torch.empty_like(dg)
+    lib.gemm_tn(A, B, lib.EPI_BIAS_GELU_BF16, dg, out1=a, bias=bias)
+    u = (ref + bias).bfloat16().float().requires_grad_(True)
+    act = torch.nn.functional.gelu(u)
+    act.sum().backward()
+    assert rel(a, act.detach()) < 6e-3
+    assert rel(dg, u.grad) < 6e-3
     # bias + residual, f32 out
     res = torch.randn(M, N, device="cuda"); o32 = torch.empty(M, N, device="cuda")
     lib.gemm_tn(A, B, lib.EPI_BIAS_RESID_F32, o32, bias=bias, resid=res)
     assert rel(o32, ref + bias + res) < 1e-5
-    # GELU backward
-    uu = torch.randn(M, N, device="cuda").bfloat16()
+    # GELU backward: multiply by the saved derivative
     g = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    lib.gemm_tn(A, B, lib.EPI_GELU_BWD_BF16, g, aux=uu)
-    ur = uu.float().requires_grad_(True)
-    torch.nn.functional.gelu(ur).backward(ref)
-    assert rel(g, ur.grad) < 6e-3
+    lib.gemm_tn(A, B, lib.EPI_GELU_BWD_BF16, g, aux=dg)
+    assert rel(g, ref * dg.float()) < 6e-3
     # bias + pos + row remap (patch-embed / encoder_to_decoder epilogue)
     group, out_group = 50, 80
     Mg = (M // group) * group
