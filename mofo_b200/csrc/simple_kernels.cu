@@ -1,6 +1,8 @@
 // HBM-/latency-bound kernels of the MOFO pretraining step: tube masking, tubelet gather, LayerNorm fwd/bwd,
 // decoder-input assembly, target + MSE, weight casts, bias-gradient column sums, gradient norm.
 // All of them are integer/byte/elementwise work: coalesced 16-byte accesses, no tensor cores.
+#include <stdlib.h>
+
 #include "../../include/mofo_b200.h"
 #include "common.cuh"
 
@@ -673,7 +675,8 @@ int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, 
   MOFO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_CHUNKS && group_rows > 0, "layernorm_bwd: unsupported M=%d D=%d", M, D);
   const int warps = 8;
   int grid = (M + warps - 1) / warps;
-  int cap = sm_count() * (D <= 512 ? 4 : 2);
+  static const int cap_mul = [] { const char* e = getenv("MOFO_LN_CAP"); return e ? atoi(e) : 0; }();   // tuning aid
+  int cap = sm_count() * (cap_mul > 0 ? cap_mul : (D <= 512 ? 4 : 2));
   if (grid > cap) grid = cap;
   size_t smem = static_cast<size_t>(warps) * 2 * D * sizeof(float);
   const int nch = (D + 127) / 128;
