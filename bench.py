@@ -377,7 +377,11 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "final_loss": final_loss,
             "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05, all fused-epilogue instances)",
                          "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": gemm_tflops / peaks["bf16_sustained"] if gemm_tflops else None, "traffic": None,
+                         "frac": gemm_tflops / peaks["bf16_sustained"] if gemm_tflops else None,
+                         # dram__bytes_read+write of ONE launch from `ncu --set full` (profiles/r01_ncu_gemm_tn_final_full.txt):
+                         # decoder fc1-dgrad instance [50176x384, K=1536]: 155.3 MB read + 24.2 MB written (rest of the
+                         # 38.5 MB output still dirty in L2) vs 193.9 MB algorithmic -> no re-reads
+                         "traffic": 179.6e6, "traffic_instance": "gemm_tn_kernel<128,PLAIN_BF16> M=50176 N=384 K=1536 (algorithmic 193.9e6 B)",
                          "launches_timed": n_gemm, "kernel_ms_per_step": gemm_ms / args.steps,
                          "share_of_step": gemm_ms / ms_instrumented, "instrumented_ms_per_step": ms_instrumented / args.steps,
                          "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"},
