@@ -153,6 +153,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
+  pdl_trigger();
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t tS = tmem_base + lane_off + half * 32, tO = tmem_base + lane_off + 64 + half * 32;
 
@@ -283,6 +285,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // =================================================================================================
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int rows,
                                   int S, int H, float* __restrict__ delta) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (row, head), head fastest
   if (i >= rows * H) return;
   const int row = i / H, h = i % H;
@@ -346,6 +350,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
+  pdl_trigger();
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t tS = tmem_base + lane_off + half * 32, tdP = tmem_base + lane_off + 64 + half * 32;
   const uint32_t tdQ = tmem_base + lane_off + 128 + half * 32;
@@ -475,6 +481,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
+  pdl_trigger();
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t tS = tmem_base + lane_off + half * 32, tdP = tmem_base + lane_off + 64 + half * 32;
 
@@ -605,9 +613,8 @@ int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_b
     attr_set = true;
   }
   dim3 grid((S + AT - 1) / AT, H, B);
-  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      tq, tkv, S, H, scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(out), lse);
-  MOFO_LAUNCH_CHECK("attn_fwd_kernel");
+  MOFO_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(ATT_THREADS), FWD_SMEM, static_cast<cudaStream_t>(stream), tq, tkv, S, H,
+                       scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(out), lse));
   return MOFO_OK;
 }
 
@@ -632,17 +639,15 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
     MOFO_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
     attr_set = true;
   }
-  attn_delta_kernel<<<(static_cast<int>(rows) * H + 127) / 128, 128, 0, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), static_cast<int>(rows), S, H, delta);
-  MOFO_LAUNCH_CHECK("attn_delta_kernel");
+  MOFO_CUDA(launch_pdl(attn_delta_kernel, dim3((static_cast<int>(rows) * H + 127) / 128), dim3(128), 0, s,
+                       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout),
+                       static_cast<int>(rows), S, H, delta));
   dim3 grid((S + AT - 1) / AT, H, B);
   const float c = scale * 1.4426950408889634f;
-  attn_bwd_dq_kernel<<<grid, ATT_THREADS, DQ_SMEM, s>>>(tq128, tq64, td128, S, H, c, scale, lse, delta,
-                                                        reinterpret_cast<__nv_bfloat16*>(dqkv));
-  MOFO_LAUNCH_CHECK("attn_bwd_dq_kernel");
-  attn_bwd_dkv_kernel<<<grid, ATT_THREADS, DKV_SMEM, s>>>(tq128, tq64, td64, S, H, c, scale, lse, delta,
-                                                          reinterpret_cast<__nv_bfloat16*>(dqkv));
-  MOFO_LAUNCH_CHECK("attn_bwd_dkv_kernel");
+  MOFO_CUDA(launch_pdl(attn_bwd_dq_kernel, grid, dim3(ATT_THREADS), DQ_SMEM, s, tq128, tq64, td128, S, H, c, scale, lse,
+                       static_cast<const float*>(delta), reinterpret_cast<__nv_bfloat16*>(dqkv)));
+  MOFO_CUDA(launch_pdl(attn_bwd_dkv_kernel, grid, dim3(ATT_THREADS), DKV_SMEM, s, tq128, tq64, td64, S, H, c, scale, lse,
+                       static_cast<const float*>(delta), reinterpret_cast<__nv_bfloat16*>(dqkv)));
   return MOFO_OK;
 }
 

@@ -45,6 +45,7 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int sm_count();
+bool pdl_enabled();   // programmatic dependent launch, opt-in with MOFO_B200_PDL=1 (measured: no gain under graph replay)
 
 // TMA tensor-map encode (driver entry point fetched through the runtime, no -lcuda needed)
 // 2D row-major bf16 tensor [rows, cols] with leading dimension ld (elements);
@@ -53,6 +54,27 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows, uint32_t box_cols = 64);
 
 #ifdef __CUDACC__
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel launched through launch_pdl() executes pdl_wait() before its first
+// global-memory access: the grid may then be scheduled while its predecessor in the stream is still draining (its
+// prologue - barrier init, TMEM allocation, descriptor prefetch - overlaps the predecessor's tail), and pdl_wait()
+// blocks until the predecessor has fully completed and flushed.  pdl_trigger() lets the successor start launching.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------------------------
 // small device utilities
 // ----------------------------------------------------------------------------------------------

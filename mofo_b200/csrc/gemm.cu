@@ -299,6 +299,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_trigger();
 
   if (warp == EPI_WARPS) {
     if (lane == 0) {  // ===== TMA producer =====
@@ -437,6 +439,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_trigger();
 
   if (warp == WG_EPI_WARPS) {
     if (lane == 0) {
@@ -555,8 +559,7 @@ static int launch_tn(const CUtensorMap& tA, const CUtensorMap& tB, int M, int N,
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tA, tB, M, N, K, ep);
-  MOFO_LAUNCH_CHECK("gemm_tn_kernel");
+  MOFO_CUDA(launch_pdl(gemm_tn_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, tA, tB, M, N, K, ep));
   return MOFO_OK;
 }
 
@@ -605,8 +608,8 @@ static int launch_wgrad(const CUtensorMap& tY, const CUtensorMap& tX, int M, int
   const int kb_per_split = (kblocks + splits - 1) / splits;
   splits = (kblocks + kb_per_split - 1) / kb_per_split;
   dim3 grid(tiles, splits);
-  gemm_wgrad_kernel<BNW><<<grid, WG_THREADS, Cfg::SMEM_BYTES, s>>>(tY, tX, M, N, K, dW, ldw, kb_per_split, dbias, skip_lo, skip_hi);
-  MOFO_LAUNCH_CHECK("gemm_wgrad_kernel");
+  MOFO_CUDA(launch_pdl(gemm_wgrad_kernel<BNW>, grid, dim3(WG_THREADS), Cfg::SMEM_BYTES, s, tY, tX, M, N, K, dW, ldw, kb_per_split,
+                       dbias, skip_lo, skip_hi));
   return MOFO_OK;
 }
 

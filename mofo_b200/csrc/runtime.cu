@@ -1,5 +1,6 @@
 // Host-side runtime of libmofo_sm100.so: error reporting, device query, TMA tensor-map encoding.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -31,6 +32,12 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  // measured on B200 (bench.py, CUDA-graph replay): 15.04 ms/step with PDL vs 14.84 ms without -> opt-in only
+  static const bool on = [] { const char* e = getenv("MOFO_B200_PDL"); return e && e[0] == '1'; }();
+  return on;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

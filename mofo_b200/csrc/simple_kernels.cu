@@ -158,6 +158,8 @@ __global__ void mask_indices_kernel(const uint8_t* __restrict__ mask, int B, int
 __global__ void __launch_bounds__(192) gather_tubes_kernel(const float* __restrict__ video,
                                                            const int32_t* __restrict__ idx, int n_idx, int frames,
                                                            int size, __nv_bfloat16* __restrict__ A) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x;
   const int b = row / n_idx;
   const int hw = size >> 4;
@@ -191,6 +193,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             int group_rows, int in_group_rows, int in_row_offset,
                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                                                             float* __restrict__ rstd) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -238,6 +242,8 @@ __global__ void __launch_bounds__(256, (NCH <= 3 ? 3 : 2)) layernorm_bwd_kernel(
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres, int M, int D,
     int group_rows, int in_group_rows, int in_row_offset, float* __restrict__ dx_f32,
     __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ ws) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float red[];  // [warps][2*D]
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -340,6 +346,8 @@ __global__ void __launch_bounds__(256, (NCH <= 3 ? 3 : 2)) layernorm_bwd_kernel(
 __global__ void assemble_fwd_kernel(const float* __restrict__ mask_token, const float* __restrict__ pos,
                                     const int32_t* __restrict__ msk_idx, int n_vis, int n_msk, int Dd,
                                     float* __restrict__ x_full) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x;                 // b*n_msk + j
   const int b = r / n_msk, j = r % n_msk;
   const float4* p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(msk_idx[r]) * Dd);
@@ -354,6 +362,8 @@ __global__ void assemble_fwd_kernel(const float* __restrict__ mask_token, const 
 // grid = (row chunks, B).  Threads own float4 column chunks; rows of the chunk are streamed.
 __global__ void assemble_bwd_kernel(const float* __restrict__ dx_full, int n_vis, int n_msk, int Dd, int rows_per_cta,
                                     float* __restrict__ dmask_token, __nv_bfloat16* __restrict__ dvis) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int N = n_vis + n_msk;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
@@ -395,6 +405,8 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
                                                          float* __restrict__ loss_partials,
                                                          __nv_bfloat16* __restrict__ dpred,
                                                          float* __restrict__ labels_out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(16) float lab[1536];
   __shared__ float sh[4];
   const int row = blockIdx.x;
@@ -468,6 +480,8 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(1024) loss_finish_kernel(const float* __restrict__ partials, int n, double inv_count,
                                                            float* __restrict__ loss) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double sh[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += static_cast<double>(partials[i]);
@@ -642,8 +656,8 @@ int mofo_gather_tubes(const float* video, const int32_t* idx, int B, int n_idx, 
                       void* stream) {
   MOFO_CHECK_ARG(video && idx && A, "gather_tubes: null pointer");
   MOFO_CHECK_ARG(B > 0 && n_idx > 0 && frames % 2 == 0 && size % 16 == 0, "gather_tubes: bad shape B=%d n=%d frames=%d size=%d", B, n_idx, frames, size);
-  gather_tubes_kernel<<<B * n_idx, 192, 0, static_cast<cudaStream_t>(stream)>>>(video, idx, n_idx, frames, size, reinterpret_cast<__nv_bfloat16*>(A));
-  MOFO_LAUNCH_CHECK("gather_tubes_kernel");
+  MOFO_CUDA(launch_pdl(gather_tubes_kernel, dim3(B * n_idx), dim3(192), 0, static_cast<cudaStream_t>(stream), video, idx, n_idx, frames,
+                       size, reinterpret_cast<__nv_bfloat16*>(A)));
   return MOFO_OK;
 }
 
@@ -652,9 +666,9 @@ int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, in
   MOFO_CHECK_ARG(x && gamma && beta && y && mean && rstd, "layernorm_fwd: null pointer");
   MOFO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_CHUNKS && group_rows > 0, "layernorm_fwd: unsupported M=%d D=%d", M, D);
   const int nch = (D + 127) / 128;
-#define MOFO_LN_FWD(NCH)                                                                                     \
-  layernorm_fwd_kernel<NCH><<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(                     \
-      x, gamma, beta, M, D, eps, group_rows, in_group_rows, in_row_offset, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd)
+#define MOFO_LN_FWD(NCH)                                                                                              \
+  MOFO_CUDA(launch_pdl(layernorm_fwd_kernel<NCH>, dim3((M + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), x, gamma, \
+                       beta, M, D, eps, group_rows, in_group_rows, in_row_offset, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd))
   if (nch <= 1) MOFO_LN_FWD(1);
   else if (nch == 2) MOFO_LN_FWD(2);
   else if (nch == 3) MOFO_LN_FWD(3);
@@ -684,9 +698,10 @@ int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, 
   do {                                                                                                                 \
     if (smem + 1024 > 48 * 1024)                                                                                       \
       MOFO_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    layernorm_bwd_kernel<NCH><<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(                          \
-        reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, M, D, group_rows, in_group_rows,       \
-        in_row_offset, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, ws);                          \
+    MOFO_CUDA(launch_pdl(layernorm_bwd_kernel<NCH>, dim3(grid), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream), \
+                         reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, M, D, group_rows,     \
+                         in_group_rows, in_row_offset, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma,      \
+                         dbeta, ws));                                                                                  \
   } while (0)
   if (nch <= 1) MOFO_LN_BWD(1);
   else if (nch == 2) MOFO_LN_BWD(2);
@@ -703,8 +718,8 @@ int mofo_decoder_assemble_fwd(const float* mask_token, const float* pos, const i
                               int n_msk, int Dd, float* x_full, void* stream) {
   MOFO_CHECK_ARG(mask_token && pos && msk_idx && x_full, "decoder_assemble_fwd: null pointer");
   MOFO_CHECK_ARG(B > 0 && n_vis >= 0 && n_msk > 0 && Dd % 4 == 0, "decoder_assemble_fwd: bad shape");
-  assemble_fwd_kernel<<<B * n_msk, 128, 0, static_cast<cudaStream_t>(stream)>>>(mask_token, pos, msk_idx, n_vis, n_msk, Dd, x_full);
-  MOFO_LAUNCH_CHECK("assemble_fwd_kernel");
+  MOFO_CUDA(launch_pdl(assemble_fwd_kernel, dim3(B * n_msk), dim3(128), 0, static_cast<cudaStream_t>(stream), mask_token, pos, msk_idx,
+                       n_vis, n_msk, Dd, x_full));
   return MOFO_OK;
 }
 
@@ -714,9 +729,8 @@ int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk,
   MOFO_CHECK_ARG(B > 0 && n_vis >= 0 && n_msk > 0 && Dd % 4 == 0, "decoder_assemble_bwd: bad shape");
   const int rows_per_cta = 16;
   dim3 grid((n_vis + n_msk + rows_per_cta - 1) / rows_per_cta, B);
-  assemble_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(dx_full, n_vis, n_msk, Dd, rows_per_cta, dmask_token,
-                                                                       reinterpret_cast<__nv_bfloat16*>(dvis));
-  MOFO_LAUNCH_CHECK("assemble_bwd_kernel");
+  MOFO_CUDA(launch_pdl(assemble_bwd_kernel, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), dx_full, n_vis, n_msk, Dd,
+                       rows_per_cta, dmask_token, reinterpret_cast<__nv_bfloat16*>(dvis)));
   return MOFO_OK;
 }
 
@@ -729,13 +743,9 @@ int mofo_target_mse(const float* video, const int32_t* msk_idx, const mofo_bf16*
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const double count = static_cast<double>(B) * n_msk * 1536.0;
   const float gscale = static_cast<float>(2.0 / count) * grad_scale;
-  target_mse_kernel<<<B * n_msk, 128, 0, s>>>(video, msk_idx, reinterpret_cast<const __nv_bfloat16*>(pred), n_msk, frames, size,
-                                              normalize_target, gscale, loss_partials, reinterpret_cast<__nv_bfloat16*>(dpred), labels_out);
-  MOFO_LAUNCH_CHECK("target_mse_kernel");
-  if (loss) {
-    loss_finish_kernel<<<1, 1024, 0, s>>>(loss_partials, B * n_msk, 1.0 / count, loss);
-    MOFO_LAUNCH_CHECK("loss_finish_kernel");
-  }
+  MOFO_CUDA(launch_pdl(target_mse_kernel, dim3(B * n_msk), dim3(128), 0, s, video, msk_idx, reinterpret_cast<const __nv_bfloat16*>(pred),
+                       n_msk, frames, size, normalize_target, gscale, loss_partials, reinterpret_cast<__nv_bfloat16*>(dpred), labels_out));
+  if (loss) MOFO_CUDA(launch_pdl(loss_finish_kernel, dim3(1), dim3(1024), 0, s, static_cast<const float*>(loss_partials), B * n_msk, 1.0 / count, loss));
   return MOFO_OK;
 }
 
