@@ -2,8 +2,9 @@
 // Replaces modeling_finetune.py:85-95 (Attention.forward between the qkv and proj linears).
 //
 // Layout: qkv bf16 [B*S, 3*H*64] (q | k | v), out / dout bf16 [B*S, H*64], lse / delta f32 [B,H,S].
-// All three kernels use 128 threads: thread r owns TMEM lane r = one row of the 128-row tile, so the
-// softmax needs no cross-thread reduction.  Thread 0 additionally issues TMA loads and tcgen05.mma.
+// All three kernels use 256 threads: each row of the 128-row tile is owned by two threads (32 of the 64 streamed
+// columns each) that read their accumulator slice straight from TMEM, so the softmax needs one bf16 exchange per row
+// and no shuffles.  Thread 0 additionally issues the TMA loads and tcgen05.mma.
 //   S = Q K^T and friends:  both operands K-major SW128 tiles [128 rows x 64 d] straight from TMA.
 //   P V / dS K / P^T dO ...: A = bf16 operand written by the threads straight into TENSOR MEMORY (tcgen05.st over their
 //                            own fp32 accumulator columns; tcgen05.mma with A in TMEM), so it never touches shared memory;
@@ -33,19 +34,6 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {   // single 
   return d;
 }
 
-// write 32 consecutive columns [c0, c0+32) (c0 = 0 or 32) of row `row` of a [128 x 64] bf16 K-major SW128 tile
-__device__ __forceinline__ void store_p_chunk(uint32_t tile_base, int row, int c0, const float (&v)[32]) {
-  const int chunk0 = c0 >> 3;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const uint32_t addr = tile_base + sw128_offset(row, chunk0 + g);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(v[g * 8 + 0], v[g * 8 + 1])),
-                 "r"(pack_bf16(v[g * 8 + 2], v[g * 8 + 3])), "r"(pack_bf16(v[g * 8 + 4], v[g * 8 + 5])),
-                 "r"(pack_bf16(v[g * 8 + 6], v[g * 8 + 7]))
-                 : "memory");
-  }
-}
-
 // D[128 x 64] = A[128 x 64] · B[64 x 64]^T, both K-major SW128 tiles straight from TMA (4 K-steps of 16)
 __device__ __forceinline__ void mma_ab_t(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
@@ -53,14 +41,6 @@ __device__ __forceinline__ void mma_ab_t(uint32_t d_tmem, uint32_t a_tile, uint3
 #pragma unroll
   for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k != 0);
 }
-// D[128 x 64] (+)= P[128 x 64] (K-major, written by the threads) · T[64 x 64] (MN-major: rows = reduction index)
-__device__ __forceinline__ void mma_p_t(uint32_t d_tmem, uint32_t p_tile, uint32_t t_tile, bool accumulate) {
-  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
-  const uint64_t a0 = umma_desc_kmajor(p_tile), b0 = umma_desc_mnmajor(t_tile, 8192);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 128 * k, idesc, (accumulate || k != 0) ? 1u : 0u);
-}
-
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
