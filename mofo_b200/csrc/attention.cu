@@ -133,12 +133,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // provably warp-uniform -> MMA operands stay in uniform registers
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   pdl_wait();
   pdl_trigger();
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t tS = tmem_base + lane_off + half * 32, tO = tmem_base + lane_off + 64 + half * 32;
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_expect_tx(bar_q, TILE_BYTES);
     tma_load_2d(sQ, &tm_q, bar_q, h * 64, row0 + q0);
     mbar_expect_tx(bar_kv(0), 2 * HTILE_BYTES);
@@ -162,7 +164,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int buf = j & 1;
     mbar_wait(bar_s, j & 1);                        // S(j) ready; also: P(j-1)V(j-1) done -> P tile and K/V buffer buf^1 free
     tc_fence_after();
-    if (tid == 0 && j >= 1 && j + 1 < n_kv) {       // refill the buffer tile j-1 used with tile j+1
+    if (warp_u == 0 && j >= 1 && j + 1 < n_kv && elect_one()) {       // refill the buffer tile j-1 used with tile j+1
       mbar_expect_tx(bar_kv(buf ^ 1), 2 * HTILE_BYTES);
       tma_load_2d(sK(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (H + h) * 64, row0 + (j + 1) * BT);
       tma_load_2d(sV(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * BT);
@@ -218,7 +220,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     l_run += rs;
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       mma_ptmem_t(tmem_base + 64, tmem_base, sV(buf), j != 0);   // O += P(j) V(j), P read from TMEM
       if (j + 1 < n_kv) {
@@ -330,6 +332,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // provably warp-uniform -> MMA operands stay in uniform registers
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   pdl_wait();
   pdl_trigger();
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -341,7 +345,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const float my_lse = q_ok ? lse[(static_cast<size_t>(b) * H + h) * S + q] : 0.f;
   const float my_delta = q_ok ? delta[(static_cast<size_t>(b) * H + h) * S + q] : 0.f;
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_expect_tx(bar_q, 2 * TILE_BYTES);
     tma_load_2d(sQ, &tm_q, bar_q, h * 64, row0 + q0);
     tma_load_2d(sdO, &tm_do, bar_q, h * 64, row0 + q0);
@@ -358,7 +362,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int buf = j % DQ_NST, nbuf = (j + 1) % DQ_NST;
     mbar_wait(bar_12, j & 1);   // also covers the dQ MMA of iteration j-1 (tensor pipe is in-order) -> stage (j-1)%NST is free
     tc_fence_after();
-    if (tid == 0 && j + DQ_NST - 1 < n_kv) load_kv(j + DQ_NST - 1);
+    if (warp_u == 0 && j + DQ_NST - 1 < n_kv && elect_one()) load_kv(j + DQ_NST - 1);
     const int kv_valid = S - j * BT - half * 32;
     uint32_t rs[32], rp[32];
     tmem_ld32(tS, rs);
@@ -377,7 +381,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     tmem_store_bf16_row(tS, ds);                               // dS (bf16) over this thread's own S columns
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       mma_ptmem_t(tmem_base + 128, tmem_base, sK(buf), j != 0);  // dQ += dS K, dS read from TMEM
       if (j + 1 < n_kv) {
@@ -419,6 +423,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // backward, part 2: dK, dV.  CTA = 128 kv rows of one (clip, head); streams 64-row Q/dO tiles.
 // TMEM: S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256) -> 2 CTAs / SM.  smem 96.6 KB (4-stage Q/dO ring); P^T / dS^T alias S^T / dP^T in TMEM.
 // =================================================================================================
+#ifndef MOFO_ATTN_PAD
+#define MOFO_ATTN_PAD 0          // tuning aid: extra dynamic smem per CTA to force lower occupancy in variant builds
+#endif
+#ifdef MOFO_ATTN_TRACE
+__device__ long long g_trace[64 * 8 * 2];
+#define TRACE(slot) do { if (trace_on && (tid == 0 || tid == 255)) g_trace[(i * 8 + (slot)) * 2 + (tid != 0)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 constexpr int DKV_NST = 4;                                                            // Q/dO ring depth (prefetch distance 3)
 constexpr int DKV_SMEM = 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 512 + 64;   // K,V, Q/dO ring, stats
 
@@ -461,6 +475,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // provably warp-uniform -> MMA operands stay in uniform registers
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   pdl_wait();
   pdl_trigger();
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -468,8 +484,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
 
   const int kv = kv0 + row;
   const bool kv_ok = kv < S;
+#ifdef MOFO_ATTN_TRACE
+  const bool trace_on = blockIdx.x == 6 && blockIdx.y == 3 && blockIdx.z == 10;
+#endif
 
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     mbar_expect_tx(bar_kv, 2 * TILE_BYTES);
     tma_load_2d(sK, &tm_kv, bar_kv, (H + h) * 64, row0 + kv0);
     tma_load_2d(sV, &tm_kv, bar_kv, (2 * H + h) * 64, row0 + kv0);
@@ -493,10 +512,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
       const int qq = (i + 1) * BT + (tid & 63);
       stat_next = qq < S ? stat_src[qq] : 0.f;
     }
+    TRACE(0);
     mbar_wait(bar_12, i & 1);    // also covers the dV/dK MMAs of iteration i-1 -> ring stage (i-1)%NST is free
     tc_fence_after();
+    TRACE(1);
     __syncthreads();             // vec[] visible
-    if (tid == 0 && i + DKV_NST - 1 < n_q) load_q(i + DKV_NST - 1);
+    TRACE(2);
+    if (warp_u == 0 && i + DKV_NST - 1 < n_q && elect_one()) load_q(i + DKV_NST - 1);
     const int q_valid = S - i * BT - half * 32;
     const float* lse_s = vec + half * 32;
     const float* del_s = lse_s + 64;
@@ -504,6 +526,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     tmem_ld32(tS, rs);
     tmem_ld32(tdP, rp);
     tc_wait_ld();
+    TRACE(3);
     float p[32], st[32];
 #pragma unroll
     for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(st + 4 * g) = reinterpret_cast<const float4*>(lse_s)[g];
@@ -515,6 +538,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
       for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? exp2f(__uint_as_float(rs[e]) * c - st[e]) : 0.f;
     }
     tmem_store_bf16_row(tS, p);                                // P^T over this thread's own S^T columns
+    TRACE(4);
 #pragma unroll
     for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(st + 4 * g) = reinterpret_cast<const float4*>(del_s)[g];
     if (q_valid >= 32) {
@@ -526,8 +550,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     }
     tmem_store_bf16_row(tdP, p);                               // dS^T over this thread's own dP^T columns
     tc_fence_before();
+    TRACE(5);
     __syncthreads();
-    if (tid == 0) {
+    TRACE(6);
+    if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       mma_ptmem_t(tmem_base + 128, tmem_base, sdO(buf), i != 0);       // dV += P^T dO   (A from TMEM)
       mma_ptmem_t(tmem_base + 192, tmem_base + 64, sQ(buf), i != 0);   // dK += dS^T Q   (A from TMEM)
@@ -541,6 +567,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
         tc_commit(bar_fin);
       }
     }
+    TRACE(7);
   }
   mbar_wait(bar_fin, 0);
   tc_fence_after();
@@ -579,6 +606,12 @@ using namespace mofo;
 
 extern "C" {
 
+#ifdef MOFO_ATTN_TRACE
+int mofo_debug_read_trace(long long* host, int n) {   // tuning aid, only in -DMOFO_ATTN_TRACE builds
+  return cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_bf16* out, float* lse, void* stream) {
   MOFO_CHECK_ARG(qkv && out && lse, "attn_fwd: null pointer");
   MOFO_CHECK_ARG(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
@@ -615,8 +648,8 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MOFO_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
-    MOFO_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    MOFO_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM + MOFO_ATTN_PAD));
+    MOFO_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM + MOFO_ATTN_PAD));
     attr_set = true;
   }
   MOFO_CUDA(launch_pdl(attn_delta_kernel, dim3((static_cast<int>(rows) * H + 127) / 128), dim3(128), 0, s,
@@ -624,9 +657,9 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
                        static_cast<int>(rows), S, H, delta));
   dim3 grid((S + AT - 1) / AT, H, B);
   const float c = scale * 1.4426950408889634f;
-  MOFO_CUDA(launch_pdl(attn_bwd_dq_kernel, grid, dim3(ATT_THREADS), DQ_SMEM, s, tq128, tq64, td128, S, H, c, scale, lse,
+  MOFO_CUDA(launch_pdl(attn_bwd_dq_kernel, grid, dim3(ATT_THREADS), DQ_SMEM + MOFO_ATTN_PAD, s, tq128, tq64, td128, S, H, c, scale, lse,
                        static_cast<const float*>(delta), reinterpret_cast<__nv_bfloat16*>(dqkv)));
-  MOFO_CUDA(launch_pdl(attn_bwd_dkv_kernel, grid, dim3(ATT_THREADS), DKV_SMEM, s, tq128, tq64, td64, S, H, c, scale, lse,
+  MOFO_CUDA(launch_pdl(attn_bwd_dkv_kernel, grid, dim3(ATT_THREADS), DKV_SMEM + MOFO_ATTN_PAD, s, tq128, tq64, td64, S, H, c, scale, lse,
                        static_cast<const float*>(delta), reinterpret_cast<__nv_bfloat16*>(dqkv)));
   return MOFO_OK;
 }

@@ -282,7 +282,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto smem_a = [&](int s) { return base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role
   const int num_n = (N + BN - 1) / BN, num_m = (M + BM - 1) / BM;
   const int tiles = num_m * num_n;
   const int kblocks = (K + BK - 1) / BK;
@@ -299,11 +299,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // uniform register -> tcgen05.mma issues without a per-lane loop
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
   pdl_trigger();
 
   if (warp == EPI_WARPS) {
-    if (lane == 0) {  // ===== TMA producer =====
+    if (elect_one()) {  // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -318,7 +319,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == EPI_WARPS + 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
+    if (elect_one()) {  // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -411,7 +412,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   auto smem_a = [&](int s) { return base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role
   const int num_k = (K + BNW - 1) / BNW;
   const int n_blk = blockIdx.x / num_k, k_blk = blockIdx.x % num_k;
   const int kblocks_total = (M + BK - 1) / BK;
@@ -439,11 +440,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // uniform register -> tcgen05.mma issues without a per-lane loop
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
   pdl_trigger();
 
   if (warp == WG_EPI_WARPS) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
@@ -458,7 +460,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
       }
     }
   } else if (warp == WG_EPI_WARPS + 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BNW, 1, 1);
       int stage = 0;
       uint32_t phase = 0;

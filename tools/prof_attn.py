@@ -20,3 +20,17 @@ for it in range(3):
     torch.cuda.synchronize()
     fl = 4.0 * B * H * S * S * 64
     print(f"fwd {e[0].elapsed_time(e[1]):.3f} ms ({fl / e[0].elapsed_time(e[1]) / 1e9:.0f} TF/s)  bwd {e[1].elapsed_time(e[2]):.3f} ms ({2.5 * fl / e[1].elapsed_time(e[2]) / 1e9:.0f} TF/s)")
+
+if os.environ.get("TRACE"):      # -DMOFO_ATTN_TRACE build: per-iteration phase timestamps of one mid-grid CTA
+    import ctypes, numpy as np
+    n_it = (S + 63) // 64
+    buf = (ctypes.c_longlong * (64 * 8 * 2))()
+    assert _lib.load().mofo_debug_read_trace(buf, 64 * 8 * 2) == 0
+    t = np.array(buf[:], dtype=np.int64).reshape(64, 8, 2)[:n_it]
+    names = os.environ["TRACE"].split(",")
+    print("iteration period (thread 0):", np.diff(t[:, 0, 0])[2:-1].mean())
+    for th in (0, 1):
+        d = np.diff(t[2:-1, :, th], axis=1)
+        print(f"thread {'0' if th == 0 else '255'} phase deltas (clk, mean over iterations):",
+              {names[k] if k < len(names) else k: round(float(d[:, k].mean())) for k in range(d.shape[1])})
+    print("per-iteration slot 0 (thread 0):", (t[1:, 0, 0] - t[:-1, 0, 0]).tolist())
