@@ -70,6 +70,19 @@ __device__ __forceinline__ void mma_ptmem_t(uint32_t d_tmem, uint32_t p_tmem, ui
   for (int k = 0; k < 4; ++k)
     umma_bf16_ts(d_tmem, p_tmem + (k >> 1) * 32 + (k & 1) * 8, b0 + 128 * k, idesc, (accumulate || k != 0) ? 1u : 0u);
 }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// same as tmem_store_bf16_row but WITHOUT the trailing tcgen05.wait::st: the caller waits once before handing over
+__device__ __forceinline__ void tmem_store_bf16_row_async(uint32_t taddr, const float (&v)[32]) {
+  uint32_t r[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) r[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_store_bf16_row(uint32_t taddr, const float (&v)[32]) {
   uint32_t pk[16];
 #pragma unroll
@@ -434,7 +447,7 @@ __device__ long long g_trace[64 * 8 * 2];
 #endif
 
 constexpr int DKV_NST = 4;                                                            // Q/dO ring depth (prefetch distance 3)
-constexpr int DKV_SMEM = 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 512 + 64;   // K,V, Q/dO ring, stats
+constexpr int DKV_SMEM = 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 1024 + 128;   // K,V, Q/dO ring, stats x2, barriers
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
@@ -446,9 +459,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
   const uint32_t sK = base, sV = base + TILE_BYTES;
   auto sQ = [&](int b) { return base + 2 * TILE_BYTES + (2 * b) * HTILE_BYTES; };
   auto sdO = [&](int b) { return base + 2 * TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
-  float* vec = reinterpret_cast<float*>(smem_raw + 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES);   // [lse 64 | delta 64]
-  const uint32_t bars = base + 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 512;
-  const uint32_t bar_kv = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 56;
+  float* vec = reinterpret_cast<float*>(smem_raw + 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES);   // 2 x [lse 64 | delta 64]
+  const uint32_t bars = base + 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 1024;
+  const uint32_t bar_kv = bars, bar_s = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 56, bar_dp = bars + 64;
   auto bar_q = [&](int b) { return bars + 24 + 8 * b; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -464,7 +477,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
   };
 
   if (tid == 0) {
-    mbar_init(bar_kv, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1);
+    mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_fin, 1);
     for (int st = 0; st < DKV_NST; ++st) mbar_init(bar_q(st), 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do);
@@ -497,58 +510,71 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     mbar_wait(bar_q(0), 0);
     tc_fence_after();
     mma_ab_t(tmem_base, sK, sQ(0));             // S^T  = K Q^T
+    tc_commit(bar_s);
     mma_ab_t(tmem_base + 64, sV, sdO(0));       // dP^T = V dO^T
-    tc_commit(bar_12);
+    tc_commit(bar_dp);
   }
 
-  // per-column (q) statistics: threads 0-63 fetch lse, 64-127 fetch delta, one tile AHEAD into a register, so the
-  // global-load latency never sits between the MMA hand-off and the softmax recompute
+  // per-column (q) statistics: threads 0-63 fetch lse, 64-127 fetch delta, two tiles AHEAD into a register and one
+  // tile ahead into the double-buffered vec[], so neither the global-load latency nor a block barrier sits between
+  // the S^T hand-off and the softmax recompute.  vec[(i+1)&1] is written during iteration i (before its block
+  // barrier) and read during iteration i+1 (after it); it was last read during iteration i-1.
   const float* stat_src = (tid < 64 ? lse : delta) + (static_cast<size_t>(b) * H + h) * S;
-  float stat_next = (tid < 128 && (tid & 63) < S) ? stat_src[tid & 63] : 0.f;
+  float stat_next = 0.f;
+  if (tid < 128) {
+    vec[tid] = (tid & 63) < S ? stat_src[tid & 63] : 0.f;
+    stat_next = BT + (tid & 63) < S ? stat_src[BT + (tid & 63)] : 0.f;
+  }
+  __syncthreads();
   for (int i = 0; i < n_q; ++i) {
     const int buf = i % DKV_NST, nbuf = (i + 1) % DKV_NST;
-    if (tid < 128) {   // vec[] was last read before the second __syncthreads of iteration i-1
-      vec[tid] = stat_next;
-      const int qq = (i + 1) * BT + (tid & 63);
+    if (tid < 128) {
+      vec[((i + 1) & 1) * 128 + tid] = stat_next;
+      const int qq = (i + 2) * BT + (tid & 63);
       stat_next = qq < S ? stat_src[qq] : 0.f;
     }
     TRACE(0);
-    mbar_wait(bar_12, i & 1);    // also covers the dV/dK MMAs of iteration i-1 -> ring stage (i-1)%NST is free
+    mbar_wait(bar_s, i & 1);     // S^T(i) ready; also covers the dV/dK MMAs of iteration i-1 -> ring stage (i-1)%NST is free
     tc_fence_after();
     TRACE(1);
-    __syncthreads();             // vec[] visible
-    TRACE(2);
     if (warp_u == 0 && i + DKV_NST - 1 < n_q && elect_one()) load_q(i + DKV_NST - 1);
     const int q_valid = S - i * BT - half * 32;
-    const float* lse_s = vec + half * 32;
+    const float* lse_s = vec + (i & 1) * 128 + half * 32;
     const float* del_s = lse_s + 64;
     uint32_t rs[32], rp[32];
     tmem_ld32(tS, rs);
-    tmem_ld32(tdP, rp);
     tc_wait_ld();
+    TRACE(2);
+    mbar_wait(bar_dp, i & 1);    // dP^T(i) was issued right behind S^T(i): ready by now; its load flies under the exps
+    tc_fence_after();
+    tmem_ld32(tdP, rp);
     TRACE(3);
-    float p[32], st[32];
+    float p[32];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(st + 4 * g) = reinterpret_cast<const float4*>(lse_s)[g];
-    if (q_valid >= 32) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) p[e] = exp2f(__uint_as_float(rs[e]) * c - st[e]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? exp2f(__uint_as_float(rs[e]) * c - st[e]) : 0.f;
+    for (int g = 0; g < 8; ++g) {
+      const float4 l = reinterpret_cast<const float4*>(lse_s)[g];
+      p[4 * g + 0] = exp2f(__uint_as_float(rs[4 * g + 0]) * c - l.x);
+      p[4 * g + 1] = exp2f(__uint_as_float(rs[4 * g + 1]) * c - l.y);
+      p[4 * g + 2] = exp2f(__uint_as_float(rs[4 * g + 2]) * c - l.z);
+      p[4 * g + 3] = exp2f(__uint_as_float(rs[4 * g + 3]) * c - l.w);
     }
-    tmem_store_bf16_row(tS, p);                                // P^T over this thread's own S^T columns
+    if (q_valid < 32) {                                        // ragged last q tile: padding columns contribute nothing
+#pragma unroll
+      for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? p[e] : 0.f;
+    }
+    tmem_store_bf16_row_async(tS, p);                          // P^T over this thread's own S^T columns
     TRACE(4);
+    tc_wait_ld();
 #pragma unroll
-    for (int g = 0; g < 8; ++g) *reinterpret_cast<float4*>(st + 4 * g) = reinterpret_cast<const float4*>(del_s)[g];
-    if (q_valid >= 32) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) p[e] *= (__uint_as_float(rp[e]) - st[e]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) p[e] = (e < q_valid) ? p[e] * (__uint_as_float(rp[e]) - st[e]) : 0.f;
+    for (int g = 0; g < 8; ++g) {
+      const float4 d = reinterpret_cast<const float4*>(del_s)[g];
+      p[4 * g + 0] *= __uint_as_float(rp[4 * g + 0]) - d.x;
+      p[4 * g + 1] *= __uint_as_float(rp[4 * g + 1]) - d.y;
+      p[4 * g + 2] *= __uint_as_float(rp[4 * g + 2]) - d.z;
+      p[4 * g + 3] *= __uint_as_float(rp[4 * g + 3]) - d.w;
     }
-    tmem_store_bf16_row(tdP, p);                               // dS^T over this thread's own dP^T columns
+    tmem_store_bf16_row_async(tdP, p);                         // dS^T over this thread's own dP^T columns
+    tc_wait_st();
     tc_fence_before();
     TRACE(5);
     __syncthreads();
@@ -561,8 +587,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
         mbar_wait(bar_q(nbuf), ((i + 1) / DKV_NST) & 1);
         tc_fence_after();
         mma_ab_t(tmem_base, sK, sQ(nbuf));
+        tc_commit(bar_s);
         mma_ab_t(tmem_base + 64, sV, sdO(nbuf));
-        tc_commit(bar_12);
+        tc_commit(bar_dp);
       } else {
         tc_commit(bar_fin);
       }

@@ -10,6 +10,7 @@
 //   gemm_wgrad_kernel dW[N,K] += dY[M,N]^T · X[M,K]     both operands MN-major (reduction over rows),
 //                     split over M across CTAs, row-coalesced fp32 red.add into the gradient arena; the bias
 //                     gradient (column sums of dY) rides along as one extra N=16 MMA against a ones tile.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <map>
@@ -383,6 +384,186 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// gemm_tn2_kernel: the same GEMM on CTA PAIRS (thread-block cluster of 2, tcgen05 cta_group::2).
+// A pair owns a 256 x BN output tile: CTA r loads A rows [r*128, +128) and B rows [r*BN/2, +BN/2) of the tile, the
+// leader CTA issues one M=256 tcgen05.mma that reads both CTAs' shared memory, and each CTA drains its own 128 TMEM
+// lanes through the same fused epilogues.  Per SM and per k-block this moves 16 KB + BN*64 B from L2 instead of
+// 16 KB + BN*128 B: these GEMMs (K = 384..3072, ~85 flop/B per 128 x 256 tile) are bound by L2 -> SM bandwidth
+// (~43 B/clk/SM), not by the tensor pipe, so halving the B traffic is what buys time.
+// Barrier protocol (all barriers live at the same smem offset in both CTAs):
+//   full[s]   leader's only, count 2: leader's expect_tx(2 x stage bytes) + the peer producer's remote arrive;
+//             both producers' TMA bytes complete on it
+//   empty[s]  one per CTA, count 1: tcgen05.commit multicast to both CTAs when the MMAs that read the stage finish
+//   tfull[a]  one per CTA, count 1: commit multicast when the pair tile's accumulator is complete
+//   tempty[a] leader's only, count 2 x EPI_WARPS: every epilogue warp of both CTAs arrives after draining
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address -> rank 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar_leader, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {   // arrive on a (possibly remote) barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");   // NOT .release.cluster: that costs a MEMBAR.ALL.GPU per arrive
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {        // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+
+template <int BN>
+struct Tn2Cfg {
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;          // per CTA
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                EpiParams ep) {
+  using Cfg = Tn2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = stg_base + STAGING_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return base + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_n = (N + BN - 1) / BN, num_m2 = (M + 2 * BM - 1) / (2 * BM);
+  const int tiles = num_m2 * num_n;
+  const int kblocks = (K + BK - 1) / BK;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARPS && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(static_cast<uint32_t>(Cfg::TMEM_COLS)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == EPI_WARPS) {
+    if (elect_one()) {  // ===== TMA producer (both CTAs): own A rows and own half of the B rows =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < tiles; tile += n_pairs) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t lbar = full_bar(stage) & PEER_MASK;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          else mbar_arrive_cluster(lbar);
+          tma_load_2d_2sm(smem_a(stage), &tmA, lbar, kb * BK, m_blk * 2 * BM + static_cast<int>(rank) * BM);
+          tma_load_2d_2sm(smem_b(stage), &tmB, lbar, kb * BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    if (leader && elect_one()) {  // ===== MMA issuer: leader CTA only =====
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = pair; tile < tiles; tile += n_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_kmajor(smem_a(stage)), bdesc = umma_desc_kmajor(smem_b(stage));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit_2sm(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {  // ===== epilogue warps (both CTAs): own 128 rows of the pair tile =====
+    using T = EpiTraits<EPI>;
+    constexpr int COLS = T::COLS;
+    constexpr int NCHUNK = BN / COLS;
+    const int quarter = warp & 3, grp = warp >> 2;
+    const uint32_t stg = stg_base + warp * 2048;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < tiles; tile += n_pairs) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row_base = m_blk * 2 * BM + static_cast<int>(rank) * BM + quarter * 32;
+      uint4 pre[4];
+      if (T::HAS_OPERAND && n_blk * BN + grp * COLS < N)
+        operand_fetch<EPI>(ep, pre, lane, row_base, M, n_blk * BN + grp * COLS, N);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = grp; ch < NCHUNK; ch += EPI_WARPS / 4) {
+        const int n0 = n_blk * BN + ch * COLS;
+        if (n0 >= N) break;
+        uint4 cur[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = pre[i];
+        const int n_next = n0 + (EPI_WARPS / 4) * COLS;
+        if (T::HAS_OPERAND && ch + EPI_WARPS / 4 < NCHUNK && n_next < N)
+          operand_fetch<EPI>(ep, pre, lane, row_base, M, n_next, N);
+        epilogue_chunk<EPI>(ep, stg, lane, row_base, M, n0, N, taddr + ch * COLS, cur);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & PEER_MASK);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  cluster_sync();      // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers / TMEM
+  if (warp == EPI_WARPS + 1)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(static_cast<uint32_t>(Cfg::TMEM_COLS)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // wgrad: dW[n, k] += sum_m dY[m, n] * X[m, k]
 // ---------------------------------------------------------------------------------------------------
 template <int BNW>
@@ -565,21 +746,66 @@ static int launch_tn(const CUtensorMap& tA, const CUtensorMap& tB, int M, int N,
   return MOFO_OK;
 }
 
-static int pick_bn(int M, int N) {
-  static const int forced = [] { const char* e = getenv("MOFO_FORCE_BN"); return e ? atoi(e) : 0; }();   // tuning aid
-  if (forced == 128 || ((forced == 192 || forced == 256) && N >= forced)) return forced;
+template <int BN, int EPI>
+static int launch_tn2(const CUtensorMap& tA, const CUtensorMap& tB, int M, int N, int K, const EpiParams& ep, cudaStream_t s) {
+  using Cfg = Tn2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MOFO_CUDA(cudaFuncSetAttribute(gemm_tn2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  // persistent grid = the number of CTA pairs that are co-resident (a pair that had to wait for a free TPC would
+  // start its share of the tiles only after the others finished theirs)
+  static int max_pairs = 0;
+  if (max_pairs == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sm_count() & ~1); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    MOFO_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tn2_kernel<BN, EPI>, &cfg));
+    if (n < 1) { set_error("gemm_tn2: no co-resident CTA pair fits"); return MOFO_ERR_CUDA; }
+    max_pairs = n < sm_count() / 2 ? n : sm_count() / 2;
+    if (getenv("MOFO_GEMM_VERBOSE")) fprintf(stderr, "mofo: gemm_tn2<%d,%d> max active CTA pairs = %d\n", BN, EPI, n);
+  }
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+  MOFO_CUDA(launch_pdl(gemm_tn2_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, tA, tB, M, N, K, ep));
+  return MOFO_OK;
+}
+
+// Tile configuration = (CTA pairs or single CTAs) x BN.  Estimated cost = waves x per-tile time, the per-tile time
+// being the slowest of the tensor pipe (bn/2 clk per k16 step), the L2 -> SM operand traffic (~43 B/clk/SM measured
+// chip-wide; a pair member loads only half of the B tile) and the epilogue, plus a fixed per-tile overhead.
+// Calibrated on B200 against tools/prof_gemm_shapes.py; MOFO_GEMM_2CTA=0/1 and MOFO_FORCE_BN override (tuning aids).
+struct TileChoice { bool pairs; int bn; };
+static TileChoice pick_tiles(int M, int N, int K) {
+  static const int forced_bn = [] { const char* e = getenv("MOFO_FORCE_BN"); return e ? atoi(e) : 0; }();
+  static const int forced_pairs = [] { const char* e = getenv("MOFO_GEMM_2CTA"); return e ? atoi(e) : -1; }();
   const int sms = sm_count();
-  const int num_m = (M + BM - 1) / BM;
-  int best = 128;
+  TileChoice best{false, 128};
   double best_cost = 1e30;
-  const int cands[3] = {256, 192, 128};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    if (bn > 128 && N < bn) continue;
-    const int tiles = num_m * ((N + bn - 1) / bn);
-    const int waves = (tiles + sms - 1) / sms;
-    const double cost = static_cast<double>(waves) * (bn + 24);   // +24: per-tile fixed overhead in "columns"
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  for (int pairs = 0; pairs < 2; ++pairs) {
+    if (pairs && (M < 2 * BM || (sms & 1))) continue;
+    if (forced_pairs >= 0 && pairs != (forced_pairs != 0) && !(pairs == 0 && M < 2 * BM)) continue;
+    const int cands[3] = {256, 192, 128};
+    for (int i = 0; i < 3; ++i) {
+      const int bn = cands[i];
+      if (bn > 128 && N < bn) continue;
+      if (forced_bn && bn != forced_bn && !(forced_bn > N && bn == 128)) continue;
+      const int rows = pairs ? 2 * BM : BM;
+      const long tiles = static_cast<long>((M + rows - 1) / rows) * ((N + bn - 1) / bn);
+      const long slots = pairs ? sms / 2 : sms;
+      const double waves = static_cast<double>((tiles + slots - 1) / slots);
+      const double t_mma = (K / 16.0) * (bn / 2.0);
+      const double t_l2 = (BM + (pairs ? bn / 2 : bn)) * 2.0 * K / 43.0 * (pairs ? 1.0 : 0.85);
+      const double t_epi = bn * 14.0;
+      const double t = (t_mma > t_l2 ? (t_mma > t_epi ? t_mma : t_epi) : (t_l2 > t_epi ? t_l2 : t_epi)) + 700.0;
+      const double cost = waves * t;
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{pairs != 0, bn}; }
+    }
   }
   return best;
 }
@@ -590,6 +816,15 @@ static int dispatch_bn(int bn, const CUtensorMap& tA, const CUtensorMap& tB, int
     case 256: return launch_tn<256, EPI>(tA, tB, M, N, K, ep, s);
     case 192: return launch_tn<192, EPI>(tA, tB, M, N, K, ep, s);
     default:  return launch_tn<128, EPI>(tA, tB, M, N, K, ep, s);
+  }
+}
+
+template <int EPI>
+static int dispatch_bn2(int bn, const CUtensorMap& tA, const CUtensorMap& tB, int M, int N, int K, const EpiParams& ep, cudaStream_t s) {
+  switch (bn) {
+    case 256: return launch_tn2<256, EPI>(tA, tB, M, N, K, ep, s);
+    case 192: return launch_tn2<192, EPI>(tA, tB, M, N, K, ep, s);
+    default:  return launch_tn2<128, EPI>(tA, tB, M, N, K, ep, s);
   }
 }
 
@@ -643,13 +878,25 @@ int mofo_gemm_tn(const mofo_bf16* A, int lda, const mofo_bf16* B, int ldb, int M
     case MOFO_EPI_BIAS_BF16: case MOFO_EPI_PLAIN_BF16: break;
     default: MOFO_CHECK_ARG(false, "gemm_tn: unknown epilogue %d", epilogue);
   }
-  const int bn = pick_bn(M, N);
+  const TileChoice tc = pick_tiles(M, N, K);
+  const bool pairs = tc.pairs;
+  const int bn = tc.bn;
   CUtensorMap tA, tB;
   int rc = get_tmap(&tA, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = get_tmap(&tB, B, N, K, ldb, bn);
+  rc = get_tmap(&tB, B, N, K, ldb, pairs ? bn / 2 : bn);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pairs) {
+    switch (epilogue) {
+      case MOFO_EPI_BIAS_BF16:      return dispatch_bn2<MOFO_EPI_BIAS_BF16>(bn, tA, tB, M, N, K, ep, s);
+      case MOFO_EPI_BIAS_GELU_BF16: return dispatch_bn2<MOFO_EPI_BIAS_GELU_BF16>(bn, tA, tB, M, N, K, ep, s);
+      case MOFO_EPI_BIAS_RESID_F32: return dispatch_bn2<MOFO_EPI_BIAS_RESID_F32>(bn, tA, tB, M, N, K, ep, s);
+      case MOFO_EPI_PLAIN_BF16:     return dispatch_bn2<MOFO_EPI_PLAIN_BF16>(bn, tA, tB, M, N, K, ep, s);
+      case MOFO_EPI_GELU_BWD_BF16:  return dispatch_bn2<MOFO_EPI_GELU_BWD_BF16>(bn, tA, tB, M, N, K, ep, s);
+      default:                      return dispatch_bn2<MOFO_EPI_BIAS_POS_F32>(bn, tA, tB, M, N, K, ep, s);
+    }
+  }
   switch (epilogue) {
     case MOFO_EPI_BIAS_BF16:      return dispatch_bn<MOFO_EPI_BIAS_BF16>(bn, tA, tB, M, N, K, ep, s);
     case MOFO_EPI_BIAS_GELU_BF16: return dispatch_bn<MOFO_EPI_BIAS_GELU_BF16>(bn, tA, tB, M, N, K, ep, s);
