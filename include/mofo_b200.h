@@ -132,18 +132,15 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
  * group_rows = N_mask, in_group_rows = N, offset = N - N_mask; modeling_pretrain.py:156).
  * fwd: y bf16 [M,D] (dense), mean/rstd f32 [M].
  * bwd: dx = LN'(dy) (+ dres[row] if dres != NULL) written to dx_f32 / dx_bf16 at the mapped x rows (either may be
- *      NULL); dgamma/dbeta f32 [D] are accumulated (+=).  ws: caller-provided scratch of
- *      mofo_layernorm_bwd_ws_floats(D) floats, zero-filled once before its first use (the kernel leaves it ready for
- *      the next call; one ws per stream): 16 accumulator rows for the CTA partial sums + a ticket counter; the last
- *      CTA folds them into dgamma/dbeta.
+ *      NULL); dgamma/dbeta f32 [D] (16-byte aligned) are accumulated (+=) with one 16-byte vector reduction per
+ *      4 columns per CTA.
  */
-int64_t mofo_layernorm_bwd_ws_floats(int D);
 int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int D, float eps,
                        int group_rows, int in_group_rows, int in_row_offset, mofo_bf16* y, float* mean, float* rstd,
                        void* stream);
 int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                        const float* dres, int M, int D, int group_rows, int in_group_rows, int in_row_offset,
-                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, float* ws, void* stream);
+                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (6) Decoder input assembly, masked rows (modeling_pretrain.py:260-263): for each clip b and masked slot j,

@@ -31,8 +31,7 @@ SIGNATURES = {
     "mofo_attn_fwd": ([_P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
     "mofo_attn_bwd": ([_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
     "mofo_layernorm_fwd": ([_P, _P, _P, _I, _I, _F, _I, _I, _I, _P, _P, _P, _P], C.c_int),
-    "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
-    "mofo_layernorm_bwd_ws_floats": ([_I], C.c_int64),
+    "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
     "mofo_decoder_assemble_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_decoder_assemble_bwd": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
     "mofo_target_mse": ([_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P], C.c_int),
@@ -220,27 +219,13 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, M, D, eps=1e-6, group_rows=0, i
     return y
 
 
-_ln_ws = {}
-
-
-def layernorm_bwd_ws(D, device):
-    """Zero-initialised scratch for mofo_layernorm_bwd (per device and D; calls on one device are stream-ordered)."""
-    key = (str(device), D)
-    ws = _ln_ws.get(key)
-    if ws is None:
-        ws = torch.zeros(int(load().mofo_layernorm_bwd_ws_floats(D)), dtype=torch.float32, device=device)
-        _ln_ws[key] = ws
-    return ws
-
-
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres, M, D, dx_f32, dx_bf16, dgamma, dbeta, group_rows=0,
                   in_group_rows=0, in_row_offset=0):
     g = group_rows if group_rows > 0 else M
     ig = in_group_rows if in_group_rows > 0 else M
-    ws = layernorm_bwd_ws(D, x.device)
     _check(load().mofo_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), M, D, g, ig,
-                                     in_row_offset, _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _ptr(ws),
-                                     _stream()), "mofo_layernorm_bwd")
+                                     in_row_offset, _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _stream()),
+           "mofo_layernorm_bwd")
 
 
 def decoder_assemble_fwd(mask_token, pos, msk_idx, B, n_vis, n_msk, Dd, x_full):

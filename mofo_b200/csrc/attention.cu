@@ -89,6 +89,18 @@ __device__ __forceinline__ void tmem_store_bf16_row(uint32_t taddr, const float 
   for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
   tmem_st16(taddr, pk);
 }
+#ifndef MOFO_ATTN_PAD
+#define MOFO_ATTN_PAD 0          // tuning aid: extra dynamic smem per CTA to force lower occupancy in variant builds
+#endif
+#ifdef MOFO_ATTN_TRACE
+__device__ long long g_trace[64 * 8 * 2];
+#define TRACE_AT(it, slot) do { if (trace_on && (tid == 0 || tid == 255)) g_trace[((it) * 8 + (slot)) * 2 + (tid != 0)] = clock64(); } while (0)
+#define TRACE(slot) TRACE_AT(i, slot)
+#else
+#define TRACE_AT(it, slot) do { } while (0)
+#define TRACE(slot) do { } while (0)
+#endif
+
 // =================================================================================================
 // forward: CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles (double buffered).
 // TMEM: S [0,64) (P aliases it) | O [64,128).  smem 48.6 KB, 3 CTAs / SM.
@@ -172,9 +184,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 
   float m_ref = -INFINITY, l_run = 0.f;             // l_run: partial row sum over this thread's columns
+#ifdef MOFO_ATTN_TRACE
+  const bool trace_on = MOFO_ATTN_TRACE == 1 && blockIdx.x == 6 && blockIdx.y == 3 && blockIdx.z == 10;
+#endif
 
   for (int j = 0; j < n_kv; ++j) {
     const int buf = j & 1;
+    TRACE_AT(j, 0);
     mbar_wait(bar_s, j & 1);                        // S(j) ready; also: P(j-1)V(j-1) done -> P tile and K/V buffer buf^1 free
     tc_fence_after();
     if (warp_u == 0 && j >= 1 && j + 1 < n_kv && elect_one()) {       // refill the buffer tile j-1 used with tile j+1
@@ -184,8 +200,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     const int kv_valid = S - j * BT - half * 32;    // own columns >= kv_valid are padding (last tile only)
     uint32_t r[32];
+    TRACE_AT(j, 1);
     tmem_ld32(tS, r);
     tc_wait_ld();
+    TRACE_AT(j, 2);
     float mx = -INFINITY;
     if (kv_valid >= 32) {
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -201,7 +219,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     // the two half-row maxima are exchanged rounded UP to bf16: both threads of a row then take identical decisions
     xch[half * 128 + row] = __float2bfloat16_ru(mx);
+    TRACE_AT(j, 3);
     __syncthreads();
+    TRACE_AT(j, 4);
     mx = fmaxf(__bfloat162float(xch[row]), __bfloat162float(xch[128 + row])) * c;
     // lazy exponent reference: move it (and rescale l and the O row) only when the maximum grew by more than 2^8
     const bool bump = mx > m_ref + 8.0f;            // always true in the first tile (m_ref = -inf)
@@ -232,7 +252,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     l_run += rs;
     tc_fence_before();
+    TRACE_AT(j, 5);
     __syncthreads();
+    TRACE_AT(j, 6);
     if (warp_u == 0 && elect_one()) {
       tc_fence_after();
       mma_ptmem_t(tmem_base + 64, tmem_base, sV(buf), j != 0);   // O += P(j) V(j), P read from TMEM
@@ -245,6 +267,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_commit(bar_fin);
       }
     }
+    TRACE_AT(j, 7);
   }
 
   mbar_wait(bar_fin, 0);                // every MMA has completed: O is final, K/V smem is free
@@ -436,16 +459,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // backward, part 2: dK, dV.  CTA = 128 kv rows of one (clip, head); streams 64-row Q/dO tiles.
 // TMEM: S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256) -> 2 CTAs / SM.  smem 96.6 KB (4-stage Q/dO ring); P^T / dS^T alias S^T / dP^T in TMEM.
 // =================================================================================================
-#ifndef MOFO_ATTN_PAD
-#define MOFO_ATTN_PAD 0          // tuning aid: extra dynamic smem per CTA to force lower occupancy in variant builds
-#endif
-#ifdef MOFO_ATTN_TRACE
-__device__ long long g_trace[64 * 8 * 2];
-#define TRACE(slot) do { if (trace_on && (tid == 0 || tid == 255)) g_trace[(i * 8 + (slot)) * 2 + (tid != 0)] = clock64(); } while (0)
-#else
-#define TRACE(slot) do { } while (0)
-#endif
-
 constexpr int DKV_NST = 4;                                                            // Q/dO ring depth (prefetch distance 3)
 constexpr int DKV_SMEM = 2 * TILE_BYTES + DKV_NST * 2 * HTILE_BYTES + 1024 + 128;   // K,V, Q/dO ring, stats x2, barriers
 
@@ -498,7 +511,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
   const int kv = kv0 + row;
   const bool kv_ok = kv < S;
 #ifdef MOFO_ATTN_TRACE
-  const bool trace_on = blockIdx.x == 6 && blockIdx.y == 3 && blockIdx.z == 10;
+  const bool trace_on = MOFO_ATTN_TRACE == 3 && blockIdx.x == 6 && blockIdx.y == 3 && blockIdx.z == 10;
 #endif
 
   if (warp_u == 0 && elect_one()) {
@@ -649,11 +662,11 @@ int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_b
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MOFO_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    MOFO_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM + MOFO_ATTN_PAD));
     attr_set = true;
   }
   dim3 grid((S + AT - 1) / AT, H, B);
-  MOFO_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(ATT_THREADS), FWD_SMEM, static_cast<cudaStream_t>(stream), tq, tkv, S, H,
+  MOFO_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(ATT_THREADS), FWD_SMEM + MOFO_ATTN_PAD, static_cast<cudaStream_t>(stream), tq, tkv, S, H,
                        scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(out), lse));
   return MOFO_OK;
 }

@@ -181,7 +181,6 @@ __global__ void __launch_bounds__(192) gather_tubes_kernel(const float* __restri
 // (5) LayerNorm
 // =================================================================================================
 constexpr int LN_MAX_CHUNKS = 8;  // D <= 1024 (float4 chunk per lane per iteration)
-constexpr int LN_SLOTS = 16;      // accumulator rows for the parameter-gradient partials of layernorm_bwd
 
 __device__ __forceinline__ size_t map_row(int m, int group_rows, int in_group_rows, int in_row_offset) {
   return static_cast<size_t>(m / group_rows) * in_group_rows + in_row_offset + (m % group_rows);
@@ -235,51 +234,90 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 }
 
 // warp per row, grid-stride over rows; per-lane register partials of dgamma/dbeta, reduced through shared
-// memory per CTA and accumulated with one atomicAdd per column per CTA.
+// memory per CTA and accumulated with one 16-byte vector reduction per 4 columns per CTA.
 template <int NCH>
-__global__ void __launch_bounds__(256, (NCH <= 3 ? 3 : 2)) layernorm_bwd_kernel(
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres, int M, int D,
     int group_rows, int in_group_rows, int in_row_offset, float* __restrict__ dx_f32,
-    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ ws) {
+    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float red[];  // [warps][2*D]
-  __shared__ int s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int nch = D >> 2;
   float4 dg[NCH], db[NCH];
 #pragma unroll
   for (int i = 0; i < NCH; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
 
-  for (int m = blockIdx.x * warps + wid; m < M; m += gridDim.x * warps) {
+  // Rows are software-pipelined for D <= 384 (NCH <= 3): the loads of the warp's NEXT row are issued before the
+  // current row is reduced and stored, so a warp always has one row of x / dy / dres in flight.  (D = 768 would need
+  // 60 more registers per thread than the 128 available at 2 CTAs / SM.)
+  constexpr bool PIPE = NCH <= 3;
+  const int stride = gridDim.x * warps;
+  float4 xv[PIPE ? NCH : 1], rres[NCH];
+  uint2 d2[PIPE ? NCH : 1];
+  float mu = 0.f, rs = 0.f;
+  auto fetch = [&](int m, float4 (&xo)[NCH], uint2 (&dyo)[NCH], float4 (&ro)[NCH], float& muo, float& rso) {
     const size_t xrow = map_row(m, group_rows, in_group_rows, in_row_offset);
     const float4* xr = reinterpret_cast<const float4*>(x + xrow * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(m) * D);
-    const float mu = mean[m], rs = rstd[m];
-    float4 xh[NCH], g[NCH], rres[NCH];
-    float s1 = 0.f, s2 = 0.f;
-    if (dres) {   // issued together with x / dy: one global-latency phase per row instead of two
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        int ch = lane + i * 32;
-        if (ch < nch) rres[i] = reinterpret_cast<const float4*>(dres + xrow * D)[ch];
-      }
-    }
+    muo = mean[m]; rso = rstd[m];
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      int ch = lane + i * 32;
+      const int ch = lane + i * 32;
       if (ch < nch) {
-        float4 xv = xr[ch];
-        uint2 d2 = dyr[ch];
-        float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
-        float4 d = make_float4(bf16_lo(d2.x), bf16_hi(d2.x), bf16_lo(d2.y), bf16_hi(d2.y));
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
-        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
-        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
-        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        xo[i] = xr[ch];
+        dyo[i] = dyr[ch];
+        if (dres) ro[i] = reinterpret_cast<const float4*>(dres + xrow * D)[ch];
+      }
+    }
+  };
+  int m = blockIdx.x * warps + wid;
+  if constexpr (PIPE) {
+    if (m < M) fetch(m, xv, d2, rres, mu, rs);
+  }
+  for (; m < M; m += stride) {
+    const size_t xrow = map_row(m, group_rows, in_group_rows, in_row_offset);
+    float4 xn[PIPE ? NCH : 1], rn[PIPE ? NCH : 1];
+    uint2 dn[PIPE ? NCH : 1];
+    float mun = 0.f, rsn = 0.f;
+    if constexpr (PIPE) {
+      if (m + stride < M) fetch(m + stride, xn, dn, rn, mun, rsn);
+    }
+    float4 xh[NCH], g[NCH];
+    float s1 = 0.f, s2 = 0.f;
+    auto accum = [&](int i, int ch, const float4& xq, const uint2& dq) {
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + ch);
+      const float4 d = make_float4(bf16_lo(dq.x), bf16_hi(dq.x), bf16_lo(dq.y), bf16_hi(dq.y));
+      xh[i] = make_float4((xq.x - mu) * rs, (xq.y - mu) * rs, (xq.z - mu) * rs, (xq.w - mu) * rs);
+      g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+    };
+    if constexpr (PIPE) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int ch = lane + i * 32;
+        if (ch < nch) accum(i, ch, xv[i], d2[i]);
+      }
+    } else {                 // D > 384: x / dy are consumed chunk by chunk as they arrive (registers)
+      const float4* xr = reinterpret_cast<const float4*>(x + xrow * D);
+      const uint2* dyr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(m) * D);
+      mu = mean[m]; rs = rstd[m];
+      if (dres) {            // issued together with x / dy: one global-latency phase per row instead of two
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int ch = lane + i * 32;
+          if (ch < nch) rres[i] = reinterpret_cast<const float4*>(dres + xrow * D)[ch];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int ch = lane + i * 32;
+        if (ch < nch) accum(i, ch, xr[ch], dyr[ch]);
       }
     }
     s1 = warp_sum(s1) / D;
@@ -298,7 +336,15 @@ __global__ void __launch_bounds__(256, (NCH <= 3 ? 3 : 2)) layernorm_bwd_kernel(
         }
       }
     }
+    if constexpr (PIPE) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) { xv[i] = xn[i]; d2[i] = dn[i]; rres[i] = rn[i]; }
+      mu = mun; rs = rsn;
+    }
   }
+#ifdef MOFO_LN_SKIP_REDUCE      // tuning aid (variant builds only): bounds the cost of the parameter-gradient reduction
+  if (dg[0].x != 12345.678f) return;
+#endif
   // CTA reduction of the parameter-gradient partials
   float* mine = red + static_cast<size_t>(wid) * 2 * D;
 #pragma unroll
@@ -310,33 +356,16 @@ __global__ void __launch_bounds__(256, (NCH <= 3 ? 3 : 2)) layernorm_bwd_kernel(
     }
   }
   __syncthreads();
-  // CTA partials are spread over LN_SLOTS accumulator rows in ws (16x less atomic contention per address than adding
-  // into dgamma/dbeta directly); the last CTA to arrive (ticket counter in ws[0]) folds the rows into dgamma/dbeta
-  // and re-zeroes them for the next call.
-  float* slots = ws + 4;
-  float* my_slot = slots + static_cast<size_t>(blockIdx.x % LN_SLOTS) * 2 * D;
-  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
-    float s = 0.f;
-    for (int w2 = 0; w2 < warps; ++w2) s += red[static_cast<size_t>(w2) * 2 * D + c];
-    atomicAdd(my_slot + c, s);
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(reinterpret_cast<unsigned int*>(ws), 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
-      float v[LN_SLOTS];
-#pragma unroll
-      for (int g = 0; g < LN_SLOTS; ++g) v[g] = __ldcg(slots + static_cast<size_t>(g) * 2 * D + c);
-      float s = 0.f;
-#pragma unroll
-      for (int g = 0; g < LN_SLOTS; ++g) { s += v[g]; slots[static_cast<size_t>(g) * 2 * D + c] = 0.f; }
-      if (c < D) dgamma[c] += s;
-      else dbeta[c - D] += s;
+  // one 16-byte vector reduction per 4 columns per CTA straight into dgamma / dbeta (red.global.add.v4.f32): no
+  // workspace pass, no ticket, no fence - the kernel boundary publishes the sums
+  for (int c4 = threadIdx.x; c4 < (2 * D) >> 2; c4 += blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w2 = 0; w2 < warps; ++w2) {
+      const float4 v = reinterpret_cast<const float4*>(red + static_cast<size_t>(w2) * 2 * D)[c4];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws) = 0u;
+    const int c = c4 << 2;
+    atomicAdd(reinterpret_cast<float4*>(c < D ? dgamma + c : dbeta + (c - D)), s);
   }
 }
 
@@ -380,8 +409,7 @@ __global__ void assemble_bwd_kernel(const float* __restrict__ dx_full, int n_vis
       }
     }
     if (any) {
-      atomicAdd(dmask_token + 4 * c + 0, acc.x); atomicAdd(dmask_token + 4 * c + 1, acc.y);
-      atomicAdd(dmask_token + 4 * c + 2, acc.z); atomicAdd(dmask_token + 4 * c + 3, acc.w);
+      atomicAdd(reinterpret_cast<float4*>(dmask_token) + c, acc);      // one red.global.add.v4.f32
     }
   }
 }
@@ -680,17 +708,17 @@ int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, in
   return MOFO_OK;
 }
 
-int64_t mofo_layernorm_bwd_ws_floats(int D) { return static_cast<int64_t>(LN_SLOTS) * 2 * D + 4; }
-
 int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                        const float* dres, int M, int D, int group_rows, int in_group_rows, int in_row_offset,
-                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, float* ws, void* stream) {
-  MOFO_CHECK_ARG(dy && x && gamma && mean && rstd && dgamma && dbeta && ws, "layernorm_bwd: null pointer");
+                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, void* stream) {
+  MOFO_CHECK_ARG(dy && x && gamma && mean && rstd && dgamma && dbeta, "layernorm_bwd: null pointer");
+  MOFO_CHECK_ARG(((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0,
+                 "layernorm_bwd: dgamma / dbeta must be 16-byte aligned");
   MOFO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_CHUNKS && group_rows > 0, "layernorm_bwd: unsupported M=%d D=%d", M, D);
   const int warps = 8;
   int grid = (M + warps - 1) / warps;
   static const int cap_mul = [] { const char* e = getenv("MOFO_LN_CAP"); return e ? atoi(e) : 0; }();   // tuning aid
-  int cap = sm_count() * (cap_mul > 0 ? cap_mul : (D <= 512 ? 4 : 2));
+  int cap = sm_count() * (cap_mul > 0 ? cap_mul : 2);          // 2 CTAs / SM are resident (128 registers): one wave
   if (grid > cap) grid = cap;
   size_t smem = static_cast<size_t>(warps) * 2 * D * sizeof(float);
   const int nch = (D + 127) / 128;
@@ -701,7 +729,7 @@ int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, 
     MOFO_CUDA(launch_pdl(layernorm_bwd_kernel<NCH>, dim3(grid), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream), \
                          reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, M, D, group_rows,     \
                          in_group_rows, in_row_offset, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma,      \
-                         dbeta, ws));                                                                                  \
+                         dbeta));                                                                                  \
   } while (0)
   if (nch <= 1) MOFO_LN_BWD(1);
   else if (nch == 2) MOFO_LN_BWD(2);
@@ -726,6 +754,7 @@ int mofo_decoder_assemble_fwd(const float* mask_token, const float* pos, const i
 int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk, int Dd, float* dmask_token,
                               mofo_bf16* dvis, void* stream) {
   MOFO_CHECK_ARG(dx_full && dmask_token && dvis, "decoder_assemble_bwd: null pointer");
+  MOFO_CHECK_ARG((reinterpret_cast<uintptr_t>(dmask_token) & 15) == 0, "decoder_assemble_bwd: dmask_token must be 16-byte aligned");
   MOFO_CHECK_ARG(B > 0 && n_vis >= 0 && n_msk > 0 && Dd % 4 == 0, "decoder_assemble_bwd: bad shape");
   const int rows_per_cta = 16;
   dim3 grid((n_vis + n_msk + rows_per_cta - 1) / rows_per_cta, B);
