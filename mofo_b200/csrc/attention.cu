@@ -547,10 +547,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
       stat_next = qq < S ? stat_src[qq] : 0.f;
     }
     TRACE(0);
-    mbar_wait(bar_s, i & 1);     // S^T(i) ready; also covers the dV/dK MMAs of iteration i-1 -> ring stage (i-1)%NST is free
+    mbar_wait(bar_s, i & 1);     // S^T(i) ready (it was issued between the dV and dK MMAs of iteration i-1)
     tc_fence_after();
     TRACE(1);
-    if (warp_u == 0 && i + DKV_NST - 1 < n_q && elect_one()) load_q(i + DKV_NST - 1);
     const int q_valid = S - i * BT - half * 32;
     const float* lse_s = vec + (i & 1) * 128 + half * 32;
     const float* del_s = lse_s + 64;
@@ -558,8 +557,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     tmem_ld32(tS, rs);
     tc_wait_ld();
     TRACE(2);
-    mbar_wait(bar_dp, i & 1);    // dP^T(i) was issued right behind S^T(i): ready by now; its load flies under the exps
+    mbar_wait(bar_dp, i & 1);    // dP^T(i) ready; also covers dV/dK of iteration i-1 -> ring stage (i-1)%NST is free
     tc_fence_after();
+    if (warp_u == 0 && i + DKV_NST - 1 < n_q && elect_one()) load_q(i + DKV_NST - 1);
     tmem_ld32(tdP, rp);
     TRACE(3);
     float p[32];
@@ -594,16 +594,19 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
     TRACE(6);
     if (warp_u == 0 && elect_one()) {
       tc_fence_after();
+      // order on the (in-order) tensor pipe: dV(i), S^T(i+1), dK(i), dP^T(i+1) - the next score tile, which starts
+      // the next iteration's dependency chain, does not queue behind dK
       mma_ptmem_t(tmem_base + 128, tmem_base, sdO(buf), i != 0);       // dV += P^T dO   (A from TMEM)
-      mma_ptmem_t(tmem_base + 192, tmem_base + 64, sQ(buf), i != 0);   // dK += dS^T Q   (A from TMEM)
       if (i + 1 < n_q) {
         mbar_wait(bar_q(nbuf), ((i + 1) / DKV_NST) & 1);
         tc_fence_after();
-        mma_ab_t(tmem_base, sK, sQ(nbuf));
+        mma_ab_t(tmem_base, sK, sQ(nbuf));                             // S^T(i+1) over P^T(i), which dV has consumed
         tc_commit(bar_s);
-        mma_ab_t(tmem_base + 64, sV, sdO(nbuf));
+        mma_ptmem_t(tmem_base + 192, tmem_base + 64, sQ(buf), i != 0); // dK += dS^T Q   (A from TMEM)
+        mma_ab_t(tmem_base + 64, sV, sdO(nbuf));                       // dP^T(i+1) over dS^T(i)
         tc_commit(bar_dp);
       } else {
+        mma_ptmem_t(tmem_base + 192, tmem_base + 64, sQ(buf), i != 0);
         tc_commit(bar_fin);
       }
     }

@@ -389,28 +389,49 @@ __global__ void assemble_fwd_kernel(const float* __restrict__ mask_token, const 
 }
 
 // grid = (row chunks, B).  Threads own float4 column chunks; rows of the chunk are streamed.
+constexpr int ASM_RG = 4;          // row groups per CTA (blockDim.y)
 __global__ void assemble_bwd_kernel(const float* __restrict__ dx_full, int n_vis, int n_msk, int Dd, int rows_per_cta,
                                     float* __restrict__ dmask_token, __nv_bfloat16* __restrict__ dvis) {
   pdl_wait();
   pdl_trigger();
+  extern __shared__ float4 part[];                      // [ASM_RG][Dd / 4]
   const int b = blockIdx.y;
   const int N = n_vis + n_msk;
+  const int C4 = Dd >> 2;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
-  for (int c = threadIdx.x; c < (Dd >> 2); c += blockDim.x) {
-    float4 acc = make_float4(0, 0, 0, 0);
-    bool any = false;
-    for (int r = r0; r < r1; ++r) {
-      float4 v = reinterpret_cast<const float4*>(dx_full + (static_cast<size_t>(b) * N + r) * Dd)[c];
-      if (r < n_vis) {
-        uint2 p; p.x = pack_bf16(v.x, v.y); p.y = pack_bf16(v.z, v.w);
-        reinterpret_cast<uint2*>(dvis + (static_cast<size_t>(b) * n_vis + r) * Dd)[c] = p;
-      } else {
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; any = true;
+  const int c = threadIdx.x, ry = threadIdx.y;
+  float4 acc = make_float4(0, 0, 0, 0);
+  if (c < C4) {
+    const float4* src = reinterpret_cast<const float4*>(dx_full + static_cast<size_t>(b) * N * Dd) + c;
+    for (int r = r0 + ry; r < r1; r += 4 * ASM_RG) {    // 4 independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + u * ASM_RG;
+        v[u] = rr < r1 ? src[static_cast<size_t>(rr) * C4] : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + u * ASM_RG;
+        if (rr >= r1) continue;
+        if (rr < n_vis) {
+          uint2 p; p.x = pack_bf16(v[u].x, v[u].y); p.y = pack_bf16(v[u].z, v[u].w);
+          reinterpret_cast<uint2*>(dvis + (static_cast<size_t>(b) * n_vis + rr) * Dd)[c] = p;
+        } else {
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+        }
       }
     }
-    if (any) {
-      atomicAdd(reinterpret_cast<float4*>(dmask_token) + c, acc);      // one red.global.add.v4.f32
+    part[ry * C4 + c] = acc;
+  }
+  __syncthreads();
+  if (ry == 0 && c < C4 && r1 > n_vis) {               // this CTA saw masked rows: one 16-byte reduction per 4 columns
+#pragma unroll
+    for (int g = 1; g < ASM_RG; ++g) {
+      const float4 o = part[g * C4 + c];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
     }
+    atomicAdd(reinterpret_cast<float4*>(dmask_token) + c, acc);
   }
 }
 
@@ -756,9 +777,16 @@ int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk,
   MOFO_CHECK_ARG(dx_full && dmask_token && dvis, "decoder_assemble_bwd: null pointer");
   MOFO_CHECK_ARG((reinterpret_cast<uintptr_t>(dmask_token) & 15) == 0, "decoder_assemble_bwd: dmask_token must be 16-byte aligned");
   MOFO_CHECK_ARG(B > 0 && n_vis >= 0 && n_msk > 0 && Dd % 4 == 0, "decoder_assemble_bwd: bad shape");
-  const int rows_per_cta = 16;
-  dim3 grid((n_vis + n_msk + rows_per_cta - 1) / rows_per_cta, B);
-  MOFO_CUDA(launch_pdl(assemble_bwd_kernel, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), dx_full, n_vis, n_msk, Dd,
+  const int N = n_vis + n_msk;
+  int chunks = (2 * sm_count() + B - 1) / B;                   // ~2 CTAs per SM over the whole batch
+  if (chunks < 1) chunks = 1;
+  int rows_per_cta = (N + chunks - 1) / chunks;
+  if (rows_per_cta < 4 * ASM_RG) rows_per_cta = 4 * ASM_RG;
+  dim3 grid((N + rows_per_cta - 1) / rows_per_cta, B);
+  const int cx = ((Dd >> 2) + 31) / 32 * 32;
+  MOFO_CHECK_ARG(cx * ASM_RG <= 1024, "decoder_assemble_bwd: Dd=%d too wide", Dd);
+  const size_t smem = static_cast<size_t>(ASM_RG) * (Dd >> 2) * sizeof(float4);
+  MOFO_CUDA(launch_pdl(assemble_bwd_kernel, grid, dim3(cx, ASM_RG), smem, static_cast<cudaStream_t>(stream), dx_full, n_vis, n_msk, Dd,
                        rows_per_cta, dmask_token, reinterpret_cast<__nv_bfloat16*>(dvis)));
   return MOFO_OK;
 }
