@@ -790,10 +790,11 @@ static TileChoice pick_tiles(int M, int N, int K) {
   for (int pairs = 0; pairs < 2; ++pairs) {
     if (pairs && (M < 2 * BM || (sms & 1))) continue;
     if (forced_pairs >= 0 && pairs != (forced_pairs != 0) && !(pairs == 0 && M < 2 * BM)) continue;
-    const int cands[3] = {256, 192, 128};
-    for (int i = 0; i < 3; ++i) {
+    const int cands[4] = {256, 224, 192, 128};                     // 224: pairs only (3 full waves for N = 2304 / 3072 at M = 5120)
+    for (int i = 0; i < 4; ++i) {
       const int bn = cands[i];
       if (bn > 128 && N < bn) continue;
+      if (bn == 224 && !pairs) continue;
       if (forced_bn && bn != forced_bn && !(forced_bn > N && bn == 128)) continue;
       const int rows = pairs ? 2 * BM : BM;
       const long tiles = static_cast<long>((M + rows - 1) / rows) * ((N + bn - 1) / bn);
@@ -823,6 +824,7 @@ template <int EPI>
 static int dispatch_bn2(int bn, const CUtensorMap& tA, const CUtensorMap& tB, int M, int N, int K, const EpiParams& ep, cudaStream_t s) {
   switch (bn) {
     case 256: return launch_tn2<256, EPI>(tA, tB, M, N, K, ep, s);
+    case 224: return launch_tn2<224, EPI>(tA, tB, M, N, K, ep, s);
     case 192: return launch_tn2<192, EPI>(tA, tB, M, N, K, ep, s);
     default:  return launch_tn2<128, EPI>(tA, tB, M, N, K, ep, s);
   }

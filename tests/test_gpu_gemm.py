@@ -20,7 +20,8 @@ def rel(a, b):
 
 
 SHAPES = [(128, 128, 64), (256, 256, 128), (5120, 768, 768), (300, 384, 192), (128, 1152, 384), (640, 64, 128),
-          (1000, 2304, 768), (4096, 1536, 384), (513, 192, 1536), (5120, 3072, 768), (32, 128, 1536)]
+          (1000, 2304, 768), (4096, 1536, 384), (513, 192, 1536), (5120, 3072, 768), (32, 128, 1536),
+          (5120, 2304, 768), (50176, 384, 384), (384, 1152, 384)]   # incl. the CTA-pair tile widths 224 / 192 / 256
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
@@ -38,7 +39,7 @@ def test_gemm_tn_bias_and_plain(lib, M, N, K):
     assert e < 6e-3, f"bias rel err {e}"
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 1536, 384), (5120, 768, 3072)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 1536, 384), (5120, 768, 3072), (5120, 3072, 768), (6272, 384, 1536)])
 def test_gemm_tn_fused_epilogues(lib, M, N, K):
     torch.manual_seed(1)
     A = torch.randn(M, K, device="cuda").bfloat16(); B = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
