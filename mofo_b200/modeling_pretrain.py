@@ -24,6 +24,7 @@ stream, LayerNorm statistics, softmax and the loss are fp32; parameters, gradien
 from __future__ import annotations
 
 import math
+import os
 from functools import partial
 
 import numpy as np
@@ -166,6 +167,14 @@ class _Runner:
         self.graph_pool = None
         self.force_cast = False
         self.external_weights = False   # bf16 operand copies maintained by mofo_b200.optim_factory.FusedAdamW
+        # weight-gradient GEMMs are off the backward critical path (nothing reads dW before the stage's all-reduce), so
+        # they CAN run on a side stream and fill SMs that the dgrad / attention / LayerNorm chain leaves idle at kernel
+        # tails.  Measured on B200 (B=32 ViT-B): 13.31 -> 13.27 ms/step, i.e. within run-to-run noise - a wgrad CTA
+        # needs ~190 KB of shared memory and rarely finds an SM to co-reside on - so it is opt-in: MOFO_SIDE_WGRAD=1.
+        self.side_wgrad = os.environ.get("MOFO_SIDE_WGRAD", "0") == "1"
+        self._side = None
+        self._side_dirty = False
+        self._readers = {}          # data_ptr of a scratch tensor -> event after the side-stream wgrad that reads it
 
     # ---- memory -------------------------------------------------------------------------------------------
     def buf(self, name, shape, dtype):
@@ -175,6 +184,46 @@ class _Runner:
             t = torch.empty(*shape, dtype=dtype, device=self.device)
             self.bufs[key] = t
         return t
+
+    # ---- side stream for the weight-gradient GEMMs --------------------------------------------------------
+    def _wgrad(self, reads, *args, **kw):
+        """``_lib.gemm_wgrad(*args, **kw)`` ordered after everything enqueued so far, on the side stream.  ``reads``:
+        the scratch tensors it reads that the main stream overwrites later (guarded by ``_before_write``)."""
+        if not self.side_wgrad:
+            _lib.gemm_wgrad(*args, **kw)
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            _lib.gemm_wgrad(*args, **kw)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        for t in reads:
+            self._readers[t.data_ptr()] = done
+        self._side_dirty = True
+
+    def _before_write(self, *tensors):
+        """The main stream is about to overwrite these scratch tensors: wait for their side-stream readers."""
+        if not self._readers:
+            return
+        main = torch.cuda.current_stream(self.device)
+        for t in tensors:
+            ev = self._readers.pop(t.data_ptr(), None)
+            if ev is not None:
+                main.wait_event(ev)
+
+    def _join_side(self):
+        """Main stream waits for every weight gradient enqueued so far (before a stage's all-reduce / the optimizer)."""
+        if self._side_dirty:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self._readers.clear()
+            self._side_dirty = False
 
     def _ensure_device(self, device):
         if self.device != device:
@@ -358,30 +407,34 @@ class _Runner:
         h2 = self.buf(pre + ".h2", (M, D), bf); mean2 = self.buf(pre + ".mean2", (M,), f32); rstd2 = self.buf(pre + ".rstd2", (M,), f32)
         u = self.buf(pre + ".u", (M, Dh), bf); a = self.buf(pre + ".a", (M, Dh), bf)
         # fc2
-        _lib.gemm_wgrad(dxA16, a, g[name + ".mlp.fc2.weight"], dbias=g[name + ".mlp.fc2.bias"])
+        self._wgrad((dxA16,), dxA16, a, g[name + ".mlp.fc2.weight"], dbias=g[name + ".mlp.fc2.bias"])
         du = self.buf("bwd.du", (M, Dh), bf)
+        self._before_write(du)                                   # previous block's fc1 wgrad reads it
         _lib.gemm_tn(dxA16, wc[pre + ".fc2"][1], _lib.EPI_GELU_BWD_BF16, du, aux=u)
         # fc1
-        _lib.gemm_wgrad(du, h2, g[name + ".mlp.fc1.weight"], dbias=g[name + ".mlp.fc1.bias"])
+        self._wgrad((du,), du, h2, g[name + ".mlp.fc1.weight"], dbias=g[name + ".mlp.fc1.bias"])
         dh = self.buf("bwd.dh", (M, D), bf)
         _lib.gemm_tn(du, wc[pre + ".fc1"][1], _lib.EPI_PLAIN_BF16, dh)
         # norm2 (+ residual gradient)
+        self._before_write(dxB16)                                # previous block's proj wgrad
         _lib.layernorm_bwd(dh, xm, blk.norm2.weight, mean2, rstd2, dxA, M, D, dxB, dxB16, g[name + ".norm2.weight"],
                            g[name + ".norm2.bias"])
         # proj
-        _lib.gemm_wgrad(dxB16, o, g[name + ".attn.proj.weight"], dbias=g[name + ".attn.proj.bias"])
+        self._wgrad((dxB16,), dxB16, o, g[name + ".attn.proj.weight"], dbias=g[name + ".attn.proj.bias"])
         do = self.buf("bwd.do", (M, D), bf)
         _lib.gemm_tn(dxB16, wc[pre + ".proj"][1], _lib.EPI_PLAIN_BF16, do)
         # attention
         dqkv = self.buf("bwd.dqkv", (M, 3 * D), bf); delta = self.buf("bwd.delta", (B, H, S), f32)
+        self._before_write(dqkv)                                 # previous block's qkv wgrad
         _lib.attn_bwd(qkv, o, do, lse, B, S, H, blk.attn.scale, dqkv, delta)
         # qkv
         # q_bias / v_bias gradients: column sums of dqkv[:, :D] and dqkv[:, 2D:], written through a [3D] window whose
         # first D floats are q_bias.grad and whose last D floats are v_bias.grad (see _make_arena: a D-float gap sits
         # between them in the arena so the window is contiguous); the K third is skipped.
-        _lib.gemm_wgrad(dqkv, h1, g[name + ".attn.qkv.weight"], dbias=g[name + ".attn.q_bias"], skip=(D, 2 * D))
+        self._wgrad((dqkv,), dqkv, h1, g[name + ".attn.qkv.weight"], dbias=g[name + ".attn.q_bias"], skip=(D, 2 * D))
         _lib.gemm_tn(dqkv, wc[pre + ".qkv"][1], _lib.EPI_PLAIN_BF16, dh)
         # norm1 (+ residual gradient)
+        self._before_write(dxA16)                                # this block's fc2 wgrad
         _lib.layernorm_bwd(dh, x_in, blk.norm1.weight, mean1, rstd1, dxB, M, D, dxA, dxA16, g[name + ".norm1.weight"],
                            g[name + ".norm1.bias"])
 
@@ -398,7 +451,7 @@ class _Runner:
         C = m.decoder.num_classes
         # head
         hd = self.buf("dec.hd", (B * Nm, Dd), bf)
-        _lib.gemm_wgrad(dpred, hd, g["decoder.head.weight"], dbias=g["decoder.head.bias"])
+        self._wgrad((), dpred, hd, g["decoder.head.weight"], dbias=g["decoder.head.bias"])
         dhd = self.buf("bwd.dhd", (B * Nm, Dd), bf)
         _lib.gemm_tn(dpred, wc["head"][1], _lib.EPI_PLAIN_BF16, dhd)
         # decoder.norm on the masked rows; visible rows receive zero gradient from the head
@@ -416,7 +469,7 @@ class _Runner:
         dvis = self.buf("bwd.dvis", (B * Nv, Dd), bf)
         _lib.decoder_assemble_bwd(dxA, B, Nv, Nm, Dd, g["mask_token"], dvis)
         hn = self.buf("enc.hn", (B * Nv, D), bf)
-        _lib.gemm_wgrad(dvis, hn, g["encoder_to_decoder.weight"])
+        self._wgrad((), dvis, hn, g["encoder_to_decoder.weight"])
         dhn = self.buf("bwd.dhn", (B * Nv, D), bf)
         _lib.gemm_tn(dvis, wc["e2d"][1], _lib.EPI_PLAIN_BF16, dhn)
         exA = self.buf("bwd.enc.dxA", (B * Nv, D), f32); exA16 = self.buf("bwd.enc.dxA16", (B * Nv, D), bf)
@@ -425,6 +478,7 @@ class _Runner:
                            self.buf("enc.rstd", (B * Nv,), f32), None, B * Nv, D, exA, exA16, g["encoder.norm.weight"],
                            g["encoder.norm.bias"])
         if stage_done is not None:
+            self._join_side()
             stage_done(0)
         ne = len(m.encoder.blocks)
         last_stage = 1 + (ne - 1) // self.enc_group
@@ -433,10 +487,12 @@ class _Runner:
             self._block_bwd(f"enc{i}", m.encoder.blocks[i], g, x_in, exA, exA16, exB, exB16, B * Nv, Nv, B, D)
             stage = 1 + (ne - 1 - i) // self.enc_group
             if stage_done is not None and stage != last_stage and (i == 0 or 1 + (ne - i) // self.enc_group != stage):
+                self._join_side()
                 stage_done(stage)
         # patch embedding (no input gradient)
         A_pe = self.buf("A_pe", (B * Nv, 1536), bf)
-        _lib.gemm_wgrad(exA16, A_pe, g["encoder.patch_embed.proj.weight"], dbias=g["encoder.patch_embed.proj.bias"])
+        self._wgrad((), exA16, A_pe, g["encoder.patch_embed.proj.weight"], dbias=g["encoder.patch_embed.proj.bias"])
+        self._join_side()
         if stage_done is not None:
             stage_done(last_stage)
 

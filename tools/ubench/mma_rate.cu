@@ -27,29 +27,31 @@ __device__ __forceinline__ void csync() {
 }
 
 // MODE 0: 1-CTA, A smem.  MODE 1: 1-CTA, A TMEM.  MODE 2: 2-CTA (cluster of 2), A smem.
+// MODE 3: 1-CTA, both operands MN-major (wgrad layout).  MODE 4: 2-CTA, both MN-major.
 template <int MODE, int N>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t sA = base, sB = base + 16384, bar = base + 16384 + 32768, slot = bar + 8;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const bool leader = MODE != 2 || ctarank() == 0;
+  constexpr bool TWO = MODE == 2 || MODE == 4;
+  const bool leader = !TWO || ctarank() == 0;
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   if (warp == 0) {
-    if (MODE == 2) {
+    if (TWO) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else tmem_alloc(slot, 512);
   }
   tc_fence_before();
-  if (MODE == 2) csync(); else __syncthreads();
+  if (TWO) csync(); else __syncthreads();
   tc_fence_after();
   uint32_t tb; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tb) : "r"(slot));
   tb = __shfl_sync(0xffffffffu, tb, 0);
   long long t0 = 0, t1 = 0;
   if (warp == 0 && leader && elect_one()) {
-    const uint32_t idesc = umma_idesc_bf16(MODE == 2 ? 256 : 128, N, 0, 0);
-    const uint64_t ad = umma_desc_kmajor(sA), bd = umma_desc_kmajor(sB);
+    const uint32_t idesc = umma_idesc_bf16(TWO ? 256 : 128, N, MODE >= 3, MODE >= 3);
+    const uint64_t ad = MODE >= 3 ? umma_desc_mnmajor(sA, 8192) : umma_desc_kmajor(sA), bd = MODE >= 3 ? umma_desc_mnmajor(sB, 8192) : umma_desc_kmajor(sB);
     t0 = clock64();
     for (int r = 0; r < reps; ++r) {
 #pragma unroll
@@ -57,18 +59,20 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long* out) 
         if (MODE == 0) umma_bf16(tb, ad + 2 * k, bd + 2 * k, idesc, 1u);
         if (MODE == 1) umma_ts(tb, tb + 256 + 8 * k, bd + 2 * k, idesc);
         if (MODE == 2) umma_2sm(tb, ad + 2 * k, bd + 2 * k, idesc);
+        if (MODE == 3) umma_bf16(tb, ad + 128 * k, bd + 128 * k, idesc, 1u);
+        if (MODE == 4) umma_2sm(tb, ad + 128 * k, bd + 128 * k, idesc);
       }
     }
-    if (MODE == 2) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)1) : "memory");
+    if (TWO) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)1) : "memory");
     else tc_commit(bar);
     mbar_wait(bar, 0);
     t1 = clock64();
     if (blockIdx.x == 0) { out[0] = t1 - t0; }
   }
   tc_fence_before();
-  if (MODE == 2) csync(); else __syncthreads();
+  if (TWO) csync(); else __syncthreads();
   if (warp == 0) {
-    if (MODE == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
     else tmem_dealloc(tb, 512);
   }
 }
@@ -80,7 +84,7 @@ void run(const char* name, int reps, long long* d) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = MODE == 2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (MODE == 2 || MODE == 4) ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   for (int it = 0; it < 2; ++it) {
     cudaLaunchKernelEx(&cfg, rate_kernel<MODE, N>, reps, d);
@@ -98,6 +102,8 @@ int main() {
   const int reps = 512;
   run<0, 64>("1cta A=smem", reps, d);  run<0, 128>("1cta A=smem", reps, d);  run<0, 256>("1cta A=smem", reps, d);
   run<1, 64>("1cta A=tmem", reps, d);  run<1, 128>("1cta A=tmem", reps, d);  run<1, 256>("1cta A=tmem", reps, d);
+  run<3, 128>("1cta MN-major", reps, d); run<3, 192>("1cta MN-major", reps, d); run<3, 256>("1cta MN-major", reps, d);
+  run<4, 128>("2cta MN-major", reps, d); run<4, 256>("2cta MN-major", reps, d);
   run<2, 64>("2cta A=smem (per-SM N/2 of B)", reps, d); run<2, 128>("2cta A=smem", reps, d); run<2, 256>("2cta A=smem", reps, d);
   return 0;
 }
