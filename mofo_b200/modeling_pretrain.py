@@ -160,7 +160,7 @@ class _Runner:
         self.arena = None
         self.arena_views = None
         self.scratch_arena = None
-        self.enc_group = 4          # encoder blocks per gradient-sync stage
+        self.enc_group = int(os.environ.get("MOFO_ENC_GROUP", "4"))   # encoder blocks per gradient-sync stage
         self.stage_end = None
         self.graphs = {}            # (B, Nv, Nm, normalize, grad_scale) -> [CUDAGraph per sync stage] | None (capture failed)
         self.static_in = {}         # (B, Nv, Nm, T, size) -> (videos, vis_idx, msk_idx) device buffers the graphs read
