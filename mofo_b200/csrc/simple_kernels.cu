@@ -233,9 +233,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
 }
 
-// warp per row, grid-stride over rows; per-lane register partials of dgamma/dbeta, reduced through shared
-// memory per CTA and accumulated with one 16-byte vector reduction per 4 columns per CTA.
-template <int NCH>
+// SPLIT warps per row (1 for D <= 384, 2 above: each warp owns a contiguous half of the columns and the two exchange
+// their partial row sums through shared memory and a 64-thread named barrier), grid-stride over rows; per-lane
+// register partials of dgamma/dbeta, reduced through shared memory per CTA and accumulated with one 16-byte vector
+// reduction per 4 columns per CTA.
+template <int NCH, int SPLIT>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres, int M, int D,
@@ -243,16 +245,20 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float red[];  // [warps][2*D]
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  const int nch = D >> 2;
+  extern __shared__ float red[];  // [warps / SPLIT][2*D]
+  __shared__ float2 xs[2][8];     // SPLIT == 2: partial (s1, s2) of every warp, double buffered over the row loop
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = (blockDim.x >> 5) / SPLIT;   // warps: row slots per CTA
+  const int slot = wid / SPLIT, hw = wid % SPLIT;
+  const int nchw = (D >> 2) / SPLIT;                 // float4 chunks per warp
+  const int ch0 = hw * nchw;                         // first chunk of this warp's column range
+  const int nch = ch0 + nchw;                        // one past its last chunk
   float4 dg[NCH], db[NCH];
 #pragma unroll
   for (int i = 0; i < NCH; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
 
-  // Rows are software-pipelined for D <= 384 (NCH <= 3): the loads of the warp's NEXT row are issued before the
-  // current row is reduced and stored, so a warp always has one row of x / dy / dres in flight.  (D = 768 would need
-  // 60 more registers per thread than the 128 available at 2 CTAs / SM.)
+  // Rows are software-pipelined when a lane owns <= 3 chunks (D <= 384, or D = 768 split over two warps): the loads
+  // of the warp's NEXT row are issued before the current row is reduced and stored, so a warp always has one row of
+  // x / dy / dres in flight (more chunks per lane would not fit the 128 registers available at 2 CTAs / SM).
   constexpr bool PIPE = NCH <= 3;
   const int stride = gridDim.x * warps;
   float4 xv[PIPE ? NCH : 1], rres[NCH];
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     muo = mean[m]; rso = rstd[m];
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int ch = lane + i * 32;
+      const int ch = ch0 + lane + i * 32;
       if (ch < nch) {
         xo[i] = xr[ch];
         dyo[i] = dyr[ch];
@@ -273,7 +279,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
       }
     }
   };
-  int m = blockIdx.x * warps + wid;
+  int m = blockIdx.x * warps + slot;
+  int it = 0;
   if constexpr (PIPE) {
     if (m < M) fetch(m, xv, d2, rres, mu, rs);
   }
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     if constexpr (PIPE) {
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
-        const int ch = lane + i * 32;
+        const int ch = ch0 + lane + i * 32;
         if (ch < nch) accum(i, ch, xv[i], d2[i]);
       }
     } else {                 // D > 384: x / dy are consumed chunk by chunk as they arrive (registers)
@@ -310,21 +317,30 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
       if (dres) {            // issued together with x / dy: one global-latency phase per row instead of two
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
-          const int ch = lane + i * 32;
+          const int ch = ch0 + lane + i * 32;
           if (ch < nch) rres[i] = reinterpret_cast<const float4*>(dres + xrow * D)[ch];
         }
       }
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
-        const int ch = lane + i * 32;
+        const int ch = ch0 + lane + i * 32;
         if (ch < nch) accum(i, ch, xr[ch], dyr[ch]);
       }
     }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if constexpr (SPLIT == 2) {
+      if (lane == 0) xs[it & 1][wid] = make_float2(s1, s2);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+      const float2 o = xs[it & 1][wid ^ 1];
+      s1 += o.x; s2 += o.y;
+      ++it;
+    }
+    s1 /= D;
+    s2 /= D;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      int ch = lane + i * 32;
+      int ch = ch0 + lane + i * 32;
       if (ch < nch) {
         float4 o = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
                                rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
@@ -346,13 +362,14 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
   if (dg[0].x != 12345.678f) return;
 #endif
   // CTA reduction of the parameter-gradient partials
-  float* mine = red + static_cast<size_t>(wid) * 2 * D;
+  float* mine = red + static_cast<size_t>(slot) * 2 * D;
+  const int Dq = D >> 2;
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
-    int ch = lane + i * 32;
+    int ch = ch0 + lane + i * 32;
     if (ch < nch) {
       reinterpret_cast<float4*>(mine)[ch] = dg[i];
-      reinterpret_cast<float4*>(mine + D)[ch] = db[i];
+      reinterpret_cast<float4*>(mine)[Dq + ch] = db[i];
     }
   }
   __syncthreads();
@@ -736,28 +753,34 @@ int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, 
   MOFO_CHECK_ARG(((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0,
                  "layernorm_bwd: dgamma / dbeta must be 16-byte aligned");
   MOFO_CHECK_ARG(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_CHUNKS && group_rows > 0, "layernorm_bwd: unsupported M=%d D=%d", M, D);
-  const int warps = 8;
-  int grid = (M + warps - 1) / warps;
+  const int split = D > 384 ? 2 : 1;                          // warps per row
+  MOFO_CHECK_ARG((D >> 2) % split == 0, "layernorm_bwd: D=%d", D);
+  const int slots = 8 / split;                                 // rows in flight per CTA (8 warps)
+  int grid = (M + slots - 1) / slots;
   static const int cap_mul = [] { const char* e = getenv("MOFO_LN_CAP"); return e ? atoi(e) : 0; }();   // tuning aid
   int cap = sm_count() * (cap_mul > 0 ? cap_mul : 2);          // 2 CTAs / SM are resident (128 registers): one wave
   if (grid > cap) grid = cap;
-  size_t smem = static_cast<size_t>(warps) * 2 * D * sizeof(float);
-  const int nch = (D + 127) / 128;
-#define MOFO_LN_BWD(NCH)                                                                                               \
+  size_t smem = static_cast<size_t>(slots) * 2 * D * sizeof(float);
+  const int nch = (D / split + 127) / 128;                     // float4 chunks per lane
+#define MOFO_LN_BWD(NCH, SPLIT)                                                                                        \
   do {                                                                                                                 \
     if (smem + 1024 > 48 * 1024)                                                                                       \
-      MOFO_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    MOFO_CUDA(launch_pdl(layernorm_bwd_kernel<NCH>, dim3(grid), dim3(warps * 32), smem, static_cast<cudaStream_t>(stream), \
+      MOFO_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    MOFO_CUDA(launch_pdl(layernorm_bwd_kernel<NCH, SPLIT>, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), \
                          reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, M, D, group_rows,     \
                          in_group_rows, in_row_offset, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma,      \
-                         dbeta));                                                                                  \
+                         dbeta));                                                                                      \
   } while (0)
-  if (nch <= 1) MOFO_LN_BWD(1);
-  else if (nch == 2) MOFO_LN_BWD(2);
-  else if (nch == 3) MOFO_LN_BWD(3);
-  else if (nch == 4) MOFO_LN_BWD(4);
-  else if (nch <= 6) MOFO_LN_BWD(6);
-  else MOFO_LN_BWD(8);
+  if (split == 1) {
+    if (nch <= 1) MOFO_LN_BWD(1, 1);
+    else if (nch == 2) MOFO_LN_BWD(2, 1);
+    else MOFO_LN_BWD(3, 1);
+  } else {
+    if (nch <= 3) MOFO_LN_BWD(3, 2);
+    else if (nch == 4) MOFO_LN_BWD(4, 2);
+    else if (nch <= 6) MOFO_LN_BWD(6, 2);
+    else MOFO_LN_BWD(8, 2);
+  }
 #undef MOFO_LN_BWD
   MOFO_LAUNCH_CHECK("layernorm_bwd_kernel");
   return MOFO_OK;
