@@ -126,7 +126,10 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 3)
+#ifndef MOFO_FWD_CTAS
+#define MOFO_FWD_CTAS 3
+#endif
+__global__ void __launch_bounds__(ATT_THREADS, MOFO_FWD_CTAS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int S, int H,
                 float c /*scale*log2e*/, __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
