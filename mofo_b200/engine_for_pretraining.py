@@ -14,10 +14,18 @@ Two paths, chosen per call:
     target kernel, ``model(videos, mask)`` runs through autograd (kernel backward), and the scaler drives
     ``backward()`` / ``step()`` exactly as in the reference; DDP wrappers work unchanged on this path.
 Aliases for the two names ``run_mae_pretraining_BB.py`` calls but the reference never defines are exported.
+
+Host / device pipelining (fused path with ``FusedAdamW``): the reference reads ``loss.item()`` and calls
+``torch.cuda.synchronize()`` every step (:306, :429), which leaves the GPU idle while Python prepares the next step.
+Here the loss and the gradient norm of step i are copied to pinned host memory asynchronously and READ WHILE STEP i+1
+RUNS: every step's values still reach the meters / log writer, and a non-finite loss still ends training with the
+reference's message and ``sys.exit(1)`` - one step later, and the device-side guard of the optimizer kernel has
+already skipped that step's update.  ``MOFO_SYNC_EVERY_STEP=1`` restores the strict per-step synchronisation.
 """
 from __future__ import annotations
 
 import math
+import os
 import sys
 from typing import Iterable
 
@@ -47,37 +55,57 @@ def build_labels(videos, msk_idx, normalize_target=True):
 class _CudaPrefetcher:
     """Wraps the data loader: the H2D copies of batch i+1 (pinned host memory -> device, `non_blocking`) are issued on
     a copy stream while step i computes, so `videos.to(device)` (engine_for_pretraining.py:239-240) costs no step time
-    when the host keeps up.  Yields batches whose tensors already live on `device`."""
+    when the host keeps up.  Yields batches whose tensors already live on `device`.
+
+    The device side is two fixed staging slots per tensor (no allocator traffic, no `record_stream` bookkeeping): the
+    copy into a slot waits for an event recorded on the compute stream once the step that consumed the slot's previous
+    content has been enqueued."""
 
     def __init__(self, loader, device):
         self.loader, self.device = loader, device
         self.quiet = getattr(loader, "quiet", False)
+        self.slots = [{}, {}]           # per slot: field index -> device tensor
+        self.consumed = [None, None]    # per slot: event after the consumer's work (compute stream)
 
     def __len__(self):
         return len(self.loader)
 
-    def _load(self, it, stream):
+    def _stage(self, slot, k, t, stream):
+        if not (isinstance(t, torch.Tensor) and t.device.type == "cpu"):
+            return t
+        buf = self.slots[slot].get(k)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+            self.slots[slot][k] = buf
+        with torch.cuda.stream(stream):
+            buf.copy_(t, non_blocking=True)
+        return buf
+
+    def _load(self, it, stream, slot):
         try:
             videos, bbox, mask = next(it)
         except StopIteration:
             return None
-        with torch.cuda.stream(stream):
-            videos = videos.to(self.device, non_blocking=True)
-            mask = mask.to(self.device, non_blocking=True)
-        return videos, bbox, mask
+        if self.consumed[slot] is not None:
+            stream.wait_event(self.consumed[slot])
+        return self._stage(slot, 0, videos, stream), bbox, self._stage(slot, 2, mask, stream)
 
     def __iter__(self):
         stream = torch.cuda.Stream(device=self.device)
+        stream.wait_stream(torch.cuda.current_stream(self.device))
         it = iter(self.loader)
-        nxt = self._load(it, stream)
+        i = 0
+        nxt = self._load(it, stream, 0)
         while nxt is not None:
             cur = torch.cuda.current_stream(self.device)
-            cur.wait_stream(stream)
-            videos, bbox, mask = nxt
-            videos.record_stream(cur)
-            mask.record_stream(cur)
-            nxt = self._load(it, stream)          # overlaps with the step the caller is about to run
-            yield videos, bbox, mask
+            cur.wait_stream(stream)                          # batch i has landed
+            batch = nxt
+            nxt = self._load(it, stream, (i + 1) & 1)        # overlaps with the step the caller is about to run
+            yield batch
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))   # the caller has enqueued everything that reads batch i
+            self.consumed[i & 1] = ev
+            i += 1
 
 
 def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer: torch.optim.Optimizer,
@@ -96,6 +124,47 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
     fused = isinstance(loss_scaler, _utils.NativeScalerWithGradNormCount)
     sync = GradSync() if fused else None
     start_steps = start_steps or 0
+    pipelined = (fused and getattr(optimizer, "fused_mofo", False) and torch.device(device).type == "cuda"
+                 and os.environ.get("MOFO_SYNC_EVERY_STEP", "0") != "1")
+    pending = None                      # (event, pinned [loss, grad_norm], host-side values) of the step in flight
+    if pipelined:
+        pinned = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+        events = [torch.cuda.Event() for _ in range(2)]
+
+    def record(loss_value, grad_norm, loss_scale_value, max_lr, min_lr, weight_decay_value):
+        if not math.isfinite(loss_value):
+            print("Loss is {}, stopping training".format(loss_value))
+            sys.exit(1)
+        metric_logger.update(loss=loss_value)
+        metric_logger.update(loss_scale=loss_scale_value)
+        metric_logger.update(lr=max_lr)
+        metric_logger.update(min_lr=min_lr)
+        metric_logger.update(weight_decay=weight_decay_value)
+        metric_logger.update(grad_norm=grad_norm)
+        if log_writer is not None:
+            log_writer.update(loss=loss_value, head="loss")
+            log_writer.update(loss_scale=loss_scale_value, head="opt")
+            log_writer.update(lr=max_lr, head="opt")
+            log_writer.update(min_lr=min_lr, head="opt")
+            log_writer.update(weight_decay=weight_decay_value, head="opt")
+            log_writer.update(grad_norm=grad_norm, head="opt")
+            log_writer.set_step()
+
+    def flush(p):
+        ev, pin, rest = p
+        ev.synchronize()
+        record(float(pin[0]), float(pin[1]), *rest)
+
+    def group_stats():
+        min_lr, max_lr = 10., 0.
+        for group in optimizer.param_groups:
+            min_lr = min(min_lr, group["lr"])
+            max_lr = max(max_lr, group["lr"])
+        weight_decay_value = None
+        for group in optimizer.param_groups:
+            if group["weight_decay"] > 0:
+                weight_decay_value = group["weight_decay"]
+        return max_lr, min_lr, weight_decay_value
 
     if torch.device(device).type == "cuda":
         data_loader = _CudaPrefetcher(data_loader, torch.device(device))
@@ -126,6 +195,18 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
                 optimizer.attach(core)
                 grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=core.parameters(), arena=arena,
                                         loss_guard=True)
+                if pipelined:
+                    slot = step & 1
+                    pinned[slot][0:1].copy_(loss.detach().reshape(1), non_blocking=True)    # :306, read one step later
+                    pinned[slot][1:2].copy_(grad_norm.detach().reshape(1), non_blocking=True)
+                    events[slot].record()
+                    mine = (events[slot], pinned[slot], (loss_scaler.state_dict()["scale"],) + group_stats())
+                    if pending is not None:
+                        flush(pending)              # step i-1's loss / grad norm: the device is busy with step i
+                    pending = mine
+                    if lr_scheduler is not None:
+                        lr_scheduler.step_update(start_steps + step)
+                    continue
                 loss_value = loss.item()                                                # :306 (the step's D2H read)
                 if not math.isfinite(loss_value):
                     print("Loss is {}, stopping training".format(loss_value))
@@ -156,32 +237,12 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
 
         torch.cuda.synchronize()                                                        # :429
 
-        metric_logger.update(loss=loss_value)
-        metric_logger.update(loss_scale=loss_scale_value)
-        min_lr, max_lr = 10., 0.
-        for group in optimizer.param_groups:
-            min_lr = min(min_lr, group["lr"])
-            max_lr = max(max_lr, group["lr"])
-        metric_logger.update(lr=max_lr)
-        metric_logger.update(min_lr=min_lr)
-        weight_decay_value = None
-        for group in optimizer.param_groups:
-            if group["weight_decay"] > 0:
-                weight_decay_value = group["weight_decay"]
-        metric_logger.update(weight_decay=weight_decay_value)
-        metric_logger.update(grad_norm=grad_norm)
-
-        if log_writer is not None:
-            log_writer.update(loss=loss_value, head="loss")
-            log_writer.update(loss_scale=loss_scale_value, head="opt")
-            log_writer.update(lr=max_lr, head="opt")
-            log_writer.update(min_lr=min_lr, head="opt")
-            log_writer.update(weight_decay=weight_decay_value, head="opt")
-            log_writer.update(grad_norm=grad_norm, head="opt")
-            log_writer.set_step()
+        record(loss_value, grad_norm, loss_scale_value, *group_stats())
         if lr_scheduler is not None:
             lr_scheduler.step_update(start_steps + step)
 
+    if pending is not None:
+        flush(pending)
     core.check_mask_rows()
     metric_logger.synchronize_between_processes()                                       # :466
     if not metric_logger.quiet:

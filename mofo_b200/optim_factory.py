@@ -148,7 +148,10 @@ class FusedAdamW(torch.optim.Optimizer):
                 assert blk.attn.v_bias.data_ptr() == qb.data_ptr() + 8 * D, "arena must hold [q_bias | gap | v_bias]"
                 qkvbias[f"{tag}{i}.qkvbias"] = self.p_arena[off:off + 3 * D]
         runner.adopt_external_weights(wc, qkvbias)
-        self.hyper_host = torch.zeros(8 + 2 * len(self.param_groups), dtype=torch.float32).pin_memory()
+        # ring of pinned staging buffers: the async H2D copy of step i reads host memory when it EXECUTES, which may be
+        # after the host has started preparing step i+1 (the engine pipelines the host one step ahead of the device)
+        self.hyper_hosts = [torch.zeros(8 + 2 * len(self.param_groups), dtype=torch.float32).pin_memory() for _ in range(4)]
+        self.hyper_host = self.hyper_hosts[0]
         self.hyper = torch.zeros_like(self.hyper_host, device=dev)
         self._attached = core
         self._runner = runner
@@ -169,7 +172,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 p.grad = gv
         self._step += 1
         beta1, beta2 = self.param_groups[0]["betas"]
-        h = self.hyper_host
+        h = self.hyper_host = self.hyper_hosts[self._step % len(self.hyper_hosts)]
         h[0], h[1], h[2] = beta1, beta2, self.param_groups[0]["eps"]
         h[3] = 1.0 - beta1 ** self._step
         h[4] = math.sqrt(1.0 - beta2 ** self._step)
