@@ -70,6 +70,28 @@ __device__ __forceinline__ void mma_ptmem_t(uint32_t d_tmem, uint32_t p_tmem, ui
   for (int k = 0; k < 4; ++k)
     umma_bf16_ts(d_tmem, p_tmem + (k >> 1) * 32 + (k & 1) * 8, b0 + 128 * k, idesc, (accumulate || k != 0) ? 1u : 0u);
 }
+__device__ __forceinline__ void tmem_ld16a(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8_async(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16_async(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // same as tmem_store_bf16_row but WITHOUT the trailing tcgen05.wait::st: the caller waits once before handing over
 __device__ __forceinline__ void tmem_store_bf16_row_async(uint32_t taddr, const float (&v)[32]) {
@@ -103,7 +125,7 @@ __device__ long long g_trace[64 * 8 * 2];
 
 // =================================================================================================
 // forward: CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles (double buffered).
-// TMEM: S [0,64) (P aliases it) | O [64,128).  smem 48.6 KB, 3 CTAs / SM.
+// TMEM: S [0,64) (P aliases it) | O [64,128).  smem 48.6 KB, 64 registers, 4 CTAs / SM.
 // O accumulates in TMEM across the kv tiles (tcgen05.mma accumulate), so the threads never read it back inside the
 // loop.  The exponent reference m_ref is updated lazily: only when the running row maximum exceeds it by more than
 // 2^8 is the O row (and the row sum) rescaled in TMEM (tcgen05.ld / .st), which happens in the first tile(s) only;
@@ -113,23 +135,7 @@ __device__ long long g_trace[64 * 8 * 2];
 // =================================================================================================
 constexpr int FWD_SMEM = TILE_BYTES + 4 * HTILE_BYTES + 512 + 64;   // Q, K0,V0,K1,V1, max xchg, barriers
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-#ifndef MOFO_FWD_CTAS
-#define MOFO_FWD_CTAS 3
-#endif
-__global__ void __launch_bounds__(ATT_THREADS, MOFO_FWD_CTAS)
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int S, int H,
                 float c /*scale*log2e*/, __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -202,57 +208,72 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tma_load_2d(sV(buf ^ 1), &tm_kv, bar_kv(buf ^ 1), (2 * H + h) * 64, row0 + (j + 1) * BT);
     }
     const int kv_valid = S - j * BT - half * 32;    // own columns >= kv_valid are padding (last tile only)
-    uint32_t r[32];
-    TRACE_AT(j, 1);
-    tmem_ld32(tS, r);
-    tc_wait_ld();
-    TRACE_AT(j, 2);
+    // 64 registers -> 4 CTAs / SM: the score row is read from TMEM twice - once for the row maximum, then again in
+    // two 16-column halves for exp2 / pack / store - instead of being held in 32 registers (TMEM reads are cheap,
+    // a fourth resident CTA is worth 6 % at S = 1568).
     float mx = -INFINITY;
-    if (kv_valid >= 32) {
-      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    {
+      uint32_t r[32];
+      TRACE_AT(j, 1);
+      tmem_ld32(tS, r);
+      tc_wait_ld();
+      TRACE_AT(j, 2);
+      if (kv_valid >= 32) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int e = 0; e < 32; e += 8) {
+        for (int e = 0; e < 32; e += 8) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) m4[k] = fmax3(m4[k], __uint_as_float(r[e + 2 * k]), __uint_as_float(r[e + 2 * k + 1]));
+          for (int k = 0; k < 4; ++k) m4[k] = fmax3(m4[k], __uint_as_float(r[e + 2 * k]), __uint_as_float(r[e + 2 * k + 1]));
+        }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) if (e < kv_valid) mx = fmaxf(mx, __uint_as_float(r[e]));
       }
-      mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-    } else {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) if (e < kv_valid) mx = fmaxf(mx, __uint_as_float(r[e]));
     }
-    // the two half-row maxima are exchanged rounded UP to bf16: both threads of a row then take identical decisions
     xch[half * 128 + row] = __float2bfloat16_ru(mx);
     TRACE_AT(j, 3);
     __syncthreads();
     TRACE_AT(j, 4);
     mx = fmaxf(__bfloat162float(xch[row]), __bfloat162float(xch[128 + row])) * c;
-    // lazy exponent reference: move it (and rescale l and the O row) only when the maximum grew by more than 2^8
-    const bool bump = mx > m_ref + 8.0f;            // always true in the first tile (m_ref = -inf)
+    const bool bump = mx > m_ref + 8.0f;
     if (__any_sync(0xffffffffu, bump) && j > 0) {
       const float alpha = bump ? exp2f(m_ref - mx) : 1.0f;
-      uint32_t o[32];
-      tmem_ld32(tO, o);
-      tc_wait_ld();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-      tmem_st32(tO, o);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[16];
+        tmem_ld16a(tO + hh * 16, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+        tmem_st16_async(tO + hh * 16, o);
+      }
+      tc_wait_st();
       l_run *= alpha;
     }
     if (bump) m_ref = mx;
     float rs = 0.f;
-    float p[32];
-    if (kv_valid >= 32) {
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 32; ++e) { p[e] = exp2f(__uint_as_float(r[e]) * c - m_ref); s4[e & 3] += p[e]; }
-      rs = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-    } else {
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t r[16];
+      tmem_ld16a(tS + hh * 16, r);
+      tc_wait_ld();
+      uint32_t pk[8];
+      float s2[2] = {0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 32; ++e) { p[e] = (e < kv_valid) ? exp2f(__uint_as_float(r[e]) * c - m_ref) : 0.f; rs += p[e]; }
+      for (int e = 0; e < 16; e += 2) {
+        float p0 = exp2f(__uint_as_float(r[e]) * c - m_ref), p1 = exp2f(__uint_as_float(r[e + 1]) * c - m_ref);
+        if (kv_valid < 32) {
+          if (hh * 16 + e >= kv_valid) p0 = 0.f;
+          if (hh * 16 + e + 1 >= kv_valid) p1 = 0.f;
+        }
+        s2[0] += p0; s2[1] += p1;
+        pk[e >> 1] = pack_bf16(p0, p1);
+      }
+      rs += s2[0] + s2[1];
+      tmem_st8_async(tS + hh * 8, pk);          // P (bf16) over this thread's own, already consumed, S columns
     }
-    {   // P (bf16) goes to TMEM over this thread's own S columns (already in registers): no smem tile, no proxy fence
-      tmem_store_bf16_row(tmem_base + lane_off + half * 32, p);
-    }
+    tc_wait_st();
     l_run += rs;
     tc_fence_before();
     TRACE_AT(j, 5);
