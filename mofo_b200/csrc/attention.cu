@@ -346,15 +346,19 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
 }
 
 // =================================================================================================
-// backward, part 1: dQ.  CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles.
-// TMEM: S [0,64) | dP [64,128) | dQ [128,192) (256 allocated) -> 2 CTAs / SM.  smem 96 KB (4-stage K/V ring); dS aliases S in TMEM.
+// backward, part 1: dQ.  CTA = 128 q rows of one (clip, head); streams 64-row K/V tiles (2-stage TMA ring).
+// TMEM: [0,64) holds, in turn, S = Q K^T, then dP = dO V^T, then dS (bf16) | dQ [64,128) -> 128 columns.
+// S and dP are TIME-MULTIPLEXED through one 64-column region (the threads turn S into P, kept in registers, before dP
+// is issued): a second tensor-pipe round trip per tile, but the CTA needs 128 instead of 256 TMEM columns, 64 KB of
+// shared memory and <= 85 registers, so 3 CTAs fit per SM instead of 2 - the per-tile dependency chain, not the
+// tensor pipe, is what bounds these kernels.
 // Rows q >= S and kv >= S: garbage rows only pollute their own (never stored) output rows, so only the
 // reduction (column) index is masked, and only in the last tile.
 // =================================================================================================
-constexpr int DQ_NST = 4;                                                       // K/V ring depth (prefetch distance 3)
-constexpr int DQ_SMEM = 2 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES + 64;   // Q, dO, K/V ring
+constexpr int DQ_NST = 2;                                                       // K/V ring depth
+constexpr int DQ_SMEM = 2 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES + 128;   // Q, dO, K/V ring, barriers
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 3)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    const __grid_constant__ CUtensorMap tm_do, int S, int H, float c, float scale,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv) {
@@ -365,15 +369,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   auto sK = [&](int b) { return base + 2 * TILE_BYTES + (2 * b) * HTILE_BYTES; };
   auto sV = [&](int b) { return base + 2 * TILE_BYTES + (2 * b + 1) * HTILE_BYTES; };
   const uint32_t bars = base + 2 * TILE_BYTES + DQ_NST * 2 * HTILE_BYTES;
-  const uint32_t bar_q = bars, bar_12 = bars + 8, bar_fin = bars + 16, tmem_slot = bars + 56;
-  auto bar_kv = [&](int b) { return bars + 24 + 8 * b; };
+  const uint32_t bar_q = bars, bar_s = bars + 8, bar_dp = bars + 16, bar_fin = bars + 24, tmem_slot = bars + 56;
+  auto bar_kv = [&](int b) { return bars + 32 + 8 * b; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   const int q0 = blockIdx.x * AT, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * S;
   const int n_kv = (S + BT - 1) / BT;
-  auto load_kv = [&](int t) {      // thread 0: tile t -> ring stage t % DQ_NST
+  auto load_kv = [&](int t) {      // elected lane: tile t -> ring stage t % DQ_NST
     const int st = t % DQ_NST;
     mbar_expect_tx(bar_kv(st), 2 * HTILE_BYTES);
     tma_load_2d(sK(st), &tm_kv, bar_kv(st), (H + h) * 64, row0 + t * BT);
@@ -381,12 +385,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   };
 
   if (tid == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_12, 1); mbar_init(bar_fin, 1);
+    mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_fin, 1);
     for (int st = 0; st < DQ_NST; ++st) mbar_init(bar_kv(st), 1);
     fence_barrier_init();
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_do);
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -397,8 +401,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   pdl_wait();
   pdl_trigger();
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const uint32_t tS = tmem_base + lane_off + half * 32, tdP = tmem_base + lane_off + 64 + half * 32;
-  const uint32_t tdQ = tmem_base + lane_off + 128 + half * 32;
+  const uint32_t tS = tmem_base + lane_off + half * 32;            // S, then dP, then dS (bf16) in this thread's columns
+  const uint32_t tdQ = tmem_base + lane_off + 64 + half * 32;
 
   const int q = q0 + row;
   const bool q_ok = q < S;
@@ -409,47 +413,63 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     mbar_expect_tx(bar_q, 2 * TILE_BYTES);
     tma_load_2d(sQ, &tm_q, bar_q, h * 64, row0 + q0);
     tma_load_2d(sdO, &tm_do, bar_q, h * 64, row0 + q0);
-    for (int t = 0; t < DQ_NST - 1 && t < n_kv; ++t) load_kv(t);
+    for (int t = 0; t < DQ_NST && t < n_kv; ++t) load_kv(t);
     mbar_wait(bar_q, 0);
     mbar_wait(bar_kv(0), 0);
     tc_fence_after();
-    mma_ab_t(tmem_base, sQ, sK(0));            // S  = Q K^T
-    mma_ab_t(tmem_base + 64, sdO, sV(0));      // dP = dO V^T
-    tc_commit(bar_12);
+    mma_ab_t(tmem_base, sQ, sK(0));            // S(0) = Q K^T
+    tc_commit(bar_s);
   }
 
   for (int j = 0; j < n_kv; ++j) {
     const int buf = j % DQ_NST, nbuf = (j + 1) % DQ_NST;
-    mbar_wait(bar_12, j & 1);   // also covers the dQ MMA of iteration j-1 (tensor pipe is in-order) -> stage (j-1)%NST is free
+    mbar_wait(bar_s, j & 1);    // S(j) ready; also covers the dQ MMA of iteration j-1 -> stage (j-1) % NST is free
     tc_fence_after();
-    if (warp_u == 0 && j + DQ_NST - 1 < n_kv && elect_one()) load_kv(j + DQ_NST - 1);
+    if (warp_u == 0 && j >= 1 && j + 1 < n_kv && elect_one()) load_kv(j + 1);
     const int kv_valid = S - j * BT - half * 32;
-    uint32_t rs[32], rp[32];
-    tmem_ld32(tS, rs);
-    tmem_ld32(tdP, rp);
-    tc_wait_ld();
-    float ds[32];
-    if (kv_valid >= 32) {
+    float p[32];
+    {
+      uint32_t rs[32];
+      tmem_ld32(tS, rs);
+      tc_wait_ld();
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        ds[e] = exp2f(__uint_as_float(rs[e]) * c - my_lse) * (__uint_as_float(rp[e]) - my_delta);
-    } else {
+      for (int e = 0; e < 32; ++e) p[e] = exp2f(__uint_as_float(rs[e]) * c - my_lse);
+      if (kv_valid < 32) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        ds[e] = (e < kv_valid) ? exp2f(__uint_as_float(rs[e]) * c - my_lse) * (__uint_as_float(rp[e]) - my_delta) : 0.f;
+        for (int e = 0; e < 32; ++e) p[e] = (e < kv_valid) ? p[e] : 0.f;
+      }
     }
-    tmem_store_bf16_row(tS, ds);                               // dS (bf16) over this thread's own S columns
+    tc_fence_before();
+    __syncthreads();            // every thread has consumed S(j): the region is free for dP(j)
+    if (warp_u == 0 && elect_one()) {
+      tc_fence_after();
+      mma_ab_t(tmem_base, sdO, sV(buf));       // dP(j) = dO V^T over S(j)
+      tc_commit(bar_dp);
+    }
+    mbar_wait(bar_dp, j & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t rp[16], pk[8];
+      tmem_ld16a(tS + hh * 16, rp);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; e += 2)
+        pk[e >> 1] = pack_bf16(p[hh * 16 + e] * (__uint_as_float(rp[e]) - my_delta),
+                               p[hh * 16 + e + 1] * (__uint_as_float(rp[e + 1]) - my_delta));
+      tmem_st8_async(tS + hh * 8, pk);         // dS (bf16) over this thread's own, already consumed, dP columns
+    }
+    tc_wait_st();
     tc_fence_before();
     __syncthreads();
     if (warp_u == 0 && elect_one()) {
       tc_fence_after();
-      mma_ptmem_t(tmem_base + 128, tmem_base, sK(buf), j != 0);  // dQ += dS K, dS read from TMEM
+      mma_ptmem_t(tmem_base + 64, tmem_base, sK(buf), j != 0);  // dQ += dS K, dS read from TMEM
       if (j + 1 < n_kv) {
         mbar_wait(bar_kv(nbuf), ((j + 1) / DQ_NST) & 1);
         tc_fence_after();
-        mma_ab_t(tmem_base, sQ, sK(nbuf));
-        mma_ab_t(tmem_base + 64, sdO, sV(nbuf));
-        tc_commit(bar_12);
+        mma_ab_t(tmem_base, sQ, sK(nbuf));     // S(j+1) over dS(j), which the dQ MMA has consumed (in-order pipe)
+        tc_commit(bar_s);
       } else {
         tc_commit(bar_fin);
       }
@@ -476,7 +496,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 // =================================================================================================
