@@ -107,6 +107,46 @@ def test_engine_with_fused_optimizer_tracks_torch_optimizer():
     assert np.abs(a - b).max() < 2e-3 * np.abs(b).max(), (a, b)
 
 
+def test_engine_pipelined_host_reports_the_same_meters_as_strict_sync(monkeypatch, capsys):
+    """One step of host/device pipelining (loss read a step late) must not change what the engine reports: every
+    step's loss / grad norm reaches the meters, and a non-finite loss still exits with the reference's message."""
+    import numpy as np
+    from mofo_b200 import engine_for_pretraining as eng, utils as U
+    from mofo_b200.optim_factory import FusedAdamW
+    from oracle import mask_oracle as mo, target_oracle as tgt
+    cfg = mdl.tiny_config(img=64, frames=16)
+    boxes = tgt.synthetic_boxes(4, seed=10, size=64)
+    masks = torch.from_numpy(np.stack([mo.tube_mask_bb(boxes[b], mo.mt19937_words(b, 300), cfg.grid)[0] for b in range(4)]))
+
+    class Loader(list):
+        quiet = True
+    batches = Loader([(tgt.synthetic_clip(4, seed=20 + i, size=64).pin_memory(), torch.zeros(4, 16, 4, dtype=torch.long), masks)
+                      for i in range(7)])
+    stats = []
+    for strict in ("1", "0"):
+        monkeypatch.setenv("MOFO_SYNC_EVERY_STEP", strict)
+        model = build()
+        opt = FusedAdamW(groups(model), lr=2e-3, betas=(0.9, 0.95), weight_decay=0.05)
+        stats.append(eng.train_one_epoch_BB(model, batches, opt, torch.device("cuda"), 0, U.NativeScalerWithGradNormCount(),
+                                            max_norm=1.0, start_steps=0))
+    for k in ("loss", "grad_norm", "lr", "weight_decay"):
+        assert abs(stats[0][k] - stats[1][k]) <= 1e-6 * abs(stats[0][k]) + 1e-12, (k, stats)
+    # non-finite loss: same message and exit status as engine_for_pretraining.py:418-420, one step late
+    monkeypatch.setenv("MOFO_SYNC_EVERY_STEP", "0")
+    bad = Loader(list(batches[:3]))
+    v = bad[1][0].clone(); v[0, 0, 0, 0, 0] = float("nan")
+    bad[1] = (v.pin_memory(), bad[1][1], bad[1][2])
+    model = build()
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    opt = FusedAdamW(groups(model), lr=2e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    with pytest.raises(SystemExit) as ex:
+        eng.train_one_epoch_BB(model, bad, opt, torch.device("cuda"), 0, U.NativeScalerWithGradNormCount(), max_norm=1.0)
+    assert ex.value.code == 1
+    assert "stopping training" in capsys.readouterr().out
+    assert all(torch.isfinite(p).all() for p in model.parameters())      # the device-side guard skipped the bad update
+    assert any(not torch.equal(before[n], p) for n, p in model.named_parameters())   # step 0 was applied
+
+
 def test_example_script_trains_and_checkpoint_round_trips(tmp_path, monkeypatch):
     """examples/pretrain_synthetic.py = the reference's main() flow on synthetic data; the checkpoint it writes has the
     reference's state_dict schema and loads back into a fresh model + optimizer."""
