@@ -350,11 +350,12 @@ def run_ours(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         vid_bytes = B * 3 * 16 * 224 * 224 * 4
         e2e = {"value": B * world * args.steps / dt.item(), "unit": "clips/s",
-               "h2d_bytes_per_step": vid_bytes + B * 1568 * 8, "d2h_bytes_per_step": 4,
+               "h2d_bytes_per_step": vid_bytes + B * 1568 * 8, "d2h_bytes_per_step": 8,
                "ms_per_step": 1e3 * dt.item() / args.steps, "h2d_pinned_gbps": h2d_gbps,
                "h2d_ms_per_step_at_that_rate": vid_bytes / h2d_gbps / 1e6,
                "api": "mofo_b200.engine_for_pretraining.train_one_epoch_BB, pinned fp32 clips + f64 masks per step "
-                      "(H2D of batch i+1 overlaps step i on a copy stream)",
+                      "(H2D of batch i+1 overlaps step i on a copy stream; loss + grad norm of every step copied to "
+                      "pinned host memory and read by the host while the next step runs)",
                "uint8_input": {"value": B * world * args.steps / dt_u8, "unit": "clips/s", "h2d_bytes_per_step": vid_bytes // 4 + B * 1568 * 8,
                                "note": "same engine call fed raw uint8 clips (1 B/sample); normalisation on the GPU (mofo_normalize_u8)"}}
 
