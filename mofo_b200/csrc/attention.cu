@@ -325,24 +325,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // =================================================================================================
 // backward, part 0: delta[b,h,q] = sum_d dO * O
 // =================================================================================================
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int rows,
-                                  int S, int H, float* __restrict__ delta) {
+// 8 lanes share one (row, head): lane j reads the j-th 16-byte chunk of the 128-byte O and dO rows, so every warp
+// load covers 4 full rows (fully used sectors); 4 rows per thread in flight; 3 shuffles finish the dot product.
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ out,
+                                                         const __nv_bfloat16* __restrict__ dout, int rows, int S, int H,
+                                                         float* __restrict__ delta) {
   pdl_wait();
   pdl_trigger();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (row, head), head fastest
-  if (i >= rows * H) return;
-  const int row = i / H, h = i % H;
-  const uint4* o = reinterpret_cast<const uint4*>(out + static_cast<size_t>(i) * 64);
-  const uint4* d = reinterpret_cast<const uint4*>(dout + static_cast<size_t>(i) * 64);
-  float s = 0.f;
+  const int total = rows * H;                                       // (row, head) pairs, head fastest
+  const int j = threadIdx.x & 7;
+  const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;      // first pair of this 8-lane group
+  const int stride = (gridDim.x * blockDim.x) >> 3;
+  for (int base = g0; base < total; base += 4 * stride) {
+    uint4 a[4], bq[4];
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    uint4 a = __ldg(o + g), bq = __ldg(d + g);
-    s += bf16_lo(a.x) * bf16_lo(bq.x) + bf16_hi(a.x) * bf16_hi(bq.x) + bf16_lo(a.y) * bf16_lo(bq.y) + bf16_hi(a.y) * bf16_hi(bq.y) +
-         bf16_lo(a.z) * bf16_lo(bq.z) + bf16_hi(a.z) * bf16_hi(bq.z) + bf16_lo(a.w) * bf16_lo(bq.w) + bf16_hi(a.w) * bf16_hi(bq.w);
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * stride;
+      if (i < total) {
+        a[u] = __ldg(reinterpret_cast<const uint4*>(out + static_cast<size_t>(i) * 64) + j);
+        bq[u] = __ldg(reinterpret_cast<const uint4*>(dout + static_cast<size_t>(i) * 64) + j);
+      } else {
+        a[u] = make_uint4(0, 0, 0, 0); bq[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float s = bf16_lo(a[u].x) * bf16_lo(bq[u].x) + bf16_hi(a[u].x) * bf16_hi(bq[u].x) + bf16_lo(a[u].y) * bf16_lo(bq[u].y) +
+                bf16_hi(a[u].y) * bf16_hi(bq[u].y) + bf16_lo(a[u].z) * bf16_lo(bq[u].z) + bf16_hi(a[u].z) * bf16_hi(bq[u].z) +
+                bf16_lo(a[u].w) * bf16_lo(bq[u].w) + bf16_hi(a[u].w) * bf16_hi(bq[u].w);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      const int i = base + u * stride;
+      if (j == 0 && i < total) {
+        const int row = i / H, h = i % H;
+        const int b = row / S, q = row % S;
+        delta[(static_cast<size_t>(b) * H + h) * S + q] = s;
+      }
+    }
   }
-  const int b = row / S, q = row % S;
-  delta[(static_cast<size_t>(b) * H + h) * S + q] = s;
 }
 
 // =================================================================================================
@@ -739,9 +760,16 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
     MOFO_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM + MOFO_ATTN_PAD));
     attr_set = true;
   }
-  MOFO_CUDA(launch_pdl(attn_delta_kernel, dim3((static_cast<int>(rows) * H + 127) / 128), dim3(128), 0, s,
-                       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout),
-                       static_cast<int>(rows), S, H, delta));
+  {
+    const long pairs = static_cast<long>(rows) * H;                 // 8 lanes per pair, 4 pairs per thread
+    long blocks = (pairs * 8 / 4 + 255) / 256;
+    const long cap = 8L * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    MOFO_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s,
+                         reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout),
+                         static_cast<int>(rows), S, H, delta));
+  }
   dim3 grid((S + AT - 1) / AT, H, B);
   const float c = scale * 1.4426950408889634f;
   MOFO_CUDA(launch_pdl(attn_bwd_dq_kernel, grid, dim3(ATT_THREADS), DQ_SMEM + MOFO_ATTN_PAD, s, tq128, tq64, td128, S, H, c, scale, lse,
