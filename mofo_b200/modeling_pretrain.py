@@ -235,6 +235,23 @@ class _Runner:
             self.pos_enc = m.encoder_pos_embed[0].to(device).contiguous()
             self.pos_dec = m.pos_embed[0].to(device).contiguous()
 
+    def enc_stage_table(self):
+        """block index -> gradient-sync stage (1-based; stage 0 is the decoder).  Blocks are grouped from the last
+        (first to finish in backward) to the first.  Default: groups of ``enc_group``; ``MOFO_ENC_STAGES="4,4,2,2"``
+        gives explicit group sizes (a smaller final group shortens the all-reduce that nothing overlaps)."""
+        ne = len(self.m.encoder.blocks)
+        spec = os.environ.get("MOFO_ENC_STAGES")
+        sizes = [max(1, int(v)) for v in spec.split(",")] if spec else [self.enc_group] * ((ne + self.enc_group - 1) // self.enc_group)
+        table, i, stage = {}, ne - 1, 1
+        while i >= 0:
+            sz = sizes[min(stage - 1, len(sizes) - 1)]
+            for _ in range(sz):
+                if i >= 0:
+                    table[i] = stage
+                    i -= 1
+            stage += 1
+        return table
+
     def backward_order(self):
         """Parameter names in the order the backward pass finishes their gradients, with the stage index at which
         each becomes final: stage 0 = decoder (+ head, mask_token, encoder_to_decoder), then encoder blocks in
@@ -253,9 +270,10 @@ class _Runner:
             add(f"decoder.blocks.{i}", 0)
         add("mask_token", 0); add("encoder_to_decoder", 0); add("encoder.norm", 0)
         ne = len(m.encoder.blocks)
+        table = self.enc_stage_table()
         for i in range(ne - 1, -1, -1):
-            add(f"encoder.blocks.{i}", 1 + (ne - 1 - i) // self.enc_group)
-        last = 1 + (ne - 1) // self.enc_group
+            add(f"encoder.blocks.{i}", table[i])
+        last = table[0]
         add("encoder.patch_embed", last)
         assert len(order) == len(names)
         return order, stage_of, last + 1
@@ -481,12 +499,13 @@ class _Runner:
             self._join_side()
             stage_done(0)
         ne = len(m.encoder.blocks)
-        last_stage = 1 + (ne - 1) // self.enc_group
+        table = self.enc_stage_table()
+        last_stage = table[0]
         for i in range(ne - 1, -1, -1):
             x_in = self.buf("x0", (B * Nv, D), f32) if i == 0 else self.buf(f"enc{i - 1}.xo", (B * Nv, D), f32)
             self._block_bwd(f"enc{i}", m.encoder.blocks[i], g, x_in, exA, exA16, exB, exB16, B * Nv, Nv, B, D)
-            stage = 1 + (ne - 1 - i) // self.enc_group
-            if stage_done is not None and stage != last_stage and (i == 0 or 1 + (ne - i) // self.enc_group != stage):
+            stage = table[i]
+            if stage_done is not None and stage != last_stage and (i == 0 or table[i - 1] != stage):
                 self._join_side()
                 stage_done(stage)
         # patch embedding (no input gradient)
