@@ -115,3 +115,27 @@ def test_model_refuses_cpu_inputs():
     m = create_model("pretrain_mae_small_patch16_224", decoder_depth=4)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 16, 224, 224), torch.zeros(1, 1568, dtype=torch.bool))
+
+
+def test_backward_order_stages_cover_every_parameter_once(monkeypatch):
+    """Gradient-sync stages (mofo_b200/modeling_pretrain.py::_Runner.backward_order): decoder first, encoder blocks from
+    the last to the first in groups, patch embedding with the final group; every parameter in exactly one stage, stage
+    indices non-decreasing along the order (so every stage is a contiguous arena slice), for the default grouping and
+    for explicit group sizes."""
+    from mofo_b200.modeling_pretrain import create_model
+    m = create_model("pretrain_videomae_base_patch16_224", decoder_depth=4)
+    names = [n for n, _ in m.named_parameters()]
+    for spec, want_sizes in ((None, [4, 4, 4]), ("5,4,3", [5, 4, 3]), ("4,4,2,2", [4, 4, 2, 2]), ("7", [7, 5])):
+        if spec is None:
+            monkeypatch.delenv("MOFO_ENC_STAGES", raising=False)
+        else:
+            monkeypatch.setenv("MOFO_ENC_STAGES", spec)
+        order, stage_of, n_stages = m._runner.backward_order()
+        assert sorted(order) == sorted(names) and len(set(order)) == len(order)
+        stages = [stage_of[n] for n in order]
+        assert stages == sorted(stages) and stages[0] == 0 and stages[-1] == n_stages - 1
+        assert all(stage_of[n] == 0 for n in names if n.startswith(("decoder.", "mask_token", "encoder_to_decoder", "encoder.norm")))
+        table = m._runner.enc_stage_table()
+        sizes = [sum(1 for i in table if table[i] == s) for s in range(1, n_stages)]
+        assert sizes == want_sizes and table[11] == 1
+        assert stage_of["encoder.patch_embed.proj.weight"] == table[0] == n_stages - 1
