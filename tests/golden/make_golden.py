@@ -165,6 +165,7 @@ def main():
               encoder_num_classes=0, decoder_num_classes=1536, decoder_embed_dim=64, decoder_depth=1,
               decoder_num_heads=1, mlp_ratio=4, qkv_bias=True)),
         ("vit_s", model_oracle.CONFIGS["pretrain_mae_small_patch16_224"], 1, None),
+        ("vit_b", model_oracle.CONFIGS["pretrain_videomae_base_patch16_224"], 1, None),   # the headline configuration
     ]:
         from functools import partial
         if ref_kwargs is None:

@@ -29,6 +29,13 @@ def build(cfg):
     return m
 
 
+def sample(t, n):
+    """Same strided sampling as tests/golden/make_golden.py (SAMPLE_STRIDE = 9973)."""
+    f = t.detach().reshape(-1)
+    idx = (torch.arange(n, dtype=torch.int64) * 9973) % f.numel()
+    return f[idx].double().numpy()
+
+
 def inputs(cfg, B, seed):
     vid = tgt.synthetic_clip(B, seed=seed, size=cfg.img)
     boxes = tgt.synthetic_boxes(B, seed=seed + 1, size=cfg.img)
@@ -109,6 +116,38 @@ def test_vit_small_c1_step_matches_oracle():
     """BASELINE.json configs[0]: ViT-S, 1 clip 16x224x224, mask 0.9 / BB 0.75."""
     rep, *_ = compare(mdl.CONFIGS["pretrain_mae_small_patch16_224"], B=1)
     check(rep)
+
+
+def test_vit_base_step_matches_reference_golden():
+    """The CUDA path against fixtures generated by the REFERENCE ITSELF (tests/golden/make_golden.py, ViT-B, 1 clip):
+    loss, sampled outputs, all 218 gradient norms and sampled gradient entries - no oracle in between."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_golden.npz"))
+    cfg = mdl.CONFIGS["pretrain_videomae_base_patch16_224"]
+    sd = mdl.random_state_dict(cfg, seed=42, perturb=0.05)
+    vid = tgt.synthetic_clip(1, seed=101, size=cfg.img)
+    boxes = tgt.synthetic_boxes(1, seed=201, size=cfg.img)
+    mask = torch.from_numpy(np.stack([mo.tube_mask_bb(boxes[0], mo.mt19937_words(10, 600), cfg.grid)[0]])).to(torch.bool)
+    model = build(cfg)
+    model.load_state_dict(sd, strict=True)
+    model.cuda().train()
+    loss = model.pretrain_step(vid.cuda(), mask.cuda()).item()
+    assert abs(loss - float(g["vit_b_loss"])) <= 1e-3 * float(g["vit_b_loss"])
+    pred = model._runner.buf("pred", (1408, 1536), torch.bfloat16).float().cpu().view(1, 1408, 1536)
+    ref = torch.from_numpy(g["vit_b_out_sample"])
+    mine = torch.from_numpy(sample(pred, 2048))
+    assert ((mine - ref).norm() / ref.norm()).item() <= 2e-2
+    names = [str(s) for s in g["vit_b_grad_names"]]
+    grads = {n: p.grad.detach().float().cpu() for n, p in model.named_parameters()}
+    assert names == list(grads.keys())
+    for n, r in zip(names, g["vit_b_grad_norms"]):
+        assert abs(float(grads[n].double().norm()) - r) <= 3e-2 * r + 1e-9, (n, float(grads[n].double().norm()), r)
+    for k in g.files:
+        if k.startswith("vit_b_gsample::"):
+            n = k.split("::", 1)[1]
+            r = torch.from_numpy(g[k]).double(); m = torch.from_numpy(sample(grads[n], 128)).double()
+            assert ((m - r).norm() / r.norm()).item() <= 3e-2, n
+            assert torch.nn.functional.cosine_similarity(m, r, dim=0).item() >= 0.999, n
 
 
 def test_vit_base_step_matches_oracle():

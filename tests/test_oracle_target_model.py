@@ -62,13 +62,15 @@ def test_schema_counts():
     assert round(n["pretrain_videomae_large_patch16_224"] / 1e6, 2) == 317.78
 
 
-@pytest.mark.parametrize("tag", ["tiny", "vit_s"])
+@pytest.mark.parametrize("tag", ["tiny", "vit_s", "vit_b"])
 def test_model_matches_reference(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, "model_golden.npz"))
     if tag == "tiny":
         cfg, B = mdl.tiny_config(img=64, frames=16), 2
-    else:
+    elif tag == "vit_s":
         cfg, B = mdl.CONFIGS["pretrain_mae_small_patch16_224"], 1
+    else:
+        cfg, B = mdl.CONFIGS["pretrain_videomae_base_patch16_224"], 1      # the headline configuration
     sd = mdl.random_state_dict(cfg, seed=42, perturb=0.05)
     vid = tgt.synthetic_clip(B, seed=100 + B, size=cfg.img)
     boxes = tgt.synthetic_boxes(B, seed=200 + B, size=cfg.img)
