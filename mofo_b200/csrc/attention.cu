@@ -4,7 +4,11 @@
 // Layout: qkv bf16 [B*S, 3*H*64] (q | k | v), out / dout bf16 [B*S, H*64], lse / delta f32 [B,H,S].
 // All three kernels use 256 threads: each row of the 128-row tile is owned by two threads (32 of the 64 streamed
 // columns each) that read their accumulator slice straight from TMEM, so the softmax needs one bf16 exchange per row
-// and no shuffles.  Thread 0 additionally issues the TMA loads and tcgen05.mma.
+// and no shuffles.  One elected lane of warp 0 additionally issues the TMA loads and tcgen05.mma - from a branch
+// the compiler can prove warp-uniform (shfl-broadcast warp id + elect.sync), otherwise every UTCHMMA / UTMALDG gets
+// wrapped in a per-lane ELECT / R2UR / BRA.U.ANY loop that costs ~80 clk per instruction.
+// Occupancy is what these kernels live on (the per-tile chain MMA -> tcgen05.ld -> softmax -> tcgen05.st -> MMA is
+// ~2500 clk): forward 4 CTAs/SM (64 registers, 128 TMEM columns), dQ 3 (S and dP share one TMEM region), dK/dV 2.
 //   S = Q K^T and friends:  both operands K-major SW128 tiles [128 rows x 64 d] straight from TMA.
 //   P V / dS K / P^T dO ...: A = bf16 operand written by the threads straight into TENSOR MEMORY (tcgen05.st over their
 //                            own fp32 accumulator columns; tcgen05.mma with A in TMEM), so it never touches shared memory;

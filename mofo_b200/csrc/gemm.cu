@@ -7,6 +7,9 @@
 //                     128 x BN output tiles (BN = 128/192/256), BLOCK_K = 64 (one 128-byte swizzle row),
 //                     multi-stage smem ring, two TMEM accumulators so the epilogue of tile i overlaps the
 //                     main loop of tile i+1.
+//   gemm_tn2_kernel   the same GEMM and epilogues on CTA PAIRS (cluster of 2, tcgen05 cta_group::2): 256 x BN tiles
+//                     (BN = 128/192/224/256), each CTA loads its 128 A rows and half of the B tile; used whenever the
+//                     cost model in pick_tiles() says so (these layers are bound by L2 -> SM operand traffic).
 //   gemm_wgrad_kernel dW[N,K] += dY[M,N]^T · X[M,K]     both operands MN-major (reduction over rows),
 //                     split over M across CTAs, 16-byte vector red.add into the gradient arena; the bias
 //                     gradient (column sums of dY) rides along as one extra N=16 MMA against a ones tile.
