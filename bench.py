@@ -2,7 +2,7 @@
 """Benchmark of the MOFO pretraining step (BASELINE.json metric: ViT-B pretrain clips/s, 16x224^2, mask 0.9).
 
     python bench.py --gpus N --steps K --warmup W            # this repo (N>1: launched with torch.distributed.run)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the UNMODIFIED reference (baseline/_ref) on host cores
 
 A step = one pass of the hot path over one batch of 32 synthetic clips per GPU: tube masking (GPU kernel, per-clip
 MT19937 words) -> fused forward + target/MSE + backward -> gradient all-reduce (N>1) -> grad-norm -> AdamW.
@@ -34,7 +34,11 @@ def parse():
     ap.add_argument("--model", default="pretrain_videomae_base_patch16_224")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall budget of the reference arm")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall budget of the oracle-port fallback of the reference arm")
+    ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the CPU reference arm (fixed, independent of N)")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference's own eager step on the same GPU(s)")
+    ap.add_argument("--gpu-ref-steps", type=int, default=30)
+    ap.add_argument("--gpu-ref-warmup", type=int, default=8)
     return ap.parse_args()
 
 
@@ -131,12 +135,41 @@ def oracle_cpu_step_fn(model_name, threads):
     return step
 
 
+def reference_cpu(args, clips, steps, warmup):
+    """The reference's own train_one_epoch_BB (baseline/_ref, unmodified: its model, create_optimizer, GradScaler-based
+    scaler, target construction, autograd backward, AdamW) on the host cores, fp32 (CUDA autocast does not touch CPU ops)."""
+    import torch
+    from baseline import refrun
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    r = refrun.run("cpu", args.model, batch=clips, steps=steps, warmup=warmup, amp="fp16", pool=2)
+    r["cores"] = cores
+    return r
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
+    from baseline import refrun
+    if refrun.available():
+        n = min(args.ref_clips, args.batch)
+        r = reference_cpu(args, n, args.steps, args.warmup)
+        val = r["clips_per_s"]
+        sample = (f"{n} clips/step (fixed, independent of --gpus) x {args.steps} steps of the {args.batch}-clip batch; the unmodified "
+                  "reference from baseline/_ref through timm.create_model -> optim_factory.create_optimizer -> "
+                  "engine_for_pretraining.train_one_epoch_BB (fp32 on CPU, AdamW step included)")
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args), "global_batch": args.batch * args.gpus, "parallelism": f"dp{args.gpus}"},
+                "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "reference", "sample": sample},
+                "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "final_loss": r["loss"]}
+        print(json.dumps(line), flush=True)
+        return
     step = oracle_cpu_step_fn(args.model, cores)
     t1, _ = step(1)                                   # probe (also first-touch warm-up)
     total_steps = args.steps + args.warmup
@@ -220,6 +253,7 @@ def run_ours(args):
         words = torch.from_numpy(words.view(np.int32)).to(dev)
         pool.append((vid.contiguous(), bb, words))
     sync = GradSync()
+    sync.sync_parameters(model, opt)
     runner = model._runner
     runner._ensure_device(dev)
     arena = runner.grad_arena()
@@ -227,12 +261,31 @@ def run_ours(args):
     def device_step(i):
         vid, bb, words = pool[i % POOL]
         mask, vis_idx, msk_idx, used = gen.generate_batch(bb, words)
-        sync.begin(arena, runner.stage_end)
-        loss = model.pretrain_step(vid, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=True, grad_scale=sync.grad_scale,
-                                   zero_grad=True, stage_done=sync.stage_done)
-        sync.finish()
-        scaler(loss, opt, clip_grad=0, parameters=None, arena=arena, loss_guard=True)
+        loss, _ = eng.fused_step(model, opt, scaler, sync, vid, vis_idx, msk_idx, True, 0)
         return loss
+
+    def dp_check():
+        """N>1 only, during warm-up: the staged, overlapped all-reduce must leave on every rank the same gradients as ONE
+        plain all-reduce of the rank-local gradients (no dropped or doubly reduced slice), and all ranks must agree bit
+        for bit.  Uses the eager (non-staged-optimizer) path so the parameters are not touched."""
+        vid, bb, words = pool[0]
+        mask, vis_idx, msk_idx, used = gen.generate_batch(bb, words)
+        sync.begin(arena, runner.stage_end)
+        model.pretrain_step(vid, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=True, grad_scale=sync.grad_scale,
+                            zero_grad=True, stage_done=sync.stage_done)
+        sync.finish()
+        staged = arena.clone()
+        model.pretrain_step(vid, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=True, grad_scale=sync.grad_scale,
+                            zero_grad=True, stage_done=None)
+        local = arena.clone()
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+        rel = ((staged.double() - local.double()).norm() / local.double().norm()).item()
+        chk = torch.stack([staged.double().sum(), staged.double().pow(2).sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(lo, hi))
+        assert rel <= 1e-5 and same, f"data-parallel gradient check failed: rel {rel:.3e}, identical across ranks: {same}"
+        return {"staged_vs_single_allreduce_rel_l2": rel, "identical_across_ranks": same, "tolerance": 1e-5}
 
     def barrier():
         if world > 1:
@@ -242,6 +295,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                                   # started before warm-up: nvidia-smi needs ~0.3 s to produce its first row
+    dp = dp_check() if world > 1 else None
     for i in range(args.warmup):
         loss = device_step(i)
     barrier()
@@ -359,6 +413,36 @@ def run_ours(args):
                "uint8_input": {"value": B * world * args.steps / dt_u8, "unit": "clips/s", "h2d_bytes_per_step": vid_bytes // 4 + B * 1568 * 8,
                                "note": "same engine call fed raw uint8 clips (1 B/sample); normalisation on the GPU (mofo_normalize_u8)"}}
 
+    # ---- the reference's own eager step on the same GPU(s) (SURVEY §8d "GPU reference baseline"): unmodified modules from
+    # baseline/_ref through train_one_epoch_BB, fp16 autocast + GradScaler as authored and under bf16 autocast; DDP
+    # (find_unused_parameters=True, run_mae_pretraining_BB.py:229-231) at N>1.  Reported beside our numbers, never mixed in.
+    gpu_ref = None
+    if not args.no_gpu_reference:
+        from baseline import refrun
+        if refrun.available():
+            torch.cuda.empty_cache()
+            gpu_ref = {}
+            for tag, amp, host in (("fp16_as_authored", "fp16", False), ("bf16_autocast", "bf16", False), ("bf16_autocast_host_inputs", "bf16", True)):
+                try:
+                    r = refrun.run(dev, args.model, batch=B, steps=args.gpu_ref_steps, warmup=args.gpu_ref_warmup, amp=amp,
+                                   host_inputs=host, ddp=world > 1)
+                    tm = torch.tensor([r["ms_per_step"]], device=dev)
+                    if world > 1:
+                        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                    r["ms_per_step"] = tm.item()
+                    r["value"] = B * world / (tm.item() * 1e-3)
+                    r["unit"] = "clips/s"
+                    del r["clips_per_s"]
+                    gpu_ref[tag] = r
+                except Exception as e:                      # noqa: BLE001 - reported, never fatal for our own line
+                    gpu_ref[tag] = {"error": repr(e)[:300]}
+            gpu_ref["how"] = ("unmodified reference modules (baseline/_ref) via timm.create_model + optim_factory.create_optimizer + "
+                              "utils.NativeScalerWithGradNormCount + engine_for_pretraining.train_one_epoch_BB, eager PyTorch "
+                              f"{torch.__version__} (cuBLAS/cuDNN/ATen kernels), same B, synthetic clips, CUDA events around the epoch call"
+                              + (", DistributedDataParallel(find_unused_parameters=True)" if world > 1 else ""))
+        else:
+            gpu_ref = {"unavailable": "baseline/_ref not staged (python baseline/setup_ref.py needs /root/reference)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -370,12 +454,12 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": f"inputs larger than L2: {POOL} rotating {B * 3 * 16 * 224 * 224 * 4 >> 20} MiB batches per GPU",
-                       "optimizer": "mofo_b200.optim_factory.FusedAdamW: one mofo_adamw_step kernel over the flat fp32 arenas, also "
-                                    "emitting the bf16 W / W^T operand copies (SURVEY §8f-1)",
-                       "launch": "fused step replayed as 4 CUDA graphs (one per gradient-sync stage); roofline leg launches kernels individually"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "final_loss": final_loss,
+            "config": {"workload": workload_name(args), "global_batch": B * world, "parallelism": f"dp{world}"},
+            "notes": {"l2": f"inputs larger than L2: {POOL} rotating {B * 3 * 16 * 224 * 224 * 4 >> 20} MiB batches per GPU",
+                      "optimizer": "mofo_b200.optim_factory.FusedAdamW: one mofo_adamw_step kernel over the flat fp32 arenas, also "
+                                   "emitting the bf16 W / W^T operand copies (SURVEY §8f-1)",
+                      "launch": "fused step replayed as CUDA graphs (one per gradient-sync stage); roofline leg launches kernels individually"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "final_loss": final_loss, "gpu_reference": gpu_ref, "dp_check": dp,
             "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05, all fused-epilogue instances)",
                          "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": gemm_tflops / peaks["bf16_sustained"] if gemm_tflops else None,
@@ -390,12 +474,20 @@ def run_ours(args):
                          "frac_of_nominal_2250": step_tflops / 2250.0 if step_tflops else None, "gflop_per_clip": gflop}}
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        step = oracle_cpu_step_fn(args.model, cores)
-        t1, _ = step(1)
-        n = 2 if t1 < 6 else 1
-        ts = [step(n)[0] for _ in range(max(1, min(3, int(20 / max(t1 * n, 1e-9)))))]
-        line["cpu_baseline"] = {"value": n * len(ts) / sum(ts), "unit": "clips/s", "cores": cores, "kind": "port",
-                                "sample": f"{len(ts)} step(s) of {n} clip(s) of the same workload (oracle port: numpy mask + torch fp32 CPU fwd/target/MSE/bwd + AdamW)"}
+        from baseline import refrun
+        if refrun.available():
+            n = min(args.ref_clips, B)
+            r = reference_cpu(args, n, 3, 1)
+            line["cpu_baseline"] = {"value": r["clips_per_s"], "unit": "clips/s", "cores": cores, "kind": "reference",
+                                    "sample": f"3 steps (after 1 warm-up) of {n} clips of the same workload: the unmodified reference "
+                                              "(baseline/_ref) train_one_epoch_BB on the host cores, fp32, AdamW step included"}
+        else:
+            step = oracle_cpu_step_fn(args.model, cores)
+            t1, _ = step(1)
+            n = 2 if t1 < 6 else 1
+            ts = [step(n)[0] for _ in range(max(1, min(3, int(20 / max(t1 * n, 1e-9)))))]
+            line["cpu_baseline"] = {"value": n * len(ts) / sum(ts), "unit": "clips/s", "cores": cores, "kind": "port",
+                                    "sample": f"{len(ts)} step(s) of {n} clip(s) of the same workload (oracle port: numpy mask + torch fp32 CPU fwd/target/MSE/bwd + AdamW)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

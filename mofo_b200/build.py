@@ -15,7 +15,11 @@ LIB = os.path.join(HERE, "libmofo_sm100.so")
 SOURCES = ["runtime.cu", "simple_kernels.cu", "gemm.cu", "attention.cu", "optimizer.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "mofo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-              "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# --use_fast_math (flush-to-zero, approximate division / sqrt) is for the GEMM / attention epilogues and the streaming
+# kernels whose results are rounded to bf16 anyway; the optimizer keeps IEEE division / sqrt and denormals so that
+# adamw_kernel really is torch.optim.AdamW's arithmetic (exp_avg_sq of tiny gradients must not flush to zero)
+FAST_MATH = {"runtime.cu": True, "simple_kernels.cu": True, "gemm.cu": True, "attention.cu": True, "optimizer.cu": False}
 
 
 def _nvcc() -> str:
@@ -44,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src = os.path.join(CSRC, s)
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + (["--use_fast_math"] if FAST_MATH.get(s, True) else []) + ["-c", src, "-o", obj]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for s, p in procs:

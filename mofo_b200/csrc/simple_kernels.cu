@@ -148,7 +148,11 @@ __global__ void mask_indices_kernel(const uint8_t* __restrict__ mask, int B, int
     cm += __popc(balm);
     cv += __popc(balv);
   }
-  if (lane == 0 && cm != n_msk) atomicAdd(bad_rows, 1);
+  if (cm != n_msk) {        // malformed row: every index entry stays a valid token id (0), and the row is reported
+    for (int i = min(cm, n_msk) + lane; i < n_msk; i += 32) msk_idx[static_cast<size_t>(b) * n_msk + i] = 0;
+    for (int i = min(cv, n_vis) + lane; i < n_vis; i += 32) vis_idx[static_cast<size_t>(b) * n_vis + i] = 0;
+    if (lane == 0) atomicAdd(bad_rows, 1);
+  }
 }
 
 // =================================================================================================
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(192) gather_tubes_kernel(const float* __restri
   const int row = blockIdx.x;
   const int b = row / n_idx;
   const int hw = size >> 4;
-  const int tok = idx[row];
+  const int tok = min(max(idx[row], 0), (frames >> 1) * hw * hw - 1);     // never index outside the clip
   const int t = tok / (hw * hw), h = (tok / hw) % hw, w = tok % hw;
   const int seg = threadIdx.x >> 1, half = threadIdx.x & 1;
   const int c = seg >> 5, p0 = (seg >> 4) & 1, p1 = seg & 15;
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
   const int row = blockIdx.x;
   const int b = row / n_msk;
   const int hw = size >> 4;
-  const int tok = msk_idx[row];
+  const int tok = min(max(msk_idx[row], 0), (frames >> 1) * hw * hw - 1);   // never index outside the clip
   const int t = tok / (hw * hw), h = (tok / hw) % hw, w = tok % hw;
   const int tid = threadIdx.x;
   const int p0 = tid >> 6, p1 = (tid >> 2) & 15, q = tid & 3;

@@ -108,6 +108,36 @@ class _CudaPrefetcher:
             i += 1
 
 
+def fused_step(core, optimizer, loss_scaler, sync, videos, vis_idx, msk_idx, normalize_target=True, max_norm=0):
+    """One fused training step on device-resident inputs: forward + target/MSE + backward (CUDA graphs), the gradient
+    exchange overlapped with backward, gradient norm and the optimizer update.  Returns (loss, grad_norm) as CUDA tensors
+    without synchronising.  With ``FusedAdamW`` and no clipping the update runs stage by stage on the exchange stream
+    right behind each slice's all-reduce (``FusedAdamW.begin_staged``); with any other optimizer (or clipping, which
+    needs the whole norm first) the scaler drives ``optimizer.step()`` after the last slice, as utils.py:353-367 does.
+    With a non-fused optimizer the caller must check the loss before the update (the engine does)."""
+    runner = core._runner
+    runner._ensure_device(videos.device)
+    arena = runner.grad_arena()
+    fused_opt = getattr(optimizer, "fused_mofo", False)
+    if fused_opt:
+        optimizer.attach(core)
+    sync.sync_parameters(core, optimizer)                   # first step only: rank 0's weights everywhere (DDP ctor)
+    clip = max_norm is not None and max_norm > 0
+    staged = fused_opt and not clip and os.environ.get("MOFO_STAGED_OPT", "1") == "1"
+    on_stage = acc = None
+    if staged:
+        on_stage, acc = optimizer.begin_staged(loss_guard=runner.buf("loss", (1,), torch.float32))
+    sync.begin(arena, runner.stage_end, on_stage=on_stage)
+    loss = core.pretrain_step(videos, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=normalize_target,
+                              grad_scale=sync.grad_scale, zero_grad=True, stage_done=sync.stage_done)
+    sync.finish()
+    if not fused_opt:
+        return loss, None
+    grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=None, arena=arena, loss_guard=True,
+                            staged_sq_norm=acc)
+    return loss, grad_norm
+
+
 def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer: torch.optim.Optimizer,
                        device: torch.device, epoch: int, loss_scaler, max_norm: float = 0, patch_size: int = 16,
                        normlize_target: bool = True, log_writer=None, lr_scheduler=None, start_steps=None,
@@ -122,13 +152,14 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
         raise NotImplementedError("the target kernel is specialised for 16x16 patches, tubelet 2")
     core = _core(model)
     fused = isinstance(loss_scaler, _utils.NativeScalerWithGradNormCount)
+    train_one_epoch_BB.last_path = "fused" if fused else "autograd-compat"      # which of the two paths this call took
     sync = GradSync() if fused else None
     start_steps = start_steps or 0
     pipelined = (fused and getattr(optimizer, "fused_mofo", False) and torch.device(device).type == "cuda"
                  and os.environ.get("MOFO_SYNC_EVERY_STEP", "0") != "1")
     pending = None                      # (event, pinned [loss, grad_norm], host-side values) of the step in flight
     if pipelined:
-        pinned = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+        pinned = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(2)]   # loss, grad norm, bad mask rows
         events = [torch.cuda.Event() for _ in range(2)]
 
     def record(loss_value, grad_norm, loss_scale_value, max_lr, min_lr, weight_decay_value):
@@ -153,6 +184,7 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
     def flush(p):
         ev, pin, rest = p
         ev.synchronize()
+        core.check_mask_rows(int(pin[2]))        # the reference raises on that step (x[~mask].reshape, modeling_pretrain.py:90)
         record(float(pin[0]), float(pin[1]), *rest)
 
     def group_stats():
@@ -185,20 +217,15 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
             core._runner._ensure_device(videos.device)
             arena = core._runner.grad_arena()
             vis_idx, msk_idx = core.indices_from_mask(bool_masked_pos)
-            sync.begin(arena, core._runner.stage_end)
-            loss = core.pretrain_step(videos, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=normlize_target,
-                                      grad_scale=sync.grad_scale, zero_grad=True, stage_done=sync.stage_done)
-            sync.finish()
+            loss, grad_norm = fused_step(core, optimizer, loss_scaler, sync, videos, vis_idx, msk_idx, normlize_target, max_norm)
             if getattr(optimizer, "fused_mofo", False):
                 # the fused optimizer skips the update on the device when the loss is not finite, so the whole step
                 # (incl. the parameter update) is enqueued before the single host read of the loss
-                optimizer.attach(core)
-                grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=core.parameters(), arena=arena,
-                                        loss_guard=True)
                 if pipelined:
                     slot = step & 1
                     pinned[slot][0:1].copy_(loss.detach().reshape(1), non_blocking=True)    # :306, read one step later
                     pinned[slot][1:2].copy_(grad_norm.detach().reshape(1), non_blocking=True)
+                    pinned[slot][2:3].copy_(core._bad_rows, non_blocking=True)
                     events[slot].record()
                     mine = (events[slot], pinned[slot], (loss_scaler.state_dict()["scale"],) + group_stats())
                     if pending is not None:
@@ -236,6 +263,7 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
         loss_scale_value = loss_scaler.state_dict()["scale"]
 
         torch.cuda.synchronize()                                                        # :429
+        core.check_mask_rows()
 
         record(loss_value, grad_norm, loss_scale_value, *group_stats())
         if lr_scheduler is not None:

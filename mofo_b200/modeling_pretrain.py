@@ -564,6 +564,10 @@ class _Runner:
             self.graphs[key] = graphs
         if graphs is None:                                     # capture unavailable: same kernels, launched one by one
             return self.step_eager(sv, si, sm, normalize_target, grad_scale, True, stage_done)
+        if self.external_weights:
+            # the optimizer kernel maintains the bf16 operand copies, so the graphs hold no casts; if something else
+            # changed the fp32 parameters since (load_state_dict, a broadcast, manual edits) re-cast eagerly first
+            self.prepare_weights()
         self.shape = (B, Nv, Nm)
         for k, (g, n_kernels) in enumerate(graphs):
             g.replay()
@@ -699,14 +703,17 @@ class PretrainVisionTransformer(nn.Module):
         if mask.dtype != torch.bool and mask.dtype != torch.uint8:
             mask = mask.to(torch.bool)
         mask = mask.contiguous()
-        if self._n_msk is None:
-            self._n_msk = int(mask[0].sum().item())
+        if self._n_msk is None or self._n_msk[0] != mask.shape[1]:
+            self._n_msk = (mask.shape[1], int(mask[0].sum().item()))   # per token count N; rows are verified on device
         if self._bad_rows is None or self._bad_rows.device != mask.device:
             self._bad_rows = torch.zeros(1, dtype=torch.int32, device=mask.device)
-        return _lib.mask_indices(mask, self._n_msk, self._bad_rows)
+        return _lib.mask_indices(mask, self._n_msk[1], self._bad_rows)
 
-    def check_mask_rows(self):
-        if self._bad_rows is not None and int(self._bad_rows.item()) != 0:
+    def check_mask_rows(self, count=None):
+        """``count``: a host copy of the device counter (the engine reads it with each step's loss); None reads it now."""
+        if count is None:
+            count = int(self._bad_rows.item()) if self._bad_rows is not None else 0
+        if count != 0:
             raise RuntimeError("mask rows with unequal masked-token counts (the reference's x[~mask].reshape(B,-1,C) "
                                "raises here too, modeling_pretrain.py:90)")
 

@@ -118,6 +118,11 @@ class FusedAdamW(torch.optim.Optimizer):
         self.w16 = torch.zeros(max(w16_elems, 8), dtype=torch.bfloat16, device=dev)
         self.segs = torch.tensor(segs, dtype=torch.int64, device=dev)
         self.tiles = torch.tensor(tiles, dtype=torch.int32, device=dev)
+        # tiles follow the arena (= backward completion) order, so the tiles of gradient-sync stage k are the contiguous
+        # range [stage_tile_end[k-1], stage_tile_end[k]): the staged step updates a stage as soon as its slice is reduced
+        self.stage_tile_end = []
+        for end in runner.stage_end:
+            self.stage_tile_end.append(sum(1 for sg, _ in tiles if segs[sg][0] < end))
         # move parameter storage into the arena (values preserved); moments become views too (state_dict layout of torch AdamW)
         with torch.no_grad():
             for name, p in named.items():
@@ -157,6 +162,41 @@ class FusedAdamW(torch.optim.Optimizer):
         self._runner = runner
         return self
 
+    # ---- staged step: one launch per gradient-sync stage, driven by mofo_b200.dp.GradSync ------------------------
+    @torch.no_grad()
+    def begin_staged(self, loss_guard=None):
+        """Call BEFORE the step's backward is enqueued: advances the step count, uploads this step's hyper-parameters and
+        returns ``(on_stage, sq_norm_acc)``.  ``on_stage(k, lo, hi)`` (run by GradSync on its stream once stage k's slice
+        is final) adds that slice's squared norm to ``sq_norm_acc`` and updates its parameters / bf16 operand copies;
+        stage k's weights are not read again in this step once its gradients exist.  No clipping on this path (the
+        clip coefficient needs the norm of ALL slices first): the scaler falls back to ``step()`` when clipping is on."""
+        if self._attached is None:
+            raise RuntimeError("FusedAdamW.begin_staged() before attach(model)")
+        garena = self._runner.grad_arena()
+        self._upload_hyper()
+        acc = torch.zeros(1, dtype=torch.float32, device=garena.device)
+        ends = self.stage_tile_end
+
+        def on_stage(k, lo, hi):
+            _lib.sq_norm_f32(garena[lo:hi], acc)
+            t0 = ends[k - 1] if k > 0 else 0
+            if ends[k] > t0:
+                _lib.adamw_step(self.p_arena, garena, self.m_arena, self.v_arena, self.w16, self.segs, self.tiles[t0:ends[k]],
+                                self.hyper, None, loss_guard)
+        return on_stage, acc
+
+    def _upload_hyper(self):
+        self._step += 1
+        beta1, beta2 = self.param_groups[0]["betas"]
+        h = self.hyper_host = self.hyper_hosts[self._step % len(self.hyper_hosts)]
+        h[0], h[1], h[2] = beta1, beta2, self.param_groups[0]["eps"]
+        h[3] = 1.0 - beta1 ** self._step
+        h[4] = math.sqrt(1.0 - beta2 ** self._step)
+        for gi, g in enumerate(self.param_groups):
+            h[8 + 2 * gi] = g["lr"]
+            h[9 + 2 * gi] = g["weight_decay"]
+        self.hyper.copy_(h, non_blocking=True)
+
     # ---- torch.optim.Optimizer API ------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None, clip_coef=None, loss_guard=None):
@@ -170,16 +210,7 @@ class FusedAdamW(torch.optim.Optimizer):
             if p.grad is not None and p.grad.data_ptr() != gv.data_ptr():
                 gv.copy_(p.grad)
                 p.grad = gv
-        self._step += 1
-        beta1, beta2 = self.param_groups[0]["betas"]
-        h = self.hyper_host = self.hyper_hosts[self._step % len(self.hyper_hosts)]
-        h[0], h[1], h[2] = beta1, beta2, self.param_groups[0]["eps"]
-        h[3] = 1.0 - beta1 ** self._step
-        h[4] = math.sqrt(1.0 - beta2 ** self._step)
-        for gi, g in enumerate(self.param_groups):
-            h[8 + 2 * gi] = g["lr"]
-            h[9 + 2 * gi] = g["weight_decay"]
-        self.hyper.copy_(h, non_blocking=True)
+        self._upload_hyper()
         _lib.adamw_step(self.p_arena, garena, self.m_arena, self.v_arena, self.w16, self.segs, self.tiles, self.hyper,
                         clip_coef, loss_guard)
         return loss

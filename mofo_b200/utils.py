@@ -161,9 +161,13 @@ class NativeScalerWithGradNormCount:
         self._scale = 1.0
 
     def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True,
-                 arena=None, loss_guard=False):
+                 arena=None, loss_guard=False, staged_sq_norm=None):
         """``arena``: the model's flat gradient arena when the gradients were produced by the fused step (the engine
-        passes it); otherwise ``loss.backward()`` runs autograd through the model's kernel backward."""
+        passes it); otherwise ``loss.backward()`` runs autograd through the model's kernel backward.
+        ``staged_sq_norm``: the squared-norm accumulator of ``FusedAdamW.begin_staged`` when the update already ran stage
+        by stage behind the gradient exchange (mofo_b200/dp.py); only the norm is finished here."""
+        if staged_sq_norm is not None:
+            return staged_sq_norm.sqrt()[0]
         if arena is None:
             loss.backward(create_graph=create_graph)
         if not update_grad:

@@ -60,6 +60,25 @@ def _worker(rank, world, port, q):
         sync.stage_done(0)
         sync.finish()
         err2 = (arena - expect).abs().max().item()
+        # on_stage hook: called once per stage, in order, with that stage's slice bounds, AFTER the slice was reduced
+        arena.copy_(local * sync.grad_scale)
+        seen = []
+        sync.begin(arena, stage_end, on_stage=lambda k, lo, hi: seen.append((k, lo, hi, (arena[lo:hi] - expect[lo:hi]).abs().max().item())))
+        for k in range(n_stages):
+            sync.stage_done(k)
+        sync.finish()
+        assert [(k, lo, hi) for k, lo, hi, _ in seen] == [(k, ([0] + stage_end)[k], stage_end[k]) for k in range(n_stages)]
+        assert all(e < 1e-6 for *_, e in seen)
+        # parameters: replicas initialised from different seeds adopt rank 0's values (DDP constructor semantics)
+        torch.manual_seed(1000 + rank)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(torch.randn_like(p) * 0.01)
+        sync.sync_parameters(model)
+        flat = torch.cat([p.detach().flatten() for p in model.parameters()])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        assert all(torch.equal(gathered[0], g) for g in gathered) and getattr(model, "_mofo_params_synced", False)
         q.put((rank, err, err2, None))
     except Exception as e:  # pragma: no cover
         import traceback

@@ -90,5 +90,7 @@ def test_two_rank_gradients_equal_single_gpu_on_concatenated_batch():
         g1 = p.grad.detach().cpu()
         for rank in range(world):
             d = ((res[rank][2][n] - g1).norm() / g1.norm().clamp_min(1e-30)).item()
-            assert d < 2e-2, (n, rank, d)          # bf16 dpred / activations are rounded per rank-local batch
+            # fp32 arena reductions; the 1/world factor folded into the bf16 dpred is a power of two (exact), so the only
+            # difference is the fp32 summation order of the weight-gradient reductions (1e-5)
+            assert d < 1e-5, (n, rank, d)
         assert torch.equal(res[0][2][n], res[1][2][n])   # both ranks hold identical reduced gradients

@@ -1,0 +1,221 @@
+"""Parity against the REFERENCE ITSELF, executed on the same GPU (baseline/_ref: unmodified modules staged by
+baseline/setup_ref.py; its own train_one_epoch_BB, optimizer factory and scaler - SURVEY.md appendix C protocol):
+
+  * headline configuration ViT-B, B = 32 (decoder M = 50176 rows, attention grid over 32 clips), at the reference's
+    initialisation AND after 20 optimizer steps of the reference's own AdamW (xavier-initialised outputs are near zero,
+    which under-tests the decoder);
+  * tolerances of SURVEY.md §8c, bf16 path vs reference fp32 (TF32 off): loss rel <= 1e-3, out rel-L2 <= 2e-2, every
+    gradient tensor rel-L2 <= 3e-2 and cosine >= 0.999, global grad-norm rel <= 5e-3 - and, calibrated in the same run,
+    each aggregate <= 2.5x the reference's OWN deviation under bf16 autocast (floors: 1/4 of the absolute tolerance);
+  * 20-step loss trajectory: reference fp32 vs our engine, both driven by the reference's create_optimizer with a
+    table-driven learning rate (engine_for_pretraining.py:230-236).
+The measured numbers are written to gpurun_out/parity_reference.json.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _refrun():
+    from baseline import refrun
+    if not refrun.available():
+        pytest.skip("baseline/_ref is not staged (python baseline/setup_ref.py needs /root/reference)")
+    return refrun
+
+
+def _ours_from(ref_model, name):
+    from mofo_b200 import modeling_pretrain as mp
+    m = mp.create_model(name, pretrained=False, drop_path_rate=0.0, drop_block_rate=None, decoder_depth=4)
+    sd = ref_model.state_dict()
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)                       # protocol step 3: never rely on matching init RNG
+    return m.cuda().train()
+
+
+def _ours_step(model, batch):
+    vid, _, mask = batch
+    model.use_cuda_graph = False
+    loss = model.pretrain_step(vid, mask.flatten(1).to(torch.bool))
+    torch.cuda.synchronize()
+    B = vid.shape[0]
+    nm = int(mask[0].sum().item())
+    pred = model._runner.buf("pred", (B * nm, 1536), torch.bfloat16).float().view(B, nm, 1536).clone()
+    return {"loss": loss.item(), "out": pred, "grads": {n: p.grad.detach().clone() for n, p in model.named_parameters()}}
+
+
+def _deviation(a, ref):
+    """a, ref: dicts from single_step / _ours_step.  Aggregates of a's deviation from ref."""
+    rels, coss, worst = [], [], ("", 0.0)
+    gn_a = gn_r = 0.0
+    for n, r in ref["grads"].items():
+        g = a["grads"][n].double(); r = r.double()
+        rel = ((g - r).norm() / r.norm().clamp_min(1e-30)).item()
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item()
+        rels.append(rel); coss.append(cos)
+        gn_a += g.pow(2).sum().item(); gn_r += r.pow(2).sum().item()
+        if rel > worst[1]:
+            worst = (n, rel)
+    out_a, out_r = a["out"].double(), ref["out"].double()
+    rels_s = sorted(rels)
+    return {"loss_rel": abs(a["loss"] - ref["loss"]) / abs(ref["loss"]),
+            "out_rel": ((out_a - out_r).norm() / out_r.norm()).item(),
+            "grad_rel_median": rels_s[len(rels_s) // 2], "grad_rel_p95": rels_s[int(0.95 * len(rels_s))],
+            "grad_rel_max": rels_s[-1], "grad_rel_max_name": worst[0], "grad_cos_min": min(coss),
+            "gnorm_rel": abs(gn_a ** 0.5 - gn_r ** 0.5) / gn_r ** 0.5}
+
+
+ABS = {"loss_rel": 1e-3, "out_rel": 2e-2, "grad_rel_max": 3e-2, "gnorm_rel": 5e-3}
+
+
+def _check(ours, ref_bf16, tag, report):
+    report[tag] = {"ours_vs_ref_fp32": ours, "ref_bf16_vs_ref_fp32": ref_bf16}
+    print(tag, json.dumps(report[tag]))
+    for k, tol in ABS.items():
+        assert ours[k] <= tol, (tag, k, ours[k], tol)
+    assert ours["grad_cos_min"] >= 0.999, (tag, ours["grad_cos_min"])
+    for k in ("loss_rel", "out_rel", "grad_rel_median", "grad_rel_p95", "grad_rel_max", "gnorm_rel"):
+        floor = 0.25 * ABS.get(k, ABS["grad_rel_max"])
+        assert ours[k] <= max(2.5 * ref_bf16[k], floor), (tag, k, ours[k], ref_bf16[k])
+
+
+@pytest.mark.parametrize("name,B", [("pretrain_videomae_base_patch16_224", 32)])
+def test_full_step_vs_reference_at_init_and_after_20_steps(name, B):
+    refrun = _refrun()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    ref_model = refrun.create_model(name).to(dev)
+    batches = refrun.synthetic_batches(B, 2, seed=77, device=dev)
+    report = {"config": f"{name}, B={B}, reference fp32 with TF32 off; tolerances SURVEY 8c"}
+
+    def one_round(tag):
+        r32 = refrun.single_step(ref_model, batches[0], dev, "fp32")
+        r16 = refrun.single_step(ref_model, batches[0], dev, "bf16")
+        ours = _ours_step(_ours_from(ref_model, name), batches[0])
+        _check(_deviation(ours, r32), _deviation(r16, r32), tag, report)
+
+    one_round("at_init")
+
+    # 20 steps of the reference's own optimizer, table-driven lr (warm-up 1e-4 -> 1e-3), reference fp32 vs our engine
+    steps = 20
+    lr_values = np.linspace(1e-4, 1e-3, steps)
+    ours_model = _ours_from(ref_model, name)
+    log_ref = refrun.LossLog()
+    opt_ref = refrun.create_optimizer(ref_model, lr=1e-3)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        refrun.train_epoch(ref_model, opt_ref, refrun.make_scaler(dev), batches, steps, dev, "fp32", lr_values, log_ref)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    from mofo_b200 import engine_for_pretraining as eng
+    from mofo_b200 import utils as U
+    log_ours = refrun.LossLog()
+    opt_ours = refrun.create_optimizer(ours_model, lr=1e-3)          # the reference's factory on OUR model (protocol step 6)
+
+    class Loader(list):
+        quiet = True
+    eng.train_one_epoch_BB(ours_model, Loader([batches[i % 2] for i in range(steps)]), opt_ours, dev, 0,
+                           U.NativeScalerWithGradNormCount(), max_norm=0, patch_size=16, normlize_target=True,
+                           log_writer=log_ours, start_steps=0, lr_schedule_values=lr_values)
+    assert len(log_ref.losses) == len(log_ours.losses) == steps
+    traj = [abs(a - b) / abs(b) for a, b in zip(log_ours.losses, log_ref.losses)]
+    report["trajectory"] = {"ref_fp32": log_ref.losses, "ours": log_ours.losses, "max_rel": max(traj)}
+    print("trajectory", json.dumps(report["trajectory"]))
+    assert log_ref.losses[-1] < log_ref.losses[0], "the 20 reference steps must actually train"
+    assert max(traj) <= 1e-2, traj
+    del ours_model, opt_ours
+
+    one_round("after_20_reference_steps")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_reference.json"), "w") as f:
+        json.dump(report, f, indent=1)
+
+
+def test_mask_generator_call_matches_reference_call_and_rng_state():
+    """The public __call__ of both generators (the a-1 / a-2 API): np.random.seed(s) -> call -> identical mask AND
+    identical numpy global RNG state as after the reference's call (masking_generator.py:62,75 / :22)."""
+    refrun = _refrun()
+    ref = refrun.load()
+    from mofo_b200 import masking_generator as mg
+    rng = np.random.default_rng(5)
+    boxes = [np.array([60., 40., 160., 180.]), np.array([0., 0., 1., 1.]), np.array([0., 0., 224., 224.]),
+             np.array([100.5, 20.25, 130.75, 60.5])] + [refrun.synthetic_boxes(1, rng)[0] for _ in range(12)]
+    g_ref = ref.masking_generator.TubeMaskingGenerator_BB((8, 14, 14), 0.9, 0.75)
+    g_our = mg.TubeMaskingGenerator_BB((8, 14, 14), 0.9, 0.75)
+    assert repr(g_ref) == repr(g_our)
+    saved = np.random.get_state()
+    try:
+        for i, bb in enumerate(boxes):
+            seed = 10 if i < 8 else 1000 + i
+            bb16 = np.repeat(bb[None], 16, 0)
+            np.random.seed(seed); m_ref = g_ref(bb16); st_ref = np.random.get_state()
+            np.random.seed(seed); m_our = g_our(bb16); st_our = np.random.get_state()
+            assert m_our.dtype == m_ref.dtype == np.float64 and m_our.shape == m_ref.shape == (1568,)
+            assert np.array_equal(m_ref, m_our), (i, bb)
+            assert st_ref[0] == st_our[0] and np.array_equal(st_ref[1], st_our[1]) and st_ref[2:] == st_our[2:], (i, bb)
+            # two calls in a row continue the same stream
+            a = g_ref(bb16); np.random.set_state(st_our); b = g_our(bb16)
+            assert np.array_equal(a, b)
+        p_ref = ref.masking_generator.TubeMaskingGenerator((8, 14, 14), 0.9)
+        p_our = mg.TubeMaskingGenerator((8, 14, 14), 0.9)
+        for seed in (10, 11, 12345):
+            np.random.seed(seed); m_ref = p_ref(); st_ref = np.random.get_state()
+            np.random.seed(seed); m_our = p_our(); st_our = np.random.get_state()
+            assert np.array_equal(m_ref, m_our)
+            assert st_ref[0] == st_our[0] and np.array_equal(st_ref[1], st_our[1]) and st_ref[2:] == st_our[2:]
+    finally:
+        np.random.set_state(saved)
+
+
+def test_dropin_chain_takes_the_fused_path():
+    """The import chain of run_mae_pretraining_BB.py (:10-16) with dropin/ ahead of the reference checkout: the scaler and
+    the optimizer factory it imports resolve to the B200 versions, so train_one_epoch_BB runs fused."""
+    import importlib
+    import sys
+    refrun = _refrun()
+    refrun.load()                                  # installs the timm shim the reference's utils.py needs
+    names = ("masking_generator", "modeling_pretrain", "engine_for_pretraining", "utils", "optim_factory", "_refmod")
+    saved = {n: sys.modules.pop(n, None) for n in names}
+    old_env = os.environ.get("MOFO_REFERENCE_DIR")
+    os.environ["MOFO_REFERENCE_DIR"] = refrun.REF_DIR
+    sys.path.insert(0, os.path.join(ROOT, "dropin"))
+    try:
+        import types
+        utils = importlib.import_module("utils")
+        optim_factory = importlib.import_module("optim_factory")
+        engine = importlib.import_module("engine_for_pretraining")
+        importlib.import_module("modeling_pretrain")
+        from mofo_b200.modeling_pretrain import create_model
+        assert hasattr(utils, "init_distributed_mode") and hasattr(utils, "auto_load_model")     # re-exported reference helpers
+        model = create_model("pretrain_mae_small_patch16_224", pretrained=False, drop_path_rate=0.0, drop_block_rate=None,
+                             decoder_depth=4).cuda()
+        args = types.SimpleNamespace(opt="adamw", opt_eps=1e-8, opt_betas=(0.9, 0.95), weight_decay=0.05, lr=1e-4, momentum=0.9)
+        optimizer = optim_factory.create_optimizer(args, model)
+        loss_scaler = utils.NativeScalerWithGradNormCount()
+        assert getattr(optimizer, "fused_mofo", False)
+        batches = refrun.synthetic_batches(2, 1, seed=3, device=torch.device("cuda", 0))
+
+        class Loader(list):
+            quiet = True
+        stats = engine.train_one_epoch_BB(model, Loader(batches * 3), optimizer, torch.device("cuda", 0), 0, loss_scaler,
+                                          max_norm=None, patch_size=16, normlize_target=True, start_steps=0)
+        assert engine.train_one_epoch_BB.last_path == "fused"
+        assert np.isfinite(stats["loss"]) and stats["loss_scale"] == 1.0
+    finally:
+        sys.path.remove(os.path.join(ROOT, "dropin"))
+        if old_env is None:
+            os.environ.pop("MOFO_REFERENCE_DIR", None)
+        else:
+            os.environ["MOFO_REFERENCE_DIR"] = old_env
+        for n in names:
+            sys.modules.pop(n, None)
+            if saved[n] is not None:
+                sys.modules[n] = saved[n]
+        sys.modules.pop("_mofo_reference_utils", None); sys.modules.pop("_mofo_reference_optim_factory", None)
