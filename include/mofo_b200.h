@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MOFO_B200_VERSION 100
+#define MOFO_B200_VERSION 200
 
 typedef uint16_t mofo_bf16;
 
@@ -119,11 +119,17 @@ int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, i
  * Replaces Attention.forward lines modeling_finetune.py:85-95 (split heads, q*scale, softmax(q k^T), attn @ v,
  * merge heads) and their backward.  qkv: bf16 [B*S, 3*H*64] = output of the QKV linear (q | k | v, each H*64 wide);
  * out: bf16 [B*S, H*64]; lse: f32 [B,H,S] (log2-domain log-sum-exp kept for backward).
- * Backward: dqkv bf16 [B*S, 3*H*64]; delta: f32 workspace [B,H,S].
+ * out_lo (may be NULL): bf16 [B*S, H*64] = out_exact - out, the second bf16 word of the attention output.  Backward uses
+ *   it only for delta_i = dO_i . O_i, the softmax-backward row term (softmax's Jacobian needs sum_j dS_ij = 0; an error
+ *   e_i in delta leaks e_i * (probability-weighted mean key) into dQ, which the q_bias gradient - a batch-wide sum of
+ *   cancelling terms - accumulates).  Sequences with S <= 192 run single-pass kernels that hold the whole score row in
+ *   tensor memory and form delta_i = sum_j P_ij dP_ij directly; they neither write nor read out_lo.
+ * Backward: dqkv bf16 [B*S, 3*H*64]; delta: f32 workspace [B,H,S] (untouched when S <= 192).
  */
-int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_bf16* out, float* lse, void* stream);
-int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* dout, const float* lse, int B, int S,
-                  int H, float scale, mofo_bf16* dqkv, float* delta, void* stream);
+int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_bf16* out, mofo_bf16* out_lo, float* lse,
+                  void* stream);
+int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* out_lo, const mofo_bf16* dout, const float* lse,
+                  int B, int S, int H, float scale, mofo_bf16* dqkv, float* delta, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (5) LayerNorm (eps 1e-6; nn.LayerNorm at modeling_finetune.py:200,206, modeling_pretrain.py:51,123).

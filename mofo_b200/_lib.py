@@ -28,8 +28,8 @@ SIGNATURES = {
     "mofo_gather_tubes": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_gemm_tn": ([_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P, _I, _P], C.c_int),
     "mofo_gemm_wgrad": ([_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P], C.c_int),
-    "mofo_attn_fwd": ([_P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
-    "mofo_attn_bwd": ([_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
+    "mofo_attn_fwd": ([_P, _I, _I, _I, _F, _P, _P, _P, _P], C.c_int),
+    "mofo_attn_bwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
     "mofo_layernorm_fwd": ([_P, _P, _P, _I, _I, _F, _I, _I, _I, _P, _P, _P, _P], C.c_int),
     "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
     "mofo_decoder_assemble_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
@@ -200,14 +200,20 @@ def gemm_wgrad(dY, X, dW, M=None, dbias=None, skip=(0, 0)):
     return dW
 
 
-def attn_fwd(qkv, B, S, H, scale, out, lse):
-    _check(load().mofo_attn_fwd(_ptr(qkv), B, S, H, float(scale), _ptr(out), _ptr(lse), _stream()), "mofo_attn_fwd")
+ATTN_SINGLE_PASS_MAX_S = 192      # sequences up to this length run the single-pass kernels (no out_lo, no delta pass)
+
+
+def attn_fwd(qkv, B, S, H, scale, out, lse, out_lo=None):
+    _check(load().mofo_attn_fwd(_ptr(qkv), B, S, H, float(scale), _ptr(out), _ptr(out_lo), _ptr(lse), _stream()), "mofo_attn_fwd")
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, B, S, H, scale, dqkv, delta):
-    _check(load().mofo_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), B, S, H, float(scale), _ptr(dqkv),
+def attn_bwd(qkv, out, dout, lse, B, S, H, scale, dqkv, delta, out_lo=None):
+    global launch_count
+    _check(load().mofo_attn_bwd(_ptr(qkv), _ptr(out), _ptr(out_lo), _ptr(dout), _ptr(lse), B, S, H, float(scale), _ptr(dqkv),
                                 _ptr(delta), _stream()), "mofo_attn_bwd")
+    if S <= ATTN_SINGLE_PASS_MAX_S and os.environ.get("MOFO_ATTN_SMALL", "1") != "0":
+        launch_count -= 2                      # one kernel instead of delta + dQ + dK/dV
     return dqkv
 
 

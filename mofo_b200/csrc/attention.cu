@@ -14,107 +14,13 @@
 //                            own fp32 accumulator columns; tcgen05.mma with A in TMEM), so it never touches shared memory;
 //                            B = the same TMA tile re-read as an MN-major operand (rows = reduction index).
 // Everything is kept in the log2 domain: t = s * scale * log2(e), p = exp2(t - lse2).
+#include <stdlib.h>
+
 #include "../../include/mofo_b200.h"
-#include "common.cuh"
+#include "attn_helpers.cuh"
 
 namespace mofo {
 
-constexpr int AT = 128;                       // rows per CTA tile (q rows in fwd/dq, kv rows in dkv)
-constexpr int BT = 64;                        // inner (streamed) tile: kv rows in fwd/dq, q rows in dkv
-constexpr int TILE_BYTES = AT * 64 * 2;       // 16 KB: [128 x 64] bf16
-constexpr int HTILE_BYTES = BT * 64 * 2;      //  8 KB: [ 64 x 64] bf16
-constexpr int ATT_THREADS = 256;              // 2 threads per tile row: each owns 32 of the 64 inner columns
-
-__device__ __forceinline__ void check_align(uint32_t base) {
-  if (base & 1023u) {
-    if (threadIdx.x == 0) printf("mofo: dynamic shared memory base not 1024-B aligned (0x%x)\n", base);
-    __trap();
-  }
-}
-
-__device__ __forceinline__ float fmax3(float a, float b, float c) {   // single FMNMX3 on sm_100
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-
-// D[128 x 64] = A[128 x 64] · B[64 x 64]^T, both K-major SW128 tiles straight from TMA (4 K-steps of 16)
-__device__ __forceinline__ void mma_ab_t(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile) {
-  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
-  const uint64_t a0 = umma_desc_kmajor(a_tile), b0 = umma_desc_kmajor(b_tile);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k != 0);
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// D[128 x 64] (+)= P[128 x 64 bf16, in TMEM: lane = row, column k/2 holds elements (k, k+1)] · T[64 x 64] (MN-major smem)
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// The bf16 operand is written by the threads over their OWN fp32 accumulator columns: the thread pair of a row owns
-// fp32 columns [0,32) and [32,64) of a 64-column region and stores its 32 bf16 values (16 packed columns) at region
-// columns [0,16) resp. [32,48).  K-steps of 16 elements therefore start at columns {0, 8, 32, 40}.
-__device__ __forceinline__ void mma_ptmem_t(uint32_t d_tmem, uint32_t p_tmem, uint32_t t_tile, bool accumulate) {
-  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
-  const uint64_t b0 = umma_desc_mnmajor(t_tile, 8192);
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    umma_bf16_ts(d_tmem, p_tmem + (k >> 1) * 32 + (k & 1) * 8, b0 + 128 * k, idesc, (accumulate || k != 0) ? 1u : 0u);
-}
-__device__ __forceinline__ void tmem_ld16a(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st8_async(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st16_async(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// same as tmem_store_bf16_row but WITHOUT the trailing tcgen05.wait::st: the caller waits once before handing over
-__device__ __forceinline__ void tmem_store_bf16_row_async(uint32_t taddr, const float (&v)[32]) {
-  uint32_t r[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) r[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_store_bf16_row(uint32_t taddr, const float (&v)[32]) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
-  tmem_st16(taddr, pk);
-}
 #ifndef MOFO_ATTN_PAD
 #define MOFO_ATTN_PAD 0          // tuning aid: extra dynamic smem per CTA to force lower occupancy in variant builds
 #endif
@@ -141,7 +47,8 @@ constexpr int FWD_SMEM = TILE_BYTES + 4 * HTILE_BYTES + 512 + 64;   // Q, K0,V0,
 
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int S, int H,
-                float c /*scale*log2e*/, __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+                float c /*scale*log2e*/, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo,
+                float* __restrict__ lse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   check_align(base);
@@ -309,15 +216,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int q = q0 + row;
   if (q < S) {
     const float inv = 1.0f / l_tot;
-    __nv_bfloat16* dst = out + (static_cast<size_t>(row0 + q) * H + h) * 64 + half * 32;
+    const size_t off = (static_cast<size_t>(row0 + q) * H + h) * 64 + half * 32;
+    __nv_bfloat16* dst = out + off;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * inv);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       uint4 v;
-      v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-      v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-      v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-      v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+      v.x = pack_bf16(__uint_as_float(o[g * 8 + 0]), __uint_as_float(o[g * 8 + 1]));
+      v.y = pack_bf16(__uint_as_float(o[g * 8 + 2]), __uint_as_float(o[g * 8 + 3]));
+      v.z = pack_bf16(__uint_as_float(o[g * 8 + 4]), __uint_as_float(o[g * 8 + 5]));
+      v.w = pack_bf16(__uint_as_float(o[g * 8 + 6]), __uint_as_float(o[g * 8 + 7]));
       reinterpret_cast<uint4*>(dst)[g] = v;
+      if (out_lo) {
+        // second bf16 word of O (o - bf16(o)): backward's delta = dO . O is then accurate to 2^-17 instead of 2^-9; an
+        // error e_i in delta leaks e_i * (P-weighted mean key) into dQ (see attention_small.cu), which is what made
+        // the decoder's q_bias gradients (batch-wide sums of cancelling terms) 20-70x noisier than the reference's
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) - bf16_lo(v.x), __uint_as_float(o[g * 8 + 1]) - bf16_hi(v.x));
+        w.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) - bf16_lo(v.y), __uint_as_float(o[g * 8 + 3]) - bf16_hi(v.y));
+        w.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) - bf16_lo(v.z), __uint_as_float(o[g * 8 + 5]) - bf16_hi(v.z));
+        w.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) - bf16_lo(v.w), __uint_as_float(o[g * 8 + 7]) - bf16_hi(v.w));
+        reinterpret_cast<uint4*>(out_lo + off)[g] = w;
+      }
     }
     if (half == 0) lse[(static_cast<size_t>(b) * H + h) * S + q] = m_ref + log2f(l_tot);
   }
@@ -332,6 +253,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // 8 lanes share one (row, head): lane j reads the j-th 16-byte chunk of the 128-byte O and dO rows, so every warp
 // load covers 4 full rows (fully used sectors); 4 rows per thread in flight; 3 shuffles finish the dot product.
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ out,
+                                                         const __nv_bfloat16* __restrict__ out_lo,
                                                          const __nv_bfloat16* __restrict__ dout, int rows, int S, int H,
                                                          float* __restrict__ delta) {
   pdl_wait();
@@ -341,22 +263,25 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
   const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;      // first pair of this 8-lane group
   const int stride = (gridDim.x * blockDim.x) >> 3;
   for (int base = g0; base < total; base += 4 * stride) {
-    uint4 a[4], bq[4];
+    uint4 a[4], bq[4], al[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = base + u * stride;
+      al[u] = make_uint4(0, 0, 0, 0);
       if (i < total) {
         a[u] = __ldg(reinterpret_cast<const uint4*>(out + static_cast<size_t>(i) * 64) + j);
         bq[u] = __ldg(reinterpret_cast<const uint4*>(dout + static_cast<size_t>(i) * 64) + j);
+        if (out_lo) al[u] = __ldg(reinterpret_cast<const uint4*>(out_lo + static_cast<size_t>(i) * 64) + j);
       } else {
         a[u] = make_uint4(0, 0, 0, 0); bq[u] = make_uint4(0, 0, 0, 0);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      float s = bf16_lo(a[u].x) * bf16_lo(bq[u].x) + bf16_hi(a[u].x) * bf16_hi(bq[u].x) + bf16_lo(a[u].y) * bf16_lo(bq[u].y) +
-                bf16_hi(a[u].y) * bf16_hi(bq[u].y) + bf16_lo(a[u].z) * bf16_lo(bq[u].z) + bf16_hi(a[u].z) * bf16_hi(bq[u].z) +
-                bf16_lo(a[u].w) * bf16_lo(bq[u].w) + bf16_hi(a[u].w) * bf16_hi(bq[u].w);
+      float s = (bf16_lo(a[u].x) + bf16_lo(al[u].x)) * bf16_lo(bq[u].x) + (bf16_hi(a[u].x) + bf16_hi(al[u].x)) * bf16_hi(bq[u].x) +
+                (bf16_lo(a[u].y) + bf16_lo(al[u].y)) * bf16_lo(bq[u].y) + (bf16_hi(a[u].y) + bf16_hi(al[u].y)) * bf16_hi(bq[u].y) +
+                (bf16_lo(a[u].z) + bf16_lo(al[u].z)) * bf16_lo(bq[u].z) + (bf16_hi(a[u].z) + bf16_hi(al[u].z)) * bf16_hi(bq[u].z) +
+                (bf16_lo(a[u].w) + bf16_lo(al[u].w)) * bf16_lo(bq[u].w) + (bf16_hi(a[u].w) + bf16_hi(al[u].w)) * bf16_hi(bq[u].w);
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -710,11 +635,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_cons
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-int get_tmap(CUtensorMap* out, const void* p, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);  // gemm.cu
-
 }  // namespace mofo
 
 using namespace mofo;
+
+// MOFO_ATTN_SMALL=0 routes short sequences through the streaming kernels too (A/B measurements, tests of both paths)
+static bool use_small_attention() {
+  const char* e = getenv("MOFO_ATTN_SMALL");
+  return !(e && e[0] == '0');
+}
 
 extern "C" {
 
@@ -724,9 +653,12 @@ int mofo_debug_read_trace(long long* host, int n) {   // tuning aid, only in -DM
 }
 #endif
 
-int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_bf16* out, float* lse, void* stream) {
+int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_bf16* out, mofo_bf16* out_lo, float* lse,
+                  void* stream) {
   MOFO_CHECK_ARG(qkv && out && lse, "attn_fwd: null pointer");
   MOFO_CHECK_ARG(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
+  if (S <= ATTN_SMALL_MAX_S && use_small_attention())            // whole score row in TMEM: single-pass kernels
+    return attn_small_fwd(qkv, B, S, H, scale, out, lse, static_cast<cudaStream_t>(stream));
   CUtensorMap tq, tkv;
   int rc = get_tmap(&tq, qkv, static_cast<uint64_t>(B) * S, 3ull * H * 64, 3ull * H * 64, AT);
   if (rc) return rc;
@@ -739,15 +671,17 @@ int mofo_attn_fwd(const mofo_bf16* qkv, int B, int S, int H, float scale, mofo_b
   }
   dim3 grid((S + AT - 1) / AT, H, B);
   MOFO_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(ATT_THREADS), FWD_SMEM + MOFO_ATTN_PAD, static_cast<cudaStream_t>(stream), tq, tkv, S, H,
-                       scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(out), lse));
+                       scale * 1.4426950408889634f, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<__nv_bfloat16*>(out_lo), lse));
   return MOFO_OK;
 }
 
-int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* dout, const float* lse, int B, int S,
-                  int H, float scale, mofo_bf16* dqkv, float* delta, void* stream) {
+int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* out_lo, const mofo_bf16* dout, const float* lse,
+                  int B, int S, int H, float scale, mofo_bf16* dqkv, float* delta, void* stream) {
   MOFO_CHECK_ARG(qkv && out && dout && lse && dqkv && delta, "attn_bwd: null pointer");
   MOFO_CHECK_ARG(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attn_bwd: bad shape B=%d S=%d H=%d", B, S, H);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (S <= ATTN_SMALL_MAX_S && use_small_attention())
+    return attn_small_bwd(qkv, out, dout, lse, B, S, H, scale, dqkv, s);
   const uint64_t rows = static_cast<uint64_t>(B) * S;
   CUtensorMap tq128, tq64, td128, td64;
   int rc = get_tmap(&tq128, qkv, rows, 3ull * H * 64, 3ull * H * 64, AT);
@@ -771,8 +705,8 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* d
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     MOFO_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s,
-                         reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout),
-                         static_cast<int>(rows), S, H, delta));
+                         reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(out_lo),
+                         reinterpret_cast<const __nv_bfloat16*>(dout), static_cast<int>(rows), S, H, delta));
   }
   dim3 grid((S + AT - 1) / AT, H, B);
   const float c = scale * 1.4426950408889634f;

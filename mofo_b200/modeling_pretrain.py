@@ -360,7 +360,9 @@ class _Runner:
         qkv = self.buf(pre + ".qkv", (M, 3 * D), bf)
         _lib.gemm_tn(h1, wc[pre + ".qkv"][0], _lib.EPI_BIAS_BF16, qkv, bias=self.buf(pre + ".qkvbias", (3 * D,), f32))
         o = self.buf(pre + ".o", (M, D), bf); lse = self.buf(pre + ".lse", (B, H, S), f32)
-        _lib.attn_fwd(qkv, B, S, H, blk.attn.scale, o, lse)
+        # long sequences (streaming kernels): second bf16 word of O, read back only by backward's delta = dO . O
+        olo = self.buf(pre + ".olo", (M, D), bf) if S > _lib.ATTN_SINGLE_PASS_MAX_S else None
+        _lib.attn_fwd(qkv, B, S, H, blk.attn.scale, o, lse, out_lo=olo)
         xm = self.buf(pre + ".xm", (M, D), f32)
         _lib.gemm_tn(o, wc[pre + ".proj"][0], _lib.EPI_BIAS_RESID_F32, xm, bias=blk.attn.proj.bias, resid=x)
         h2 = self.buf(pre + ".h2", (M, D), bf); mean2 = self.buf(pre + ".mean2", (M,), f32); rstd2 = self.buf(pre + ".rstd2", (M,), f32)
@@ -444,7 +446,8 @@ class _Runner:
         # attention
         dqkv = self.buf("bwd.dqkv", (M, 3 * D), bf); delta = self.buf("bwd.delta", (B, H, S), f32)
         self._before_write(dqkv)                                 # previous block's qkv wgrad
-        _lib.attn_bwd(qkv, o, do, lse, B, S, H, blk.attn.scale, dqkv, delta)
+        olo = self.buf(pre + ".olo", (M, D), bf) if S > _lib.ATTN_SINGLE_PASS_MAX_S else None
+        _lib.attn_bwd(qkv, o, do, lse, B, S, H, blk.attn.scale, dqkv, delta, out_lo=olo)
         # qkv
         # q_bias / v_bias gradients: column sums of dqkv[:, :D] and dqkv[:, 2D:], written through a [3D] window whose
         # first D floats are q_bias.grad and whose last D floats are v_bias.grad (see _make_arena: a D-float gap sits

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 def test_version_and_error_string(lib):
     cdll = lib.load()
-    assert cdll.mofo_version() == 100
+    assert cdll.mofo_version() == 200          # MOFO_B200_VERSION (include/mofo_b200.h)
     assert isinstance(cdll.mofo_last_error(), bytes)
 
 

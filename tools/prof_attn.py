@@ -34,3 +34,14 @@ if os.environ.get("TRACE"):      # -DMOFO_ATTN_TRACE build: per-iteration phase 
         print(f"thread {'0' if th == 0 else '255'} phase deltas (clk, mean over iterations):",
               {names[k] if k < len(names) else k: round(float(d[:, k].mean())) for k in range(d.shape[1])})
     print("per-iteration slot 0 (thread 0):", (t[1:, 0, 0] - t[:-1, 0, 0]).tolist())
+
+if os.environ.get("STRACE"):     # -DMOFO_ATTN_TRACE=4 build: phase timestamps of the single-pass forward kernel
+    import ctypes, numpy as np
+    buf = (ctypes.c_longlong * 64)()
+    assert _lib.load().mofo_debug_read_strace(buf, 64) == 0
+    t = np.array(buf[:], dtype=np.int64).reshape(32, 2)
+    names = ["start", "prologue done", "loads landed (t0 only)", "S0 ready", "-", "softmax0 done", "sync0", "S1+O0 ready", "epilogue0 done",
+             "softmax1 done", "sync1", "O1 ready", "epilogue1 done", "dealloc"]
+    for th in (0, 1):
+        base = t[0, th]
+        print(f"thread {'0' if th == 0 else '255'}:", {names[k]: int(t[k, th] - base) for k in range(14) if t[k, th] > 0})
