@@ -32,6 +32,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE configs[1]: 32)")
     ap.add_argument("--model", default="pretrain_videomae_base_patch16_224")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"],
+                    help="finetune = BASELINE configs[4]: vit_base_patch16_224 classifier fwd+bwd on all 1568 tokens, batch 8 (not the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall budget of the oracle-port fallback of the reference arm")
@@ -493,9 +495,81 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_finetune(args):
+    """BASELINE configs[4] (dense-attention stress): classifier forward + cross-entropy + backward on all 1568
+    tokens, B = 8 per GPU (FINETUNE.md:25), through the public nn.Module API; CUDA events, inputs resident in HBM (two
+    rotating batches + a 256 MiB L2 flush write between steps).  The reference's own module on the same GPU is timed beside it."""
+    import torch
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    from mofo_b200 import _lib
+    from mofo_b200 import modeling_finetune as mf
+    _lib.load()
+    B = 8 if args.batch == 32 else args.batch
+    name = "vit_base_patch16_224" if args.model.startswith("pretrain") else args.model
+    kw = dict(num_classes=174, all_frames=16, tubelet_size=2, drop_rate=0.0, drop_path_rate=0.0, attn_drop_rate=0.0,
+              use_mean_pooling=True, init_scale=0.001)
+    torch.manual_seed(0)
+    model = mf.create_model(name, pretrained=False, drop_block_rate=None, **kw).to(dev).train()
+    g = torch.Generator(device=dev).manual_seed(1234)
+    xs = [torch.randn(B, 3, 16, 224, 224, generator=g, device=dev) for _ in range(2)]
+    ys = [torch.randint(0, 174, (B,), device=dev, generator=g) for _ in range(2)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(m, i, amp=None):
+        flush.zero_()
+        for p in m.parameters():
+            p.grad = None
+        if amp is None:
+            loss = torch.nn.functional.cross_entropy(m(xs[i % 2]), ys[i % 2])
+        else:
+            with torch.autocast("cuda", dtype=amp):
+                loss = torch.nn.functional.cross_entropy(m(xs[i % 2]).float(), ys[i % 2])
+        loss.backward()
+        return loss
+
+    def timed(m, amp=None):
+        for i in range(args.warmup):
+            step(m, i, amp)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count
+        e0.record()
+        for i in range(args.steps):
+            loss = step(m, i, amp)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, loss.item(), _lib.launch_count - n0
+    ms, loss, launches = timed(model)
+    gflop = 1078.0                                   # SURVEY 8d: ViT-B finetune fwd+bwd per clip
+    line = {"metric": "MOFO ViT-B finetune clips/s (16x224^2, all 1568 tokens, fwd+bwd, no optimizer)", "value": B / (ms * 1e-3), "unit": "clips/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: {name} classifier fwd + CE + bwd on all 1568 tokens, batch {B}, dense-attention stress", "global_batch": B, "parallelism": "dp1"},
+            "gpu_launches": launches, "final_loss": loss,
+            "step_mfu": {"algorithmic_tflops_per_gpu": B / (ms * 1e-3) * gflop / 1e3, "gflop_per_clip": gflop,
+                         "frac_of_nominal_2250": B / (ms * 1e-3) * gflop / 1e3 / 2250.0},
+            "notes": {"l2": "256 MiB flush write between steps", "includes": "L2 flush fill (0.04 ms) inside the timed region for both arms"}}
+    del model
+    torch.cuda.empty_cache()
+    from baseline import refrun
+    if refrun.available() and not args.no_gpu_reference:
+        ref = refrun.load()
+        torch.manual_seed(0)
+        rm = getattr(ref.modeling_finetune, name)(pretrained=False, **kw).to(dev).train()
+        line["gpu_reference"] = {}
+        for tag, amp in (("fp16_autocast_as_authored", torch.float16), ("bf16_autocast", torch.bfloat16)):
+            rms, rloss, _ = timed(rm, amp)
+            line["gpu_reference"][tag] = {"ms_per_step": rms, "value": B / (rms * 1e-3), "unit": "clips/s", "loss": rloss}
+        line["gpu_reference"]["how"] = "unmodified reference modeling_finetune." + name + " (baseline/_ref), eager PyTorch, same inputs, same timing loop (no GradScaler: forward + CE + backward only)"
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "finetune" and a.impl != "reference":
+        run_finetune(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

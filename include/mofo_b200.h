@@ -160,6 +160,15 @@ int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk,
                               mofo_bf16* dvis, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * (6b) Token mean pooling of the finetuning classifier: VisionTransformer.forward_features ends with
+ * fc_norm(x.mean(1)) (modeling_finetune.py:398-401).  fwd: pooled f32 [B, D] = mean over the N tokens of x f32 [B, N, D]
+ * (pooled is zeroed by the call, 16-byte aligned).  bwd: dx[b, n, :] = dpooled[b, :] / N for every token, written as
+ * f32 and / or bf16 [B*N, D] (either may be NULL) - the gradient entering the last transformer block.
+ */
+int mofo_token_mean_fwd(const float* x, int B, int N, int D, float* pooled, void* stream);
+int mofo_token_mean_bwd(const float* dpooled, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * (7) Target + loss (engine_for_pretraining.py:258-304): un-normalise with ImageNet mean/std (:260-265), patchify
  * 'b c (t p0) (h p1) (w p2) -> b (t h w) (p0 p1 p2) c' (:268), per-(tube,channel) mean / unbiased std + 1e-6
  * (:269-270), flatten to feature f = p*3 + c (:276), gather the masked tubes (:285-286), MSE mean (:301-304).

@@ -34,6 +34,8 @@ SIGNATURES = {
     "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
     "mofo_decoder_assemble_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_decoder_assemble_bwd": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
+    "mofo_token_mean_fwd": ([_P, _I, _I, _I, _P, _P], C.c_int),
+    "mofo_token_mean_bwd": ([_P, _I, _I, _I, _P, _P, _P], C.c_int),
     "mofo_target_mse": ([_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P], C.c_int),
     "mofo_cast_weight": ([_P, _I, _I, _P, _P, _P], C.c_int),
     "mofo_pack_qkv_bias": ([_P, _P, _I, _P, _P], C.c_int),
@@ -69,7 +71,7 @@ def load() -> C.CDLL:
 
 
 # kernels launched per successful C-ABI call (bench.py reports the count it observed as "gpu_launches")
-_LAUNCHES = {"mofo_target_mse": 2, "mofo_attn_bwd": 3}
+_LAUNCHES = {"mofo_target_mse": 2, "mofo_attn_bwd": 3}      # (mofo_token_mean_fwd also issues a memset node, not a kernel)
 launch_count = 0
 
 
@@ -242,6 +244,16 @@ def decoder_assemble_fwd(mask_token, pos, msk_idx, B, n_vis, n_msk, Dd, x_full):
 def decoder_assemble_bwd(dx_full, B, n_vis, n_msk, Dd, dmask_token, dvis):
     _check(load().mofo_decoder_assemble_bwd(_ptr(dx_full), B, n_vis, n_msk, Dd, _ptr(dmask_token), _ptr(dvis),
                                             _stream()), "mofo_decoder_assemble_bwd")
+
+
+def token_mean_fwd(x, B, N, D, pooled):
+    """pooled f32 [B, D] = mean over tokens of x f32 [B*N, D]."""
+    _check(load().mofo_token_mean_fwd(_ptr(x), B, N, D, _ptr(pooled), _stream()), "mofo_token_mean_fwd")
+    return pooled
+
+
+def token_mean_bwd(dpooled, B, N, D, dx_f32, dx_bf16):
+    _check(load().mofo_token_mean_bwd(_ptr(dpooled), B, N, D, _ptr(dx_f32), _ptr(dx_bf16), _stream()), "mofo_token_mean_bwd")
 
 
 def target_mse(video, msk_idx, pred, loss_partials, loss, dpred, normalize_target=True, grad_scale=1.0,

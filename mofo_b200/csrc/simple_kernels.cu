@@ -469,6 +469,68 @@ __global__ void assemble_bwd_kernel(const float* __restrict__ dx_full, int n_vis
 }
 
 // =================================================================================================
+// (6b) token mean pooling (finetuning classifier)  — modeling_finetune.py:400-401  fc_norm(x.mean(1))
+// =================================================================================================
+// grid = (row chunks, B), block (D/4 rounded up to 32, ASM_RG): threads own float4 column chunks, rows of the chunk are
+// streamed with 4 independent 16-byte loads in flight; one 16-byte vector reduction per 4 columns per CTA into out[b].
+__global__ void token_mean_fwd_kernel(const float* __restrict__ x, int N, int D, int rows_per_cta, float inv_n,
+                                      float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float4 part[];                      // [ASM_RG][D / 4]
+  const int b = blockIdx.y;
+  const int C4 = D >> 2;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+  const int c = threadIdx.x, ry = threadIdx.y;
+  float4 acc = make_float4(0, 0, 0, 0);
+  if (c < C4) {
+    const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * N * D) + c;
+    for (int r = r0 + ry; r < r1; r += 4 * ASM_RG) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = r + u * ASM_RG;
+        v[u] = rr < r1 ? src[static_cast<size_t>(rr) * C4] : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    part[ry * C4 + c] = acc;
+  }
+  __syncthreads();
+  if (ry == 0 && c < C4) {
+#pragma unroll
+    for (int g = 1; g < ASM_RG; ++g) {
+      const float4 o = part[g * C4 + c];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    acc.x *= inv_n; acc.y *= inv_n; acc.z *= inv_n; acc.w *= inv_n;
+    atomicAdd(reinterpret_cast<float4*>(out + static_cast<size_t>(b) * D) + c, acc);
+  }
+}
+
+// dx[b, n, :] = dpooled[b, :] / N for every token n (f32 and / or bf16 copy), 16 bytes per thread and iteration
+__global__ void __launch_bounds__(256) token_mean_bwd_kernel(const float* __restrict__ dpooled, int N, int D, float inv_n,
+                                                             int64_t total4, float* __restrict__ dx_f32,
+                                                             __nv_bfloat16* __restrict__ dx_bf16) {
+  pdl_wait();
+  pdl_trigger();
+  const int C4 = D >> 2;
+  const int64_t per_clip = static_cast<int64_t>(N) * C4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_clip), c = static_cast<int>(i % C4);
+    float4 v = __ldg(reinterpret_cast<const float4*>(dpooled + static_cast<size_t>(b) * D) + c);
+    v.x *= inv_n; v.y *= inv_n; v.z *= inv_n; v.w *= inv_n;
+    if (dx_f32) reinterpret_cast<float4*>(dx_f32)[i] = v;
+    if (dx_bf16) {
+      uint2 p; p.x = pack_bf16(v.x, v.y); p.y = pack_bf16(v.z, v.w);
+      reinterpret_cast<uint2*>(dx_bf16)[i] = p;
+    }
+  }
+}
+
+// =================================================================================================
 // (7) target + MSE  — engine_for_pretraining.py:258-304
 // =================================================================================================
 __device__ __forceinline__ float block_sum_128(float v, float* sh) {  // 128 threads; result broadcast
@@ -838,6 +900,33 @@ int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk,
   const size_t smem = static_cast<size_t>(ASM_RG) * (Dd >> 2) * sizeof(float4);
   MOFO_CUDA(launch_pdl(assemble_bwd_kernel, grid, dim3(cx, ASM_RG), smem, static_cast<cudaStream_t>(stream), dx_full, n_vis, n_msk, Dd,
                        rows_per_cta, dmask_token, reinterpret_cast<__nv_bfloat16*>(dvis)));
+  return MOFO_OK;
+}
+
+int mofo_token_mean_fwd(const float* x, int B, int N, int D, float* pooled, void* stream) {
+  MOFO_CHECK_ARG(x && pooled, "token_mean_fwd: null pointer");
+  MOFO_CHECK_ARG(B > 0 && N > 0 && D > 0 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 15) == 0, "token_mean_fwd: bad shape B=%d N=%d D=%d", B, N, D);
+  const int cx = ((D >> 2) + 31) / 32 * 32;
+  MOFO_CHECK_ARG(cx * ASM_RG <= 1024, "token_mean_fwd: D=%d too wide", D);
+  int chunks = (2 * sm_count() + B - 1) / B;
+  int rows_per_cta = (N + chunks - 1) / chunks;
+  if (rows_per_cta < 4 * ASM_RG) rows_per_cta = 4 * ASM_RG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MOFO_CUDA(cudaMemsetAsync(pooled, 0, static_cast<size_t>(B) * D * sizeof(float), s));
+  dim3 grid((N + rows_per_cta - 1) / rows_per_cta, B);
+  const size_t smem = static_cast<size_t>(ASM_RG) * (D >> 2) * sizeof(float4);
+  MOFO_CUDA(launch_pdl(token_mean_fwd_kernel, grid, dim3(cx, ASM_RG), smem, s, x, N, D, rows_per_cta, 1.0f / N, pooled));
+  return MOFO_OK;
+}
+
+int mofo_token_mean_bwd(const float* dpooled, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16, void* stream) {
+  MOFO_CHECK_ARG(dpooled && (dx_f32 || dx_bf16), "token_mean_bwd: null pointer");
+  MOFO_CHECK_ARG(B > 0 && N > 0 && D > 0 && D % 4 == 0, "token_mean_bwd: bad shape B=%d N=%d D=%d", B, N, D);
+  const int64_t total4 = static_cast<int64_t>(B) * N * (D >> 2);
+  int64_t blocks = (total4 + 255) / 256;
+  if (blocks > 16L * sm_count()) blocks = 16L * sm_count();
+  MOFO_CUDA(launch_pdl(token_mean_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                       dpooled, N, D, 1.0f / N, total4, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16)));
   return MOFO_OK;
 }
 

@@ -1,0 +1,304 @@
+"""B200-native look-alike of the reference's ``modeling_finetune.VisionTransformer`` (BASELINE configs[4]).
+
+Same public surface as /root/reference/modeling_finetune.py:305-409 for the plain classifier: constructor keywords,
+``forward(x) -> logits [B, num_classes]``, ``forward_features``, ``get_num_layers``, ``no_weight_decay``,
+``get_classifier`` / ``reset_classifier`` and the reference's ``state_dict`` names (``patch_embed.proj.*``,
+``blocks.i.{norm1,attn.{q_bias,v_bias,qkv,proj},norm2,mlp.{fc1,fc2}}``, ``fc_norm.*``, ``head.*``), so a pretraining
+checkpoint whose ``encoder.`` prefix was stripped (run_class_finetuning.py) loads unchanged; registry entry points
+``vit_small_patch16_224``, ``vit_base_patch16_224``, ``vit_large_patch16_224``.
+
+All 1568 tokens of a clip run through the encoder - the dense-attention stress of the hot path: tubelet gather + patch
+embedding GEMM with the position table fused, 12 pre-LN blocks on the same kernels as the pretraining step
+(``_Runner._block_fwd/_block_bwd``: tcgen05 GEMMs with fused epilogues, streaming attention at S = 1568, LayerNorm),
+token mean pooling (``mofo_token_mean_fwd/bwd``), ``fc_norm`` and the classifier head (a padded-N GEMM).  ``forward`` is
+one ``autograd.Function`` whose backward is the manual kernel backward, so the reference's ``engine_for_finetuning``
+(criterion on the logits, ``loss_scaler(loss, optimizer, ...)``) drives it unchanged.  No CPU / eager fallback.
+
+Not implemented (raises): DropPath > 0 (the finetuning recipe's 0.1), dropout, ``init_values`` > 0, learnable position
+embedding, ``use_mean_pooling=False``; the box-focused classifier ``VisionTransformer_BB_focused`` (:422-635) is out of
+scope of this round.
+"""
+from __future__ import annotations
+
+import os
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .modeling_pretrain import _Block, _PatchEmbed, _Runner, _trunc_normal_, get_sinusoid_encoding_table
+
+__all__ = ["VisionTransformer", "vit_small_patch16_224", "vit_base_patch16_224", "vit_large_patch16_224", "create_model"]
+
+
+class _FtRunner(_Runner):
+    """Kernel orchestration of the classifier: reuses the block forward / backward, buffers, weight cache and arena
+    machinery of the pretraining runner; only the ends of the network differ."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.blk_group = int(os.environ.get("MOFO_ENC_GROUP", "4"))
+
+    def _ensure_device(self, device):
+        if self.device != device:
+            self.device = device
+            self.bufs.clear(); self.wcache.clear(); self.wversion = None
+            self.arena = None; self.arena_views = None; self.scratch_arena = None
+            self.pos = self.m.pos_embed[0].to(device).contiguous()
+
+    def backward_order(self):
+        m = self.m
+        names = dict(m.named_parameters())
+        order, stage_of = [], {}
+
+        def add(prefix, stage):
+            for n in names:
+                if (n == prefix or n.startswith(prefix + ".")) and n not in stage_of:
+                    order.append(n); stage_of[n] = stage
+        add("head", 0); add("fc_norm", 0)
+        nb = len(m.blocks)
+        for i in range(nb - 1, -1, -1):
+            add(f"blocks.{i}", (nb - 1 - i) // self.blk_group)
+        last = (nb - 1) // self.blk_group
+        add("patch_embed", last)
+        assert len(order) == len(names)
+        return order, stage_of, last + 1
+
+    def prepare_weights(self):
+        m = self.m
+        version = tuple(p._version for p in m.parameters())
+        if version == self.wversion:
+            return
+        self.wversion = version
+        wc = self.wcache
+
+        def cast(name, W, need_t=True, pad_rows=0):
+            R = W.shape[0]
+            C = W.numel() // R
+            Rp = R + pad_rows
+            if name not in wc:
+                wb = torch.zeros(Rp, C, dtype=torch.bfloat16, device=self.device)
+                wt = torch.zeros(C, Rp, dtype=torch.bfloat16, device=self.device) if need_t else None
+                wc[name] = (wb, wt)
+            wb, wt = wc[name]
+            if pad_rows == 0:
+                _lib.cast_weight(W.detach(), wb, wt)
+            else:                   # classifier head: rows padded to a multiple of 8 with zeros (GEMM N / K granularity)
+                tmp = torch.zeros(Rp, C, dtype=torch.float32, device=self.device)
+                tmp[:R].copy_(W.detach())
+                _lib.cast_weight(tmp, wb, wt)
+
+        cast("pe", m.patch_embed.proj.weight, need_t=False)
+        for i, blk in enumerate(m.blocks):
+            pre = f"blk{i}"
+            cast(pre + ".qkv", blk.attn.qkv.weight)
+            cast(pre + ".proj", blk.attn.proj.weight)
+            cast(pre + ".fc1", blk.mlp.fc1.weight)
+            cast(pre + ".fc2", blk.mlp.fc2.weight)
+            qb = self.buf(pre + ".qkvbias", (3 * blk.attn.q_bias.numel(),), torch.float32)
+            _lib.pack_qkv_bias(blk.attn.q_bias.detach(), blk.attn.v_bias.detach(), qb)
+        C = m.num_classes
+        self.c_pad = (C + 7) // 8 * 8
+        cast("head", m.head.weight, pad_rows=self.c_pad - C)
+        hb = self.buf("head.bias_pad", (self.c_pad,), torch.float32)
+        hb.zero_()
+        hb[:C].copy_(m.head.bias.detach())
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def forward(self, x):
+        m = self.m
+        self._ensure_device(x.device)
+        self.prepare_weights()
+        bf, f32 = torch.bfloat16, torch.float32
+        B = x.shape[0]
+        N = m.patch_embed.num_patches
+        D = m.embed_dim
+        wc = self.wcache
+        self.shape = (B, N)
+        idx = self.bufs.get(("idx_all", B, N))
+        if idx is None:
+            idx = torch.arange(N, dtype=torch.int32, device=self.device).repeat(B, 1).contiguous()
+            self.bufs[("idx_all", B, N)] = idx
+        # patch embedding of every tube + bias + position table (modeling_finetune.py:390-394)
+        A_pe = self.buf("A_pe", (B * N, 1536), bf)
+        _lib.gather_tubes(x, idx, A_pe)
+        xe = self.buf("x0", (B * N, D), f32)
+        pe = m.patch_embed.proj
+        _lib.gemm_tn(A_pe, wc["pe"][0], _lib.EPI_BIAS_POS_F32, xe, bias=pe.bias, pos=self.pos, row_idx=idx, group_rows=N,
+                     out_group_rows=N)
+        for i, blk in enumerate(m.blocks):
+            xe = self._block_fwd(f"blk{i}", blk, xe, B * N, N, B, D)
+        self.x_out = xe
+        # norm = Identity, fc_norm(x.mean(1)), head  (:398-401, 405-406)
+        pooled = self.buf("pooled", (B, D), f32)
+        _lib.token_mean_fwd(xe, B, N, D, pooled)
+        hn = self.buf("fc.hn", (B, D), bf); mean = self.buf("fc.mean", (B,), f32); rstd = self.buf("fc.rstd", (B,), f32)
+        _lib.layernorm_fwd(pooled, m.fc_norm.weight, m.fc_norm.bias, hn, mean, rstd, B, D, m.fc_norm.eps)
+        logits = self.buf("logits", (B, self.c_pad), f32)
+        zero = self.buf("logits.zero", (B, self.c_pad), f32)
+        if not getattr(self, "_zeroed", False):
+            zero.zero_(); self._zeroed = True
+        _lib.gemm_tn(hn, wc["head"][0], _lib.EPI_BIAS_RESID_F32, logits, bias=self.buf("head.bias_pad", (self.c_pad,), f32),
+                     resid=zero)
+        return logits
+
+    # ---- backward -----------------------------------------------------------------------------------------
+    def backward(self, dlogits, g):
+        """dlogits f32 [B, num_classes]; g: name -> fp32 tensor the parameter gradient is ACCUMULATED into."""
+        m = self.m
+        bf, f32 = torch.bfloat16, torch.float32
+        B, N = self.shape
+        D = m.embed_dim
+        C = m.num_classes
+        wc = self.wcache
+        dl = self.buf("bwd.dl", (B, self.c_pad), bf)
+        dl.zero_()
+        dl[:, :C].copy_(dlogits)
+        hn = self.buf("fc.hn", (B, D), bf)
+        dWp = self.buf("bwd.dWhead", (self.c_pad, D), f32); dbp = self.buf("bwd.dbhead", (self.c_pad,), f32)
+        dWp.zero_(); dbp.zero_()
+        _lib.gemm_wgrad(dl, hn, dWp, dbias=dbp)
+        g["head.weight"].add_(dWp[:C]); g["head.bias"].add_(dbp[:C])
+        dhn = self.buf("bwd.dhn", (B, D), bf)
+        _lib.gemm_tn(dl, wc["head"][1], _lib.EPI_PLAIN_BF16, dhn)
+        dpooled = self.buf("bwd.dpooled", (B, D), f32)
+        _lib.layernorm_bwd(dhn, self.buf("pooled", (B, D), f32), m.fc_norm.weight, self.buf("fc.mean", (B,), f32),
+                           self.buf("fc.rstd", (B,), f32), None, B, D, dpooled, None, g["fc_norm.weight"], g["fc_norm.bias"])
+        dxA = self.buf("bwd.dxA", (B * N, D), f32); dxA16 = self.buf("bwd.dxA16", (B * N, D), bf)
+        dxB = self.buf("bwd.dxB", (B * N, D), f32); dxB16 = self.buf("bwd.dxB16", (B * N, D), bf)
+        _lib.token_mean_bwd(dpooled, B, N, D, dxA, dxA16)
+        nb = len(m.blocks)
+        for i in range(nb - 1, -1, -1):
+            x_in = self.buf("x0", (B * N, D), f32) if i == 0 else self.buf(f"blk{i - 1}.xo", (B * N, D), f32)
+            self._block_bwd(f"blk{i}", m.blocks[i], g, x_in, dxA, dxA16, dxB, dxB16, B * N, N, B, D)
+        A_pe = self.buf("A_pe", (B * N, 1536), bf)
+        self._wgrad((), dxA16, A_pe, g["patch_embed.proj.weight"], dbias=g["patch_embed.proj.bias"])
+        self._join_side()
+
+
+class _FtForwardFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, x, *params):
+        logits = runner.forward(x)
+        ctx.runner = runner
+        return logits[:, :runner.m.num_classes].clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        r = ctx.runner
+        if r.scratch_arena is None:
+            r.scratch_arena = r._make_arena()
+        arena, views = r.scratch_arena
+        arena.zero_()
+        r.backward(dlogits.float().contiguous(), views)
+        return (None, None) + tuple(views[n] for n, _ in r.m.named_parameters())
+
+
+class VisionTransformer(nn.Module):
+    """Constructor signature of modeling_finetune.py:308-328."""
+
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
+                 mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.,
+                 norm_layer=nn.LayerNorm, init_values=0., use_learnable_pos_emb=False, init_scale=0., all_frames=16,
+                 tubelet_size=2, use_mean_pooling=True):
+        super().__init__()
+        unsupported = dict(patch_size=(patch_size, 16), in_chans=(in_chans, 3), qk_scale=(qk_scale, None), drop_rate=(drop_rate, 0.),
+                           attn_drop_rate=(attn_drop_rate, 0.), drop_path_rate=(drop_path_rate, 0.), init_values=(init_values, 0.),
+                           use_learnable_pos_emb=(use_learnable_pos_emb, False), tubelet_size=(tubelet_size, 2),
+                           use_mean_pooling=(use_mean_pooling, True))
+        for k, (v, want) in unsupported.items():
+            if v != want and not (v is None and want is None):
+                raise NotImplementedError(f"mofo_b200 finetuning classifier supports {k}={want!r} only (got {v!r})")
+        if embed_dim // num_heads != 64 or num_classes <= 0:
+            raise NotImplementedError("attention kernels are specialised for head_dim 64; num_classes must be positive")
+        self.num_classes = num_classes
+        self.num_features = self.embed_dim = embed_dim
+        self.tubelet_size = tubelet_size
+        self.patch_embed = _PatchEmbed(img_size, patch_size, in_chans, embed_dim, num_frames=all_frames, tubelet_size=tubelet_size)
+        self.pos_embed = get_sinusoid_encoding_table(self.patch_embed.num_patches, embed_dim)   # attribute, not a buffer (:338-340)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        self.blocks = nn.ModuleList([_Block(embed_dim, num_heads, mlp_ratio, qkv_bias, norm_layer) for _ in range(depth)])
+        self.norm = nn.Identity()
+        self.fc_norm = norm_layer(embed_dim)
+        self.head = nn.Linear(embed_dim, num_classes)
+        _trunc_normal_(self.head.weight, std=.02)
+        self.apply(self._init_weights)
+        self.head.weight.data.mul_(init_scale)
+        self.head.bias.data.mul_(init_scale)
+        for i, blk in enumerate(self.blocks):
+            blk._mofo_name = f"blocks.{i}"
+        self._runner = _FtRunner(self)
+
+    def _init_weights(self, m):                       # modeling_finetune.py:365-372
+        if isinstance(m, nn.Linear):
+            _trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def get_num_layers(self):
+        return len(self.blocks)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'pos_embed', 'cls_token'}
+
+    def get_classifier(self):
+        return self.head
+
+    def reset_classifier(self, num_classes, global_pool=''):
+        self.num_classes = num_classes
+        self.head = nn.Linear(self.embed_dim, num_classes).to(self.head.weight.device)
+        self._runner.wcache.pop("head", None); self._runner.wversion = None
+        self._runner.arena = None; self._runner.arena_views = None; self._runner.scratch_arena = None
+
+    def forward(self, x):
+        """x: CUDA f32 [B,3,all_frames,224,224] -> logits f32 [B, num_classes] (autograd flows to every parameter)."""
+        if not x.is_cuda:
+            raise RuntimeError("mofo_b200.VisionTransformer runs on CUDA (sm_100a) only; there is no CPU path")
+        x = x.float().contiguous()
+        r = self._runner
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return _FtForwardFn.apply(r, x, *self.parameters())
+        with torch.no_grad():
+            return r.forward(x)[:, :self.num_classes].clone()
+
+
+_REGISTRY = {}
+
+
+def _register(fn):
+    _REGISTRY[fn.__name__] = fn
+    try:
+        from timm.models.registry import register_model
+        register_model(fn)
+    except Exception:
+        pass
+    return fn
+
+
+@_register
+def vit_small_patch16_224(pretrained=False, **kwargs):
+    return VisionTransformer(patch_size=16, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, qkv_bias=True,
+                             norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+@_register
+def vit_base_patch16_224(pretrained=False, **kwargs):
+    return VisionTransformer(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                             norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+@_register
+def vit_large_patch16_224(pretrained=False, **kwargs):
+    return VisionTransformer(patch_size=16, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4, qkv_bias=True,
+                             norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+def create_model(name, pretrained=False, **kwargs):
+    """timm.create_model look-alike (drops None-valued kwargs like timm 0.4.12; run_class_finetuning.py)."""
+    kwargs = {k: v for k, v in kwargs.items() if v is not None}
+    return _REGISTRY[name](pretrained=pretrained, **kwargs)

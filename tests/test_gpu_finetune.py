@@ -1,0 +1,79 @@
+"""Finetuning classifier (BASELINE configs[4]): the B200 VisionTransformer against the REFERENCE's own
+modeling_finetune.VisionTransformer (baseline/_ref, unmodified) on the same GPU - logits and every parameter gradient of a
+cross-entropy step, reference fp32 (TF32 off) as ground truth and the reference under bf16 autocast as the calibration of
+what a 16-bit path can reach (same rule as tests/test_gpu_reference_parity.py)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _refrun():
+    from baseline import refrun
+    if not refrun.available():
+        pytest.skip("baseline/_ref is not staged (python baseline/setup_ref.py needs /root/reference)")
+    return refrun
+
+
+def _ref_step(model, x, y, amp):
+    model.zero_grad(set_to_none=True)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            logits = model(x)
+            loss = torch.nn.functional.cross_entropy(logits.float(), y)
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    return logits.detach().float(), loss.item(), {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+
+
+@pytest.mark.parametrize("name,B,classes,init_scale", [("vit_small_patch16_224", 2, 174, 1.0), ("vit_base_patch16_224", 2, 174, 0.001),
+                                                       ("vit_base_patch16_224", 3, 97, 1.0)])
+def test_classifier_step_matches_reference(name, B, classes, init_scale):
+    refrun = _refrun()
+    ref = refrun.load()
+    from mofo_b200 import modeling_finetune as mf
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    kw = dict(num_classes=classes, all_frames=16, tubelet_size=2, drop_rate=0.0, drop_path_rate=0.0, attn_drop_rate=0.0,
+              use_mean_pooling=True, init_scale=init_scale)
+    ref_model = getattr(ref.modeling_finetune, name)(pretrained=False, **kw).to(dev).train()
+    with torch.no_grad():                           # biases / norms away from their (0, 1) initialisation
+        for n, p in ref_model.named_parameters():
+            if p.ndim == 1:
+                p.add_(torch.randn_like(p) * 0.05)
+    ours = mf.create_model(name, pretrained=False, drop_block_rate=None, **kw)
+    sd = ref_model.state_dict()
+    assert list(ours.state_dict().keys()) == list(sd.keys())
+    ours.load_state_dict(sd, strict=True)
+    ours = ours.to(dev).train()
+    x = refrun.synthetic_batches(B, 1, seed=11, device=dev)[0][0]
+    y = torch.randint(0, classes, (B,), device=dev)
+
+    l32, loss32, g32 = _ref_step(ref_model, x, y, amp=False)
+    l16, loss16, g16 = _ref_step(ref_model, x, y, amp=True)
+    logits = ours(x)
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == (B, classes)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    g = {n: p.grad.detach().clone() for n, p in ours.named_parameters()}
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300)).item()
+    e_logits, r_logits = rel(logits.detach(), l32), rel(l16, l32)
+    e_loss, r_loss = abs(loss.item() - loss32) / abs(loss32), abs(loss16 - loss32) / abs(loss32)
+    print(f"{name} B={B}: logits rel {e_logits:.3e} (reference bf16 {r_logits:.3e}); loss rel {e_loss:.3e} ({r_loss:.3e})")
+    assert e_logits <= max(2e-2, 2.5 * r_logits) and e_loss <= max(1e-3, 2.5 * r_loss)
+    bad, worst = [], (0.0, "")
+    for n in g32:
+        e, r = rel(g[n], g32[n]), rel(g16[n], g32[n])
+        worst = max(worst, (e, n))
+        if e > max(3e-2, 2.5 * r):
+            bad.append((n, e, r))
+    print("worst gradient:", worst)
+    assert not bad, bad[:8]
+    # eval / no_grad forward returns the same logits
+    with torch.no_grad():
+        assert torch.equal(ours(x), logits.detach())

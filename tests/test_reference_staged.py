@@ -87,3 +87,25 @@ def test_dropin_utils_and_optim_factory_resolve_to_b200_versions(monkeypatch):
             sys.modules.pop(n, None)
             if saved[n] is not None:
                 sys.modules[n] = saved[n]
+
+
+def test_finetune_classifier_schema_matches_reference():
+    """state_dict keys / shapes / order of the classifier look-alike equal the reference's VisionTransformer
+    (modeling_finetune.py:305-409), and its values load."""
+    refrun = _refrun()
+    ref = refrun.load()
+    from mofo_b200 import modeling_finetune as mf
+    kw = dict(num_classes=174, all_frames=16, tubelet_size=2, drop_path_rate=0.0, use_mean_pooling=True, init_scale=0.001)
+    torch.manual_seed(2)
+    rm = ref.modeling_finetune.vit_small_patch16_224(pretrained=False, **kw)
+    om = mf.create_model("vit_small_patch16_224", pretrained=False, drop_block_rate=None, **kw)
+    sd = rm.state_dict()
+    assert list(sd.keys()) == list(om.state_dict().keys())
+    assert all(tuple(sd[k].shape) == tuple(v.shape) for k, v in om.state_dict().items())
+    om.load_state_dict(sd, strict=True)
+    assert om.no_weight_decay() == rm.no_weight_decay() and om.get_num_layers() == rm.get_num_layers()
+    assert torch.equal(om.pos_embed, rm.pos_embed)
+    with pytest.raises(NotImplementedError):
+        mf.create_model("vit_small_patch16_224", num_classes=174, drop_path_rate=0.1)
+    with pytest.raises(RuntimeError):
+        om(torch.zeros(1, 3, 16, 224, 224))
