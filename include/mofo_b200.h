@@ -203,6 +203,19 @@ int mofo_sq_norm_f32(const float* x, int64_t n, float* out, void* stream);
 int mofo_normalize_u8(const uint8_t* clip_u8, int B, int frames, int size, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * (8c) Clip preprocessing on the GPU: what the reference does per sample on the CPU in
+ * GroupMultiScaleCrop_BB_no_global_union.__call__ (transforms.py:103-135: albumentations Crop + Resize(224, bilinear) with
+ * the pascal_voc motion box riding along) -> Stack -> ToTorchFormatTensor(div=True) -> GroupNormalize (datasets.py:44-50).
+ * frames: uint8 [B,T,H,W,3] (decoded RGB frames, HWC); crops: int32 [B,4] = (x_off, y_off, crop_w, crop_h) per clip (chosen
+ * on the host as transforms.py:137-159 does); boxes_in f64 [B,T,4] (x1,y1,x2,y2 in frame pixels; may be NULL).
+ * clip_out: f32 [B,3,T,out,out] (NCTHW), bit-identical to cv2.resize(INTER_LINEAR) + /255 + (x-mean)/std;
+ * boxes_out: f64 [B,T,4] in output pixels, [0,0,1,1] where the crop leaves nothing of the box (transforms.py:120-123).
+ * crop_w / crop_h must fit inside the frame.  The host ships 1 byte per source pixel instead of 4 per output sample.
+ */
+int mofo_clip_preprocess(const uint8_t* frames, int B, int T, int H, int W, const int32_t* crops, const double* boxes_in,
+                         int out_size, float* clip_out, double* boxes_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * (9) Fused AdamW over the flat arenas.  Replaces torch.optim.AdamW.step() as created by
  * optim_factory.create_optimizer (optim_factory.py:126-127) and driven by utils.py:355-364 (clip + step), plus the
  * per-step fp32->bf16 operand casts.  params / grads / exp_avg / exp_avg_sq are f32 arenas with identical layout.

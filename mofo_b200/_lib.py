@@ -42,6 +42,7 @@ SIGNATURES = {
     "mofo_colsum_bf16": ([_P, _I, _I, _I, _P, _P], C.c_int),
     "mofo_sq_norm_f32": ([_P, _L, _P, _P], C.c_int),
     "mofo_normalize_u8": ([_P, _I, _I, _I, _P, _P], C.c_int),
+    "mofo_clip_preprocess": ([_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P], C.c_int),
     "mofo_adamw_step": ([_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P], C.c_int),
 }
 
@@ -290,6 +291,17 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, w16, segs, tiles, hyper, clip
     _check(load().mofo_adamw_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(w16), _ptr(segs),
                                   _ptr(tiles), tiles.shape[0], _ptr(hyper), _ptr(clip_coef), _ptr(loss_guard), _stream()),
            "mofo_adamw_step")
+
+
+def clip_preprocess(frames_u8, crops, boxes_in, out_size, clip_out, boxes_out):
+    """frames_u8 uint8 [B,T,H,W,3], crops int32 [B,4], boxes_in f64 [B,T,4] | None -> clip_out f32 [B,3,T,S,S], boxes_out f64 [B,T,4]."""
+    B, T, H, W, Cc = frames_u8.shape
+    assert Cc == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+    assert crops.dtype == torch.int32 and crops.shape == (B, 4) and crops.is_contiguous()
+    assert boxes_in is None or (boxes_in.dtype == torch.float64 and boxes_in.shape == (B, T, 4) and boxes_in.is_contiguous())
+    _check(load().mofo_clip_preprocess(_ptr(frames_u8), B, T, H, W, _ptr(crops), _ptr(boxes_in), out_size, _ptr(clip_out),
+                                       _ptr(boxes_out), _stream()), "mofo_clip_preprocess")
+    return clip_out, boxes_out
 
 
 def normalize_u8(clip_u8, out):

@@ -733,6 +733,89 @@ __global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __rest
   }
 }
 
+// =================================================================================================
+// (8c) clip preprocessing: crop + bilinear resize + /255 + normalise + NCTHW, and the box transform
+// =================================================================================================
+// One CTA per frame (b, t).  OpenCV's 8-bit INTER_LINEAR is reproduced bit for bit: taps in float exactly as resize.cpp
+// computes them, 11-bit coefficients, int32 horizontal pass, the (>> 4, >> 16, + 2, >> 2) vertical pass.
+struct Tap { int idx; int a0; int a1; };
+__device__ __forceinline__ Tap linear_tap(int d, int dn, int sn, bool is_y) {
+  // separately rounded double operations (no FMA contraction), as the host code of resize.cpp evaluates them
+  const double scale = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dn), static_cast<double>(sn)));
+  float f = __double2float_rn(__dsub_rn(__dmul_rn(d + 0.5, scale), 0.5));
+  int s = static_cast<int>(floorf(f));
+  f = __fsub_rn(f, static_cast<float>(s));
+  if (!is_y) {                                   // columns: taps outside the row are reset; rows are clipped instead
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+  }
+  Tap t;
+  t.idx = s;
+  t.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  t.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  return t;
+}
+
+__global__ void __launch_bounds__(256) clip_preprocess_kernel(const uint8_t* __restrict__ frames, int T, int H, int W,
+                                                              const int32_t* __restrict__ crops,
+                                                              const double* __restrict__ boxes_in, int S,
+                                                              float* __restrict__ out, double* __restrict__ boxes_out) {
+  extern __shared__ int tap_s[];                 // [2][S][3]: x taps then y taps
+  const int t = blockIdx.x, b = blockIdx.y;
+  const int x_off = crops[b * 4 + 0], y_off = crops[b * 4 + 1], cw = crops[b * 4 + 2], ch = crops[b * 4 + 3];
+  for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) {
+    const bool is_y = i >= S;
+    const Tap tp = linear_tap(is_y ? i - S : i, S, is_y ? ch : cw, is_y);
+    tap_s[i * 3 + 0] = tp.idx; tap_s[i * 3 + 1] = tp.a0; tap_s[i * 3 + 2] = tp.a1;
+  }
+  if (threadIdx.x == 0 && boxes_in != nullptr) {                 // pascal_voc box through Crop + Resize (albumentations semantics)
+    const double* bi = boxes_in + (static_cast<size_t>(b) * T + t) * 4;
+    double* bo = boxes_out + (static_cast<size_t>(b) * T + t) * 4;
+    const double dims[4] = {static_cast<double>(W), static_cast<double>(H), static_cast<double>(W), static_cast<double>(H)};
+    const double offs[4] = {static_cast<double>(x_off), static_cast<double>(y_off), static_cast<double>(x_off), static_cast<double>(y_off)};
+    const double cdim[4] = {static_cast<double>(cw), static_cast<double>(ch), static_cast<double>(cw), static_cast<double>(ch)};
+    double c[4];
+    for (int k = 0; k < 4; ++k) {                 // normalise, shift into the crop, re-normalise: separately rounded steps
+      const double n = __ddiv_rn(bi[k], dims[k]);
+      c[k] = __ddiv_rn(__dsub_rn(__dmul_rn(n, dims[k]), offs[k]), cdim[k]);
+      c[k] = fmin(fmax(c[k], 0.0), 1.0);
+    }
+    if (__dmul_rn(__dsub_rn(c[2], c[0]), __dsub_rn(c[3], c[1])) <= 0.0) { bo[0] = 0.0; bo[1] = 0.0; bo[2] = 1.0; bo[3] = 1.0; }   // transforms.py:120-123
+    else { for (int k = 0; k < 4; ++k) bo[k] = __dmul_rn(c[k], static_cast<double>(S)); }
+  }
+  __syncthreads();
+  const uint8_t* src = frames + ((static_cast<size_t>(b) * T + t) * H + y_off) * W * 3 + static_cast<size_t>(x_off) * 3;
+  const size_t row_bytes = static_cast<size_t>(W) * 3;
+  const float mean_c[3] = {0.485f, 0.456f, 0.406f}, std_c[3] = {0.229f, 0.224f, 0.225f};
+  const int groups = S >> 2;                      // 4 output pixels per thread and iteration
+  const size_t plane = static_cast<size_t>(S) * S;
+  float* dst = out + (static_cast<size_t>(b) * 3 * T + t) * plane;       // channel c plane at + c * T * plane
+  for (int g = threadIdx.x; g < S * groups; g += blockDim.x) {
+    const int dy = g / groups, dx0 = (g % groups) * 4;
+    const int sy = tap_s[(S + dy) * 3], b0 = tap_s[(S + dy) * 3 + 1], b1 = tap_s[(S + dy) * 3 + 2];
+    const uint8_t* r0 = src + static_cast<size_t>(min(max(sy, 0), ch - 1)) * row_bytes;
+    const uint8_t* r1 = src + static_cast<size_t>(min(max(sy + 1, 0), ch - 1)) * row_bytes;
+    float v[3][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int sx = tap_s[(dx0 + e) * 3], a0 = tap_s[(dx0 + e) * 3 + 1], a1 = tap_s[(dx0 + e) * 3 + 2];
+      const int sx1 = min(sx + 1, cw - 1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int S0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
+        const int S1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+        int px = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+        px = min(max(px, 0), 255);
+        v[c][e] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(px), 255.0f), mean_c[c]), std_c[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      *reinterpret_cast<float4*>(dst + static_cast<size_t>(c) * T * plane + static_cast<size_t>(dy) * S + dx0) =
+          make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+  }
+}
+
 __global__ void __launch_bounds__(256) sq_norm_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
   __shared__ float sh[8];
   float s = 0.f;
@@ -978,6 +1061,19 @@ int mofo_normalize_u8(const uint8_t* clip_u8, int B, int frames, int size, float
   const int64_t n16 = static_cast<int64_t>(B) * 3 * plane / 16;
   normalize_u8_kernel<<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(clip_u8, out, n16, plane / 16);
   MOFO_LAUNCH_CHECK("normalize_u8_kernel");
+  return MOFO_OK;
+}
+
+int mofo_clip_preprocess(const uint8_t* frames, int B, int T, int H, int W, const int32_t* crops, const double* boxes_in,
+                         int out_size, float* clip_out, double* boxes_out, void* stream) {
+  MOFO_CHECK_ARG(frames && crops && clip_out && (!boxes_in || boxes_out), "clip_preprocess: null pointer");
+  MOFO_CHECK_ARG(B > 0 && T > 0 && H > 1 && W > 1 && out_size > 0 && out_size % 4 == 0 && out_size <= 1024 && B <= 65535,
+                 "clip_preprocess: bad shape B=%d T=%d H=%d W=%d out=%d", B, T, H, W, out_size);
+  MOFO_CHECK_ARG((reinterpret_cast<uintptr_t>(clip_out) & 15) == 0, "clip_preprocess: clip_out must be 16-byte aligned");
+  const size_t smem = static_cast<size_t>(2) * out_size * 3 * sizeof(int);
+  clip_preprocess_kernel<<<dim3(T, B), 256, smem, static_cast<cudaStream_t>(stream)>>>(frames, T, H, W, crops, boxes_in, out_size,
+                                                                                      clip_out, boxes_out);
+  MOFO_LAUNCH_CHECK("clip_preprocess_kernel");
   return MOFO_OK;
 }
 

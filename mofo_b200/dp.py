@@ -26,6 +26,7 @@ class GradSync:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.comm_stream = None
+        self.hook_stream = None
         self.arena = None
         self.stage_end = None
         self.prev_end = 0
@@ -60,6 +61,10 @@ class GradSync:
         self.used_stream = False
         if (self.world > 1 or on_stage is not None) and arena.is_cuda and self.comm_stream is None:
             self.comm_stream = torch.cuda.Stream(device=arena.device)
+        if on_stage is not None and arena.is_cuda and getattr(self, "hook_stream", None) is None:
+            # the hook (optimizer update of a reduced slice) runs on its OWN stream behind an event, so that the next
+            # slice's all-reduce does not queue behind it on the communication stream
+            self.hook_stream = torch.cuda.Stream(device=arena.device)
 
     def stage_done(self, k):
         """Called by the backward pass right after the last gradient of arena stage ``k`` has been enqueued."""
@@ -76,7 +81,9 @@ class GradSync:
             with torch.cuda.stream(self.comm_stream):
                 if self.world > 1:
                     dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.pg)
-                if on_stage is not None:
+            if on_stage is not None:
+                self.hook_stream.wait_stream(self.comm_stream)
+                with torch.cuda.stream(self.hook_stream):
                     on_stage(k, lo, end)
             self.used_stream = True
         else:                                   # gloo / CPU tensors (host-logic tests)
@@ -94,3 +101,5 @@ class GradSync:
             self.stage_done(len(self.stage_end) - 1)
         if self.arena.is_cuda and self.comm_stream is not None:
             torch.cuda.current_stream(self.arena.device).wait_stream(self.comm_stream)
+            if getattr(self, "on_stage", None) is not None and getattr(self, "hook_stream", None) is not None:
+                torch.cuda.current_stream(self.arena.device).wait_stream(self.hook_stream)

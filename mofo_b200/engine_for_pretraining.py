@@ -36,7 +36,7 @@ from . import _lib
 from . import utils as _utils
 from .dp import GradSync
 
-__all__ = ["train_one_epoch_BB", "train_one_epoch_BB_no_global_union_gradual", "build_labels"]
+__all__ = ["train_one_epoch_BB", "train_one_epoch_BB_no_global_union_gradual", "build_labels", "fused_step", "masks_from_bbox"]
 
 
 def _core(model):
@@ -50,6 +50,31 @@ def build_labels(videos, msk_idx, normalize_target=True):
     out = torch.empty(B * n, 1536, dtype=torch.float32, device=videos.device)
     _lib.target_mse(videos, msk_idx, None, None, None, None, normalize_target, 1.0, out)
     return out.view(B, n, 1536)
+
+
+_MASK_GEN = {}
+
+
+def masks_from_bbox(bbox, device, grid=(8, 14, 14), mask_ratio=0.9, mask_ratio_bb=0.75, seed=10):
+    """Tube masks for a batch, generated ON THE GPU from the batch's motion boxes: (mask uint8 [B,N], vis_idx, msk_idx).
+
+    The reference builds the mask in DataLoader workers (datasets.py:56-58 -> masking_generator.py:43-85) right after
+    ``np.random.seed(10)`` (transforms.py:139), i.e. the mask is a deterministic function of the clip's first-frame box.
+    CUDA is not usable in forked workers, so instead of moving the generator there this reproduces exactly what the
+    worker would have returned - same box predicate, same MT19937 word stream of seed ``seed`` for every clip - from the
+    ``bbox`` tensor the batch already carries ([B,16,4] or [B,4]; float boxes reproduce the worker bit for bit, the
+    truncated LongTensor of kinetics.py:1064 reproduces what the generator returns for the truncated box)."""
+    from . import masking_generator as mg
+    key = (tuple(grid), float(mask_ratio), float(mask_ratio_bb), int(seed), str(device))
+    ent = _MASK_GEN.get(key)
+    if ent is None:
+        gen = mg.TubeMaskingGenerator_BB(grid, mask_ratio, mask_ratio_bb, device=device)
+        words = torch.from_numpy(mg.mt19937_words(seed, mg.words_per_clip(grid[1], grid[2])).view("int32")).to(device)
+        ent = _MASK_GEN[key] = (gen, words)
+    gen, words = ent
+    B = bbox.shape[0]
+    mask, vis_idx, msk_idx, _ = gen.generate_batch(bbox, words[None, :].expand(B, -1).contiguous())
+    return mask, vis_idx, msk_idx
 
 
 class _CudaPrefetcher:
@@ -159,6 +184,8 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
     start_steps = start_steps or 0
     pipelined = (fused and getattr(optimizer, "fused_mofo", False) and torch.device(device).type == "cuda"
                  and os.environ.get("MOFO_SYNC_EVERY_STEP", "0") != "1")
+    gpu_masks = fused and (os.environ.get("MOFO_GPU_MASKS", "0") == "1" or bool(getattr(data_loader, "mofo_gpu_masks", False)))
+    gpu_mask_ratios = getattr(data_loader, "mofo_mask_ratios", (0.9, 0.75))     # (mask_ratio, mask_ratio_BB) of the run
     pending = None                      # (event, pinned [loss, grad_norm], host-side values) of the step in flight
     if pipelined:
         pinned = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(2)]   # loss, grad norm, bad mask rows
@@ -213,12 +240,21 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
 
         videos, bbox, bool_masked_pos = batch                                           # :238
         videos = videos.to(device, non_blocking=True)
-        bool_masked_pos = bool_masked_pos.to(device, non_blocking=True).flatten(1).to(torch.bool)
+        if not gpu_masks:
+            bool_masked_pos = bool_masked_pos.to(device, non_blocking=True).flatten(1).to(torch.bool)
 
         if fused:
             core._runner._ensure_device(videos.device)
             arena = core._runner.grad_arena()
-            vis_idx, msk_idx = core.indices_from_mask(bool_masked_pos)
+            if gpu_masks:
+                # opt-in (MOFO_GPU_MASKS=1 or data_loader.mofo_gpu_masks): the loader's mask is ignored and the masks are
+                # generated on the GPU from the batch's boxes - lets the DataLoader keep num_workers > 0 with a no-op
+                # mask transform (CUDA cannot run in forked workers), see masks_from_bbox
+                pe = core.encoder.patch_embed
+                grid = (videos.shape[2] // pe.tubelet_size, videos.shape[3] // pe.patch_size[0], videos.shape[4] // pe.patch_size[1])
+                _, vis_idx, msk_idx = masks_from_bbox(bbox, videos.device, grid, *gpu_mask_ratios)
+            else:
+                vis_idx, msk_idx = core.indices_from_mask(bool_masked_pos)
             loss, grad_norm = fused_step(core, optimizer, loss_scaler, sync, videos, vis_idx, msk_idx, normlize_target, max_norm)
             if getattr(optimizer, "fused_mofo", False):
                 # the fused optimizer skips the update on the device when the loss is not finite, so the whole step
@@ -227,7 +263,8 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
                     slot = step & 1
                     pinned[slot][0:1].copy_(loss.detach().reshape(1), non_blocking=True)    # :306, read one step later
                     pinned[slot][1:2].copy_(grad_norm.detach().reshape(1), non_blocking=True)
-                    pinned[slot][2:3].copy_(core._bad_rows, non_blocking=True)
+                    if core._bad_rows is not None:
+                        pinned[slot][2:3].copy_(core._bad_rows, non_blocking=True)
                     events[slot].record()
                     mine = (events[slot], pinned[slot], (loss_scaler.state_dict()["scale"],) + group_stats())
                     if pending is not None:

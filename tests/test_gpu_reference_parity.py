@@ -247,3 +247,48 @@ def test_dropin_chain_takes_the_fused_path():
             if saved[n] is not None:
                 sys.modules[n] = saved[n]
         sys.modules.pop("_mofo_reference_utils", None); sys.modules.pop("_mofo_reference_optim_factory", None)
+
+
+def test_engine_gpu_masks_equal_the_reference_workers_masks():
+    """Opt-in engine mode (MOFO_GPU_MASKS / data_loader.mofo_gpu_masks): masks generated on the GPU from the batch's boxes are
+    what the reference's worker-side generator returns for the same boxes (np.random.seed(10) + TubeMaskingGenerator_BB),
+    bit for bit - for float boxes and for the truncated LongTensor the batch carries; and an epoch driven that way equals
+    an epoch fed the reference's masks through the loader."""
+    refrun = _refrun()
+    from mofo_b200 import engine_for_pretraining as eng
+    from mofo_b200 import modeling_pretrain as mp
+    from mofo_b200 import utils as U
+    from mofo_b200.optim_factory import FusedAdamW
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(9)
+    boxes = refrun.synthetic_boxes(24, rng) + rng.random((24, 4)) * 0.9          # float boxes, as albumentations yields
+    want = refrun.reference_masks(boxes)
+    bb16 = torch.from_numpy(boxes)[:, None, :].expand(24, 16, 4).contiguous()
+    mask, vis, msk = eng.masks_from_bbox(bb16, dev)
+    assert np.array_equal(mask.cpu().numpy(), want.astype(np.uint8))
+    assert torch.equal(vis.cpu(), torch.from_numpy(np.stack([np.nonzero(want[b] == 0)[0] for b in range(24)])).int())
+    assert torch.equal(msk.cpu(), torch.from_numpy(np.stack([np.nonzero(want[b] == 1)[0] for b in range(24)])).int())
+    bb_long = bb16.long()
+    want_long = refrun.reference_masks(bb_long[:, 0].numpy().astype(np.float64))
+    assert np.array_equal(eng.masks_from_bbox(bb_long, dev)[0].cpu().numpy(), want_long.astype(np.uint8))
+
+    def epoch(gpu_masks):
+        torch.manual_seed(0)
+        model = mp.create_model("pretrain_mae_small_patch16_224", pretrained=False, drop_path_rate=0.0, drop_block_rate=None,
+                                decoder_depth=4).to(dev)
+        opt = FusedAdamW([{"params": list(model.parameters()), "weight_decay": 0.05, "lr_scale": 1.0}], lr=1e-4, betas=(0.9, 0.95))
+        vids = refrun.synthetic_batches(4, 1, seed=5, device=dev)[0][0]
+
+        class Loader(list):
+            quiet = True
+            mofo_gpu_masks = gpu_masks
+        m = None if gpu_masks else torch.from_numpy(want_long[:4])
+        loader = Loader([(vids, bb_long[:4], m)] * 3)
+        stats = eng.train_one_epoch_BB(model, loader, opt, dev, 0, U.NativeScalerWithGradNormCount(), max_norm=None, patch_size=16,
+                                       normlize_target=True, start_steps=0)
+        return stats["loss"], torch.cat([p.detach().flatten() for p in model.parameters()])
+    l0, p0 = epoch(False)
+    l1, p1 = epoch(True)
+    # same masks -> same steps; the fp32 atomics of the weight-gradient reductions order differently between runs and Adam's
+    # m / sqrt(v) normalisation amplifies that on near-zero gradients, hence not bit-equal
+    assert abs(l0 - l1) <= 1e-5 * abs(l0) and ((p0 - p1).norm() / p0.norm()).item() < 1e-4
