@@ -571,22 +571,31 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ---------------------------------------------------------------------------------------------------
 // wgrad: dW[n, k] += sum_m dY[m, n] * X[m, k]
 // ---------------------------------------------------------------------------------------------------
-template <int BNW>
+// NT = 128-row n-tiles per CTA: the CTA owns an (NT*128) x BNW block of dW, i.e. NT accumulators that share every X tile
+// (one tcgen05.mma per n-tile and K-step against the same B operand).  These GEMMs are bound by L2 -> SM operand traffic
+// (a 128 x 256 tile is 85 flop per operand byte, the SM would need ~96 B/clk at the tensor rate and gets ~45-60), so
+// what NT buys is operand bytes per flop: 2 x 192 -> 112 flop/B, 3 x 128 -> 98 flop/B.  TMEM: NT*BNW accumulator columns
+// + NT*16 for the bias-gradient MMAs.
+template <int BNW, int NT>
 struct WgCfg {
-  static constexpr int A_BYTES = 2 * 64 * 128;            // two 64-wide n panels x 64 m rows
+  static constexpr int A_BYTES = NT * 2 * 64 * 128;       // per n-tile: two 64-wide n panels x 64 m rows
   static constexpr int B_BYTES = (BNW / 64) * 64 * 128;   // BNW/64 panels
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BNW == 128 ? 6 : 4;
-  static constexpr int TMEM_COLS = BNW == 256 ? 512 : 256;   // accumulator + 16 columns for the bias-gradient MMA
+  static constexpr int STAGES = NT > 1 ? 3 : (BNW == 128 ? 6 : 4);
+  static constexpr int ACC_COLS = NT * BNW + NT * 16;
+  static constexpr int TMEM_COLS = ACC_COLS <= 256 ? 256 : 512;
+  static_assert(ACC_COLS <= 512, "accumulators do not fit tensor memory");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + WG_STAGING_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int BNW>
+template <int BNW, int NT>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
                   float* __restrict__ dW, int ldw, int kb_per_split, float* __restrict__ dbias, int skip_lo, int skip_hi) {
-  using Cfg = WgCfg<BNW>;
+  using Cfg = WgCfg<BNW, NT>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int BIAS_COL = NT * BNW;                    // first TMEM column of the bias-gradient accumulators
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = base + STAGES * Cfg::STAGE_BYTES;
@@ -600,7 +609,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role
   const int num_k = (K + BNW - 1) / BNW;
-  const int n_blk = blockIdx.x / num_k, k_blk = blockIdx.x % num_k;
+  const int n_blk = blockIdx.x / num_k, k_blk = blockIdx.x % num_k;      // n_blk counts (NT*128)-row blocks
   const int kblocks_total = (M + BK - 1) / BK;
   const int kb0 = blockIdx.y * kb_per_split;
   const int kb1 = min(kblocks_total, kb0 + kb_per_split);
@@ -639,7 +648,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         mbar_wait(empty_bar(stage), phase ^ 1);
         mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
 #pragma unroll
-        for (int p = 0; p < 2; ++p) tma_load_2d(smem_a(stage) + p * 8192, &tmY, full_bar(stage), n_blk * 128 + p * 64, m0);
+        for (int p = 0; p < 2 * NT; ++p) tma_load_2d(smem_a(stage) + p * 8192, &tmY, full_bar(stage), n_blk * 128 * NT + p * 64, m0);
 #pragma unroll
         for (int p = 0; p < BNW / 64; ++p) tma_load_2d(smem_b(stage) + p * 8192, &tmX, full_bar(stage), k_blk * BNW + p * 64, m0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -655,12 +664,15 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t adesc = umma_desc_mnmajor(smem_a(stage) + k * 2048, 8192);
           const uint64_t bdesc = umma_desc_mnmajor(smem_b(stage) + k * 2048, 8192);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
-          if (do_bias)
-            umma_bf16(tmem_base + BNW, adesc, umma_desc_mnmajor(stg_base, 8192), umma_idesc_bf16(128, 16, 1, 1),
-                      (i | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const uint64_t adesc = umma_desc_mnmajor(smem_a(stage) + nt * 16384 + k * 2048, 8192);
+            umma_bf16(tmem_base + nt * BNW, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+            if (do_bias)
+              umma_bf16(tmem_base + BIAS_COL + nt * 16, adesc, umma_desc_mnmajor(stg_base, 8192), umma_idesc_bf16(128, 16, 1, 1),
+                        (i | k) != 0 ? 1u : 0u);
+          }
         }
         tc_commit(empty_bar(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -673,11 +685,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
     const uint32_t stg = stg_base + warp * 4096;
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
-    const int n_base = n_blk * 128 + quarter * 32;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+    for (int nt = 0; nt < NT; ++nt) {
+    const int n_base = (n_blk * NT + nt) * 128 + quarter * 32;
+    if (n_base - quarter * 32 >= N) break;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + nt * BNW;
     if (do_bias && grp == 0) {
-      uint32_t r[32];
-      tmem_ld32(taddr + BNW, r);
+      uint32_t r[16];
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + BIAS_COL + nt * 16, r);
       tc_wait_ld();
       const int n = n_base + lane;
       if (n < N && !(n >= skip_lo && n < skip_hi)) atomicAdd(dbias + n, __uint_as_float(r[0]));
@@ -708,6 +723,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
         }
       }
       __syncwarp();
+    }
     }
   }
   tc_fence_before();
@@ -840,16 +856,16 @@ static int dispatch_bn2(int bn, const CUtensorMap& tA, const CUtensorMap& tB, in
   }
 }
 
-template <int BNW>
+template <int BNW, int NT>
 static int launch_wgrad(const CUtensorMap& tY, const CUtensorMap& tX, int M, int N, int K, float* dW, int ldw, float* dbias,
                         int skip_lo, int skip_hi, cudaStream_t s) {
-  using Cfg = WgCfg<BNW>;
+  using Cfg = WgCfg<BNW, NT>;
   static bool attr_set = false;
   if (!attr_set) {
-    MOFO_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MOFO_CUDA(cudaFuncSetAttribute((gemm_wgrad_kernel<BNW, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((N + 127) / 128) * ((K + BNW - 1) / BNW);
+  const int tiles = ((N + 128 * NT - 1) / (128 * NT)) * ((K + BNW - 1) / BNW);
   const int kblocks = (M + BK - 1) / BK;
   int splits = sm_count() / tiles;
   if (splits < 1) splits = 1;
@@ -857,7 +873,7 @@ static int launch_wgrad(const CUtensorMap& tY, const CUtensorMap& tX, int M, int
   const int kb_per_split = (kblocks + splits - 1) / splits;
   splits = (kblocks + kb_per_split - 1) / kb_per_split;
   dim3 grid(tiles, splits);
-  MOFO_CUDA(launch_pdl(gemm_wgrad_kernel<BNW>, grid, dim3(WG_THREADS), Cfg::SMEM_BYTES, s, tY, tX, M, N, K, dW, ldw, kb_per_split,
+  MOFO_CUDA(launch_pdl((gemm_wgrad_kernel<BNW, NT>), grid, dim3(WG_THREADS), Cfg::SMEM_BYTES, s, tY, tX, M, N, K, dW, ldw, kb_per_split,
                        dbias, skip_lo, skip_hi));
   return MOFO_OK;
 }
@@ -931,9 +947,15 @@ int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, i
   rc = get_tmap(&tX, X, M, K, ldx, 64);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (K % 256 == 0) return launch_wgrad<256>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
-  if (K % 192 == 0) return launch_wgrad<192>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
-  return launch_wgrad<128>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
+  // Default: one n-tile x 256 / 192 / 128.  The multi-accumulator tiles (MOFO_WGRAD_NT=2 or 3: 2 n-tiles x 192, 3 x 128) cut
+  // the operand bytes per flop by 25-30 % but measured NO faster on B200 (decoder fc1 62.2 vs 62.9 us, encoder fc1 30.4 vs
+  // 27.5 us, step 13.22 vs 13.13 ms): wgrad is not limited by L2 -> SM operand bytes.  Kept opt-in for experiments.
+  static const int max_nt = [] { const char* e = getenv("MOFO_WGRAD_NT"); return e ? atoi(e) : 1; }();
+  if (max_nt >= 2 && N % 256 == 0 && K % 192 == 0) return launch_wgrad<192, 2>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
+  if (max_nt >= 3 && N % 384 == 0 && K % 128 == 0) return launch_wgrad<128, 3>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
+  if (K % 256 == 0) return launch_wgrad<256, 1>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
+  if (K % 192 == 0) return launch_wgrad<192, 1>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
+  return launch_wgrad<128, 1>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
 }
 
 }  // extern "C"

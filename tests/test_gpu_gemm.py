@@ -87,8 +87,12 @@ def test_gemm_tn_strided_views(lib):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (5120, 768, 1536), (1000, 384, 192), (6272, 1536, 384),
-                                   (5120, 2304, 768), (333, 64, 128), (4096, 384, 1536), (64, 1536, 384)])
+                                   (5120, 2304, 768), (333, 64, 128), (4096, 384, 1536), (64, 1536, 384),
+                                   (6272, 1152, 384), (1000, 384, 384), (5120, 3072, 768), (777, 768, 3072), (300, 256, 192),
+                                   (2000, 1536, 1536), (500, 1152, 128)])
 def test_gemm_wgrad(lib, M, N, K):
+    """Covers every tile shape of mofo_gemm_wgrad: 2 n-tiles x 192 (N % 256 == 0, K % 192 == 0), 3 n-tiles x 128
+    (N % 384 == 0), and the single-accumulator 256 / 192 / 128 tiles."""
     torch.manual_seed(M + N + K)
     dY = torch.randn(M, N, device="cuda").bfloat16(); X = torch.randn(M, K, device="cuda").bfloat16()
     dW = torch.zeros(N, K, device="cuda")
