@@ -260,9 +260,28 @@ def run_ours(args):
     runner._ensure_device(dev)
     arena = runner.grad_arena()
 
+    # the mask of step i+1 is sampled on a side stream while step i runs (the reference's DataLoader workers likewise
+    # prepare masks ahead of the step that consumes them); every step's mask kernel is inside the timed region
+    mask_stream = torch.cuda.Stream(device=dev)
+    ahead = {}
+
+    def sample_masks(i):
+        _, bb, words = pool[i % POOL]                      # static inputs: nothing on the main stream to wait for
+        with torch.cuda.stream(mask_stream):
+            out = gen.generate_batch(bb, words)
+            ev = torch.cuda.Event()
+            ev.record(mask_stream)
+        return out, ev
+
     def device_step(i):
-        vid, bb, words = pool[i % POOL]
-        mask, vis_idx, msk_idx, used = gen.generate_batch(bb, words)
+        vid = pool[i % POOL][0]
+        (mask, vis_idx, msk_idx, used), ev = ahead.pop(i) if i in ahead else sample_masks(i)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev)
+        for t in (vis_idx, msk_idx):
+            t.record_stream(cur)
+        ahead.clear()
+        ahead[i + 1] = sample_masks(i + 1)                 # enqueued before step i, runs beside it
         loss, _ = eng.fused_step(model, opt, scaler, sync, vid, vis_idx, msk_idx, True, 0)
         return loss
 

@@ -221,17 +221,20 @@ int mofo_clip_preprocess(const uint8_t* frames, int B, int T, int H, int W, cons
  * per-step fp32->bf16 operand casts.  params / grads / exp_avg / exp_avg_sq are f32 arenas with identical layout.
  * segs  : int64 [n_seg][6] = {arena offset, rows, cols, param-group index, w16 offset or -1, wt16 offset or -1}
  *         (offsets into w16 in elements: bf16 copy W[rows,cols] and transposed copy W^T[cols,rows]).
- * tiles : int32 [n_tiles][2] = {segment, tile}: a tile is a 32x32 block when the segment has a transposed copy,
- *         else 1024 consecutive elements.
+ * tiles : int32 [n_tiles][2] = {segment, tile}: a tile is a 32 x 128 block (row-major tile order, ceil(cols/128) tiles
+ *         per tile row) when the segment has a transposed copy, else 4096 consecutive elements.
  * hyper : f32 device array {beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), 0, 0, 0, lr_0, wd_0, lr_1, wd_1, ...}.
  * clip_coef (may be NULL): device scalar multiplied into every gradient (gradient clipping, utils.py:358).
  * loss_guard (may be NULL): device scalar; when it is NaN/Inf the whole update is skipped (the engine then exits as
  * engine_for_pretraining.py:418-420 does, with parameters untouched).
+ * sq_norm_out (may be NULL): device scalar; += sum of squares of the (unclipped) gradients of the tiles processed - the
+ * gradient norm of utils.py:376-388 without a second pass over the gradient arena (only usable when no clip coefficient
+ * derived from that norm is needed first).
  * Update rule = torch AdamW: p *= 1-lr*wd; m = lerp(m,g,1-b1); v = b2 v + (1-b2) g^2; p -= lr/bc1 * m/(sqrt(v)/sqrt(bc2)+eps).
  */
 int mofo_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, mofo_bf16* w16,
                     const int64_t* segs, const int32_t* tiles, int n_tiles, const float* hyper, const float* clip_coef,
-                    const float* loss_guard, void* stream);
+                    const float* loss_guard, float* sq_norm_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,7 @@ SIGNATURES = {
     "mofo_sq_norm_f32": ([_P, _L, _P, _P], C.c_int),
     "mofo_normalize_u8": ([_P, _I, _I, _I, _P, _P], C.c_int),
     "mofo_clip_preprocess": ([_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P], C.c_int),
-    "mofo_adamw_step": ([_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P], C.c_int),
+    "mofo_adamw_step": ([_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P], C.c_int),
 }
 
 
@@ -287,10 +287,14 @@ def sq_norm_f32(x, out):
     _check(load().mofo_sq_norm_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "mofo_sq_norm_f32")
 
 
-def adamw_step(params, grads, exp_avg, exp_avg_sq, w16, segs, tiles, hyper, clip_coef=None, loss_guard=None):
+ADAMW_TILE = (32, 128)      # rows x cols of a 2-D tile of mofo_adamw_step
+ADAMW_RUN = 4096            # elements of a 1-D tile
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, w16, segs, tiles, hyper, clip_coef=None, loss_guard=None, sq_norm_out=None):
     _check(load().mofo_adamw_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(w16), _ptr(segs),
-                                  _ptr(tiles), tiles.shape[0], _ptr(hyper), _ptr(clip_coef), _ptr(loss_guard), _stream()),
-           "mofo_adamw_step")
+                                  _ptr(tiles), tiles.shape[0], _ptr(hyper), _ptr(clip_coef), _ptr(loss_guard),
+                                  _ptr(sq_norm_out), _stream()), "mofo_adamw_step")
 
 
 def clip_preprocess(frames_u8, crops, boxes_in, out_size, clip_out, boxes_out):

@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
   pdl_trigger();
   __shared__ __align__(16) float lab[1536];
   __shared__ float sh[4];
+  __shared__ float sh3[2][4][3];
   const int row = blockIdx.x;
   const int b = row / n_msk;
   const int hw = size >> 4;
@@ -560,6 +561,13 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
   const int t = tok / (hw * hw), h = (tok / hw) % hw, w = tok % hw;
   const int tid = threadIdx.x;
   const int p0 = tid >> 6, p1 = (tid >> 2) & 15, q = tid & 3;
+  // the prediction row (192 x 16 B, 1.5 vectors per thread) is fetched up front, together with the pixels, so that the
+  // tube costs ONE global-latency phase instead of two
+  uint4 pv_pre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+  if (pred) {
+    pv_pre[0] = __ldg(reinterpret_cast<const uint4*>(pred + static_cast<size_t>(row) * 1536 + tid * 8));
+    if (tid < 64) pv_pre[1] = __ldg(reinterpret_cast<const uint4*>(pred + static_cast<size_t>(row) * 1536 + (tid + 128) * 8));
+  }
   const float mean_c[3] = {0.485f, 0.456f, 0.406f};     // IMAGENET_DEFAULT_MEAN  (:260)
   const float std_c[3] = {0.229f, 0.224f, 0.225f};      // IMAGENET_DEFAULT_STD   (:261)
   float xv[3][4];
@@ -575,26 +583,45 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
     xv[c][3] = __fadd_rn(__fmul_rn(v.w, std_c[c]), mean_c[c]);
   }
   const int pbase = p0 * 256 + p1 * 16 + q * 4;         // pixel index p = p0*256 + p1*16 + p2  (:268)
+  // the three channels' statistics go through the block reductions together (2 + 2 barriers per tube instead of 12);
+  // per channel the summation tree is the one block_sum_128 uses
+  float mu[3] = {0.f, 0.f, 0.f}, sd[3] = {1.f, 1.f, 1.f};
+  if (normalize_target) {
+    float s3[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s3[c] = warp_sum((xv[c][0] + xv[c][1]) + (xv[c][2] + xv[c][3]));
+    if ((tid & 31) == 0) { sh3[0][tid >> 5][0] = s3[0]; sh3[0][tid >> 5][1] = s3[1]; sh3[0][tid >> 5][2] = s3[2]; }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      mu[c] = ((sh3[0][0][c] + sh3[0][1][c]) + (sh3[0][2][c] + sh3[0][3][c])) * (1.0f / 512.0f);   // mean over the 512 pixels (:269)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d0 = xv[c][0] - mu[c], d1 = xv[c][1] - mu[c], d2 = xv[c][2] - mu[c], d3 = xv[c][3] - mu[c];
+      s3[c] = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+    }
+    if ((tid & 31) == 0) { sh3[1][tid >> 5][0] = s3[0]; sh3[1][tid >> 5][1] = s3[1]; sh3[1][tid >> 5][2] = s3[2]; }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float var = ((sh3[1][0][c] + sh3[1][1][c]) + (sh3[1][2][c] + sh3[1][3][c])) * (1.0f / 511.0f);   // unbiased (:270)
+      sd[c] = sqrtf(var) + 1e-6f;
+    }
+  }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float mu = 0.f, sd = 1.f;
-    if (normalize_target) {
-      float s = (xv[c][0] + xv[c][1]) + (xv[c][2] + xv[c][3]);
-      mu = block_sum_128(s, sh) * (1.0f / 512.0f);                       // mean over the 512 pixels  (:269)
-      float d0 = xv[c][0] - mu, d1 = xv[c][1] - mu, d2 = xv[c][2] - mu, d3 = xv[c][3] - mu;
-      float qs = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-      float var = block_sum_128(qs, sh) * (1.0f / 511.0f);               // unbiased  (:270)
-      sd = sqrtf(var) + 1e-6f;
-    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float v = normalize_target ? __fdiv_rn(xv[c][e] - mu, sd) : xv[c][e];
+      float v = normalize_target ? __fdiv_rn(xv[c][e] - mu[c], sd[c]) : xv[c][e];
       lab[(pbase + e) * 3 + c] = v;                                      // feature f = p*3 + c  (:276)
     }
   }
   __syncthreads();
   float acc = 0.f;
-  for (int v = tid; v < 192; v += 128) {
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int v = tid + it * 128;
+    if (v >= 192) break;
     const size_t off = static_cast<size_t>(row) * 1536 + v * 8;
     float l[8];
     *reinterpret_cast<float4*>(l) = *reinterpret_cast<const float4*>(lab + v * 8);
@@ -604,7 +631,7 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
       *reinterpret_cast<float4*>(labels_out + off + 4) = *reinterpret_cast<float4*>(l + 4);
     }
     if (pred) {
-      uint4 pv = __ldg(reinterpret_cast<const uint4*>(pred + off));
+      const uint4 pv = pv_pre[it];
       float p[8] = {bf16_lo(pv.x), bf16_hi(pv.x), bf16_lo(pv.y), bf16_hi(pv.y),
                     bf16_lo(pv.z), bf16_hi(pv.z), bf16_lo(pv.w), bf16_hi(pv.w)};
       float d[8];

@@ -113,7 +113,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 rows, cols, w_off, wt_off = 1, p.numel(), -1, -1
             seg = len(segs)
             segs.append([off, rows, cols, group_of[id(p)], w_off, wt_off])
-            ntile = ((rows + 31) // 32) * ((cols + 31) // 32) if wt_off >= 0 else (rows * cols + 1023) // 1024
+            tr, tc = _lib.ADAMW_TILE
+            ntile = ((rows + tr - 1) // tr) * ((cols + tc - 1) // tc) if wt_off >= 0 else (rows * cols + _lib.ADAMW_RUN - 1) // _lib.ADAMW_RUN
             tiles.extend([seg, t] for t in range(ntile))
         self.w16 = torch.zeros(max(w16_elems, 8), dtype=torch.bfloat16, device=dev)
         self.segs = torch.tensor(segs, dtype=torch.int64, device=dev)
@@ -178,11 +179,10 @@ class FusedAdamW(torch.optim.Optimizer):
         ends = self.stage_tile_end
 
         def on_stage(k, lo, hi):
-            _lib.sq_norm_f32(garena[lo:hi], acc)
             t0 = ends[k - 1] if k > 0 else 0
             if ends[k] > t0:
                 _lib.adamw_step(self.p_arena, garena, self.m_arena, self.v_arena, self.w16, self.segs, self.tiles[t0:ends[k]],
-                                self.hyper, None, loss_guard)
+                                self.hyper, None, loss_guard, sq_norm_out=acc)
         return on_stage, acc
 
     def _upload_hyper(self):
@@ -199,7 +199,7 @@ class FusedAdamW(torch.optim.Optimizer):
 
     # ---- torch.optim.Optimizer API ------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, closure=None, clip_coef=None, loss_guard=None):
+    def step(self, closure=None, clip_coef=None, loss_guard=None, sq_norm_out=None):
         if self._attached is None:
             raise RuntimeError("FusedAdamW.step() before attach(model)")
         loss = closure() if closure is not None else None
@@ -212,7 +212,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 p.grad = gv
         self._upload_hyper()
         _lib.adamw_step(self.p_arena, garena, self.m_arena, self.v_arena, self.w16, self.segs, self.tiles, self.hyper,
-                        clip_coef, loss_guard)
+                        clip_coef, loss_guard, sq_norm_out=sq_norm_out)
         return loss
 
     def zero_grad(self, set_to_none: bool = True):

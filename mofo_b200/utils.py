@@ -172,6 +172,12 @@ class NativeScalerWithGradNormCount:
             loss.backward(create_graph=create_graph)
         if not update_grad:
             return None
+        clip = clip_grad is not None and clip_grad > 0
+        if arena is not None and not clip and getattr(optimizer, "fused_mofo", False):
+            # no clip coefficient to derive first: the optimizer kernel accumulates sum(g^2) while it reads the gradients
+            acc = torch.zeros(1, dtype=torch.float32, device=arena.device)
+            optimizer.step(loss_guard=loss.detach().reshape(-1)[:1] if loss_guard else None, sq_norm_out=acc)
+            return acc.sqrt()[0]
         if arena is not None:
             acc = torch.zeros(1, dtype=torch.float32, device=arena.device)
             _lib.sq_norm_f32(arena, acc)

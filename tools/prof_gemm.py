@@ -27,8 +27,13 @@ We2 = t(D, 4 * D); be2 = t(D, dt=torch.float32); xe = t(Me, D, dt=torch.float32)
 cases.append(("enc_fc2_resid", lambda: _lib.gemm_tn(ae, We2, _lib.EPI_BIAS_RESID_F32, xeo, bias=be2, resid=xe), 2.0 * Me * 4 * D * D))
 dW1 = torch.zeros(4 * Dd, Dd, device=dev); db1 = torch.zeros(4 * Dd, device=dev)
 cases.append(("dec_fc1_wgrad", lambda: _lib.gemm_wgrad(du, h2, dW1, dbias=db1), 2.0 * Md * 4 * Dd * Dd))
+cases.append(("dec_fc1_wgrad_nobias", lambda: _lib.gemm_wgrad(du, h2, dW1), 2.0 * Md * 4 * Dd * Dd))
+dW2 = torch.zeros(Dd, 4 * Dd, device=dev); db2 = torch.zeros(Dd, device=dev)
+cases.append(("dec_fc2_wgrad", lambda: _lib.gemm_wgrad(dx, a, dW2, dbias=db2), 2.0 * Md * 4 * Dd * Dd))
+cases.append(("dec_fc2_wgrad_nobias", lambda: _lib.gemm_wgrad(dx, a, dW2), 2.0 * Md * 4 * Dd * Dd))
 dWe1 = torch.zeros(4 * D, D, device=dev); dbe1 = torch.zeros(4 * D, device=dev)
 cases.append(("enc_fc1_wgrad", lambda: _lib.gemm_wgrad(ue, he, dWe1, dbias=dbe1), 2.0 * Me * 4 * D * D))
+cases.append(("enc_fc1_wgrad_nobias", lambda: _lib.gemm_wgrad(ue, he, dWe1), 2.0 * Me * 4 * D * D))
 x32 = t(Md, Dd, dt=torch.float32); g = torch.ones(Dd, device=dev); bb = torch.zeros(Dd, device=dev)
 y = torch.empty(Md, Dd, dtype=torch.bfloat16, device=dev); mean = torch.empty(Md, device=dev); rstd = torch.empty(Md, device=dev)
 cases.append(("dec_ln_fwd", lambda: _lib.layernorm_fwd(x32, g, bb, y, mean, rstd, Md, Dd), 0))
