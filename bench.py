@@ -36,6 +36,7 @@ def parse():
                     help="finetune = BASELINE configs[4]: vit_base_patch16_224 classifier fwd+bwd on all 1568 tokens, batch 8 (not the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline-leg", action="store_true", help="profiling runs: skip the per-launch-event leg (roofline = null)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall budget of the oracle-port fallback of the reference arm")
     ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the CPU reference arm (fixed, independent of N)")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference's own eager step on the same GPU(s)")
@@ -344,18 +345,20 @@ def run_ours(args):
     # class (kept out of the region above because ~270 extra event records per step perturb the step time)
     e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
     barrier()
-    model.use_cuda_graph = False          # per-launch events need individually launched kernels
-    device_step(0); device_step(1)
-    barrier()
-    with _lib.timing("mofo_gemm_tn") as ktimer:
-        e2.record()
-        for i in range(args.steps):
-            device_step(args.warmup + args.steps + i)
-        e3.record()
+    n_gemm, gemm_ms, gemm_flops, ms_instrumented = 0, 0.0, 0.0, 1.0
+    if not args.no_roofline_leg:
+        model.use_cuda_graph = False          # per-launch events need individually launched kernels
+        device_step(0); device_step(1)
         barrier()
-    n_gemm, gemm_ms, gemm_flops = ktimer.summary()
-    ms_instrumented = e2.elapsed_time(e3)
-    model.use_cuda_graph = True
+        with _lib.timing("mofo_gemm_tn") as ktimer:
+            e2.record()
+            for i in range(args.steps):
+                device_step(args.warmup + args.steps + i)
+            e3.record()
+            barrier()
+        n_gemm, gemm_ms, gemm_flops = ktimer.summary()
+        ms_instrumented = e2.elapsed_time(e3)
+        model.use_cuda_graph = True
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the public engine API with HOST (pinned) batches; H2D + loss D2H inside the timed region ----------
@@ -424,15 +427,21 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         vid_bytes = B * 3 * 16 * 224 * 224 * 4
-        e2e = {"value": B * world * args.steps / dt.item(), "unit": "clips/s",
-               "h2d_bytes_per_step": vid_bytes + B * 1568 * 8, "d2h_bytes_per_step": 8,
-               "ms_per_step": 1e3 * dt.item() / args.steps, "h2d_pinned_gbps": h2d_gbps,
-               "h2d_ms_per_step_at_that_rate": vid_bytes / h2d_gbps / 1e6,
-               "api": "mofo_b200.engine_for_pretraining.train_one_epoch_BB, pinned fp32 clips + f64 masks per step "
-                      "(H2D of batch i+1 overlaps step i on a copy stream; loss + grad norm of every step copied to "
-                      "pinned host memory and read by the host while the next step runs)",
-               "uint8_input": {"value": B * world * args.steps / dt_u8, "unit": "clips/s", "h2d_bytes_per_step": vid_bytes // 4 + B * 1568 * 8,
-                               "note": "same engine call fed raw uint8 clips (1 B/sample); normalisation on the GPU (mofo_normalize_u8)"}}
+        # headline e2e = the engine fed what a decoder hands over: uint8 clips (1 B / sample; ToTorchFormatTensor +
+        # GroupNormalize run on the GPU, mofo_normalize_u8); the same call fed pre-normalised fp32 clips - what the
+        # reference's CPU DataLoader workers produce - is reported beside it
+        fp32_rate = B * world * args.steps / dt.item()
+        e2e = {"value": B * world * args.steps / dt_u8, "unit": "clips/s",
+               "h2d_bytes_per_step": vid_bytes // 4 + B * 1568 * 8, "d2h_bytes_per_step": 12,
+               "ms_per_step": 1e3 * dt_u8 / args.steps, "h2d_pinned_gbps": h2d_gbps,
+               "input": "pinned host uint8 clips [B,3,16,224,224] + f64 masks [B,1568] per step",
+               "api": "mofo_b200.engine_for_pretraining.train_one_epoch_BB (H2D of batch i+1 overlaps step i on a copy stream; loss, "
+                      "grad norm and the mask-row check of every step are copied to pinned host memory and read by the host while "
+                      "the next step runs)",
+               "fp32_input": {"value": fp32_rate, "unit": "clips/s", "h2d_bytes_per_step": vid_bytes + B * 1568 * 8,
+                              "ms_per_step": 1e3 * dt.item() / args.steps,
+                              "h2d_ms_per_step_at_the_measured_rate": vid_bytes / h2d_gbps / 1e6,
+                              "note": "same engine call fed pre-normalised fp32 clips (4 B / sample), as the reference's DataLoader yields them"}}
 
     # ---- the reference's own eager step on the same GPU(s) (SURVEY §8d "GPU reference baseline"): unmodified modules from
     # baseline/_ref through train_one_epoch_BB, fp16 autocast + GradScaler as authored and under bf16 autocast; DDP
@@ -481,16 +490,19 @@ def run_ours(args):
                                    "emitting the bf16 W / W^T operand copies (SURVEY §8f-1)",
                       "launch": "fused step replayed as CUDA graphs (one per gradient-sync stage); roofline leg launches kernels individually"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "final_loss": final_loss, "gpu_reference": gpu_ref, "dp_check": dp,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05, all fused-epilogue instances)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_tn2_kernel / gemm_tn_kernel (tcgen05 cta_group::2 and ::1, every fused-epilogue instance behind mofo_gemm_tn)",
                          "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": gemm_tflops / peaks["bf16_sustained"] if gemm_tflops else None,
-                         # dram__bytes_read+write of ONE launch from `ncu --set full` (profiles/r01_ncu_gemm_tn_final_full.txt):
-                         # decoder fc1-dgrad instance [50176x384, K=1536]: 155.3 MB read + 24.2 MB written (rest of the
-                         # 38.5 MB output still dirty in L2) vs 193.9 MB algorithmic -> no re-reads
-                         "traffic": 179.6e6, "traffic_instance": "gemm_tn_kernel<128,PLAIN_BF16> M=50176 N=384 K=1536 (algorithmic 193.9e6 B)",
-                         "launches_timed": n_gemm, "kernel_ms_per_step": gemm_ms / args.steps,
-                         "share_of_step": gemm_ms / ms_instrumented, "instrumented_ms_per_step": ms_instrumented / args.steps,
-                         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"},
+                         "frac_of_burst_peak": gemm_tflops / peaks["bf16_burst"] if gemm_tflops else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the shipped kernel, `ncu --set full`
+                         # (profiles/r02_ncu_gemm_tn2_gelu_full.txt): decoder fc1 + GELU instance gemm_tn2_kernel<256,1>
+                         # [50176 x 1536, K = 384]: 40.1 MB read + 257.4 MB written vs 347.9 MB algorithmic (A 38.5 + W 1.2 +
+                         # two bf16 outputs 2 x 154.1; the tail of the outputs was still dirty in L2) -> no re-reads
+                         "traffic": 297.5e6, "traffic_instance": "gemm_tn2_kernel<256,BIAS_GELU_BF16> M=50176 N=1536 K=384 (algorithmic 347.9e6 B)",
+                         "launches_timed": n_gemm, "kernel_ms_per_step": gemm_ms / args.steps if n_gemm else None,
+                         "share_of_step": gemm_ms / ms_instrumented if n_gemm else None,
+                         "instrumented_ms_per_step": ms_instrumented / args.steps if n_gemm else None,
+                         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step); frac_of_burst_peak uses bf16_tflops"},
             "step_mfu": {"algorithmic_tflops_per_gpu": step_tflops, "frac_of_measured_sustained": step_tflops / peaks["bf16_sustained"] if step_tflops else None,
                          "frac_of_nominal_2250": step_tflops / 2250.0 if step_tflops else None, "gflop_per_clip": gflop}}
     if not args.no_cpu_baseline and world == 1:

@@ -541,7 +541,10 @@ __device__ __forceinline__ float block_sum_128(float v, float* sh) {  // 128 thr
   return (sh[0] + sh[1]) + (sh[2] + sh[3]);
 }
 
-// one CTA (128 threads) per masked tube.  thread -> (p0, p1, quad of 4 px) for each of the 3 channels.
+// one CTA (128 threads) per masked tube.  thread -> (p0, p1, quad of 4 px) for each of the 3 channels.  The 12 label
+// values of a thread (4 pixels x 3 channels) are CONTIGUOUS in the reference's feature order f = p*3 + c, so the thread
+// reads its 24 bytes of the prediction row and writes its 24 bytes of dpred directly (a warp covers 768 contiguous
+// bytes): no shared-memory interleave, two block barriers per tube (the mean and the variance of the three channels).
 __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict__ video,
                                                          const int32_t* __restrict__ msk_idx,
                                                          const __nv_bfloat16* __restrict__ pred, int n_msk, int frames,
@@ -551,7 +554,6 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
                                                          float* __restrict__ labels_out) {
   pdl_wait();
   pdl_trigger();
-  __shared__ __align__(16) float lab[1536];
   __shared__ float sh[4];
   __shared__ float sh3[2][4][3];
   const int row = blockIdx.x;
@@ -561,12 +563,12 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
   const int t = tok / (hw * hw), h = (tok / hw) % hw, w = tok % hw;
   const int tid = threadIdx.x;
   const int p0 = tid >> 6, p1 = (tid >> 2) & 15, q = tid & 3;
-  // the prediction row (192 x 16 B, 1.5 vectors per thread) is fetched up front, together with the pixels, so that the
-  // tube costs ONE global-latency phase instead of two
-  uint4 pv_pre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-  if (pred) {
-    pv_pre[0] = __ldg(reinterpret_cast<const uint4*>(pred + static_cast<size_t>(row) * 1536 + tid * 8));
-    if (tid < 64) pv_pre[1] = __ldg(reinterpret_cast<const uint4*>(pred + static_cast<size_t>(row) * 1536 + (tid + 128) * 8));
+  const int pbase = p0 * 256 + p1 * 16 + q * 4;         // pixel index p = p0*256 + p1*16 + p2  (:268)
+  const size_t foff = static_cast<size_t>(row) * 1536 + static_cast<size_t>(pbase) * 3;   // first of this thread's 12 features
+  uint2 pv[3] = {make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
+  if (pred) {                                           // fetched together with the pixels: one global-latency phase
+#pragma unroll
+    for (int j = 0; j < 3; ++j) pv[j] = __ldg(reinterpret_cast<const uint2*>(pred + foff) + j);
   }
   const float mean_c[3] = {0.485f, 0.456f, 0.406f};     // IMAGENET_DEFAULT_MEAN  (:260)
   const float std_c[3] = {0.229f, 0.224f, 0.225f};      // IMAGENET_DEFAULT_STD   (:261)
@@ -582,9 +584,8 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
     xv[c][2] = __fadd_rn(__fmul_rn(v.z, std_c[c]), mean_c[c]);
     xv[c][3] = __fadd_rn(__fmul_rn(v.w, std_c[c]), mean_c[c]);
   }
-  const int pbase = p0 * 256 + p1 * 16 + q * 4;         // pixel index p = p0*256 + p1*16 + p2  (:268)
-  // the three channels' statistics go through the block reductions together (2 + 2 barriers per tube instead of 12);
-  // per channel the summation tree is the one block_sum_128 uses
+  // the three channels' statistics go through the block reductions together; per channel the summation tree is
+  // warp_sum, then (w0 + w1) + (w2 + w3)
   float mu[3] = {0.f, 0.f, 0.f}, sd[3] = {1.f, 1.f, 1.f};
   if (normalize_target) {
     float s3[3];
@@ -608,40 +609,34 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
       sd[c] = sqrtf(var) + 1e-6f;
     }
   }
+  float l[12];                                           // feature order: l[e*3 + c] = label of pixel pbase+e, channel c  (:276)
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
+  for (int e = 0; e < 4; ++e) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float v = normalize_target ? __fdiv_rn(xv[c][e] - mu[c], sd[c]) : xv[c][e];
-      lab[(pbase + e) * 3 + c] = v;                                      // feature f = p*3 + c  (:276)
-    }
+    for (int c = 0; c < 3; ++c) l[e * 3 + c] = normalize_target ? __fdiv_rn(xv[c][e] - mu[c], sd[c]) : xv[c][e];
   }
-  __syncthreads();
+  if (labels_out) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      reinterpret_cast<float4*>(labels_out + foff)[j] = make_float4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+  }
   float acc = 0.f;
+  if (pred) {
+    float d[12];
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int v = tid + it * 128;
-    if (v >= 192) break;
-    const size_t off = static_cast<size_t>(row) * 1536 + v * 8;
-    float l[8];
-    *reinterpret_cast<float4*>(l) = *reinterpret_cast<const float4*>(lab + v * 8);
-    *reinterpret_cast<float4*>(l + 4) = *reinterpret_cast<const float4*>(lab + v * 8 + 4);
-    if (labels_out) {
-      *reinterpret_cast<float4*>(labels_out + off) = *reinterpret_cast<float4*>(l);
-      *reinterpret_cast<float4*>(labels_out + off + 4) = *reinterpret_cast<float4*>(l + 4);
+    for (int j = 0; j < 3; ++j) {
+      d[4 * j + 0] = bf16_lo(pv[j].x) - l[4 * j + 0]; d[4 * j + 1] = bf16_hi(pv[j].x) - l[4 * j + 1];
+      d[4 * j + 2] = bf16_lo(pv[j].y) - l[4 * j + 2]; d[4 * j + 3] = bf16_hi(pv[j].y) - l[4 * j + 3];
     }
-    if (pred) {
-      const uint4 pv = pv_pre[it];
-      float p[8] = {bf16_lo(pv.x), bf16_hi(pv.x), bf16_lo(pv.y), bf16_hi(pv.y),
-                    bf16_lo(pv.z), bf16_hi(pv.z), bf16_lo(pv.w), bf16_hi(pv.w)};
-      float d[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { d[e] = p[e] - l[e]; acc += d[e] * d[e]; }
-      if (dpred) {
-        uint4 o;
-        o.x = pack_bf16(d[0] * gscale, d[1] * gscale); o.y = pack_bf16(d[2] * gscale, d[3] * gscale);
-        o.z = pack_bf16(d[4] * gscale, d[5] * gscale); o.w = pack_bf16(d[6] * gscale, d[7] * gscale);
-        *reinterpret_cast<uint4*>(dpred + off) = o;
+    for (int e = 0; e < 12; ++e) acc += d[e] * d[e];
+    if (dpred) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        uint2 o;
+        o.x = pack_bf16(d[4 * j + 0] * gscale, d[4 * j + 1] * gscale);
+        o.y = pack_bf16(d[4 * j + 2] * gscale, d[4 * j + 3] * gscale);
+        reinterpret_cast<uint2*>(dpred + foff)[j] = o;
       }
     }
   }
