@@ -283,7 +283,7 @@ def run_ours(args):
             t.record_stream(cur)
         ahead.clear()
         ahead[i + 1] = sample_masks(i + 1)                 # enqueued before step i, runs beside it
-        loss, _ = eng.fused_step(model, opt, scaler, sync, vid, vis_idx, msk_idx, True, 0)
+        loss, _ = eng.fused_step(model, opt, scaler, sync, vid, vis_idx, msk_idx, True, 0, return_sq=True)
         return loss
 
     def dp_check():

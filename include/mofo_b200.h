@@ -158,6 +158,10 @@ int mofo_decoder_assemble_fwd(const float* mask_token, const float* pos, const i
                               int n_msk, int Dd, float* x_full, void* stream);
 int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk, int Dd, float* dmask_token,
                               mofo_bf16* dvis, void* stream);
+/* mofo_zero_rows: zeroes the first n_zero rows of every group of group_rows rows of x_f32 / x_bf16 [groups*group_rows, D]
+ * (either may be NULL).  The head of the decoder sees only the masked rows (x[:, -N_mask:], modeling_pretrain.py:156), so
+ * the gradient entering the last decoder block is zero on each clip's visible rows. */
+int mofo_zero_rows(float* x_f32, mofo_bf16* x_bf16, int groups, int group_rows, int n_zero, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (6b) Token mean pooling of the finetuning classifier: VisionTransformer.forward_features ends with

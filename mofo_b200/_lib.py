@@ -34,6 +34,7 @@ SIGNATURES = {
     "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
     "mofo_decoder_assemble_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_decoder_assemble_bwd": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
+    "mofo_zero_rows": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
     "mofo_token_mean_fwd": ([_P, _I, _I, _I, _P, _P], C.c_int),
     "mofo_token_mean_bwd": ([_P, _I, _I, _I, _P, _P, _P], C.c_int),
     "mofo_target_mse": ([_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P], C.c_int),
@@ -245,6 +246,10 @@ def decoder_assemble_fwd(mask_token, pos, msk_idx, B, n_vis, n_msk, Dd, x_full):
 def decoder_assemble_bwd(dx_full, B, n_vis, n_msk, Dd, dmask_token, dvis):
     _check(load().mofo_decoder_assemble_bwd(_ptr(dx_full), B, n_vis, n_msk, Dd, _ptr(dmask_token), _ptr(dvis),
                                             _stream()), "mofo_decoder_assemble_bwd")
+
+
+def zero_rows(x_f32, x_bf16, groups, group_rows, n_zero, D):
+    _check(load().mofo_zero_rows(_ptr(x_f32), _ptr(x_bf16), groups, group_rows, n_zero, D, _stream()), "mofo_zero_rows")
 
 
 def token_mean_fwd(x, B, N, D, pooled):

@@ -468,6 +468,22 @@ __global__ void assemble_bwd_kernel(const float* __restrict__ dx_full, int n_vis
   }
 }
 
+// zero the first `nz` rows of every group of `group_rows` rows of an f32 and / or a bf16 [groups*group_rows, D] matrix
+__global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ f32, __nv_bfloat16* __restrict__ b16, int group_rows,
+                                                        int nz, int D, int64_t total4) {
+  pdl_wait();
+  pdl_trigger();
+  const int C4 = D >> 2;
+  const int64_t per_group = static_cast<int64_t>(nz) * C4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t g = i / per_group, r = i % per_group;
+    const int64_t dst = g * group_rows * C4 + r;
+    if (f32) reinterpret_cast<float4*>(f32)[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b16) reinterpret_cast<uint2*>(b16)[dst] = make_uint2(0u, 0u);
+  }
+}
+
 // =================================================================================================
 // (6b) token mean pooling (finetuning classifier)  — modeling_finetune.py:400-401  fc_norm(x.mean(1))
 // =================================================================================================
@@ -1005,6 +1021,18 @@ int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk,
   const size_t smem = static_cast<size_t>(ASM_RG) * (Dd >> 2) * sizeof(float4);
   MOFO_CUDA(launch_pdl(assemble_bwd_kernel, grid, dim3(cx, ASM_RG), smem, static_cast<cudaStream_t>(stream), dx_full, n_vis, n_msk, Dd,
                        rows_per_cta, dmask_token, reinterpret_cast<__nv_bfloat16*>(dvis)));
+  return MOFO_OK;
+}
+
+int mofo_zero_rows(float* x_f32, mofo_bf16* x_bf16, int groups, int group_rows, int n_zero, int D, void* stream) {
+  MOFO_CHECK_ARG(x_f32 || x_bf16, "zero_rows: null pointer");
+  MOFO_CHECK_ARG(groups > 0 && group_rows > 0 && n_zero >= 0 && n_zero <= group_rows && D > 0 && D % 4 == 0, "zero_rows: bad shape");
+  if (n_zero == 0) return MOFO_OK;
+  const int64_t total4 = static_cast<int64_t>(groups) * n_zero * (D >> 2);
+  int64_t blocks = (total4 + 255) / 256;
+  if (blocks > 8L * sm_count()) blocks = 8L * sm_count();
+  MOFO_CUDA(launch_pdl(zero_rows_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), x_f32,
+                       reinterpret_cast<__nv_bfloat16*>(x_bf16), group_rows, n_zero, D, total4));
   return MOFO_OK;
 }
 

@@ -89,6 +89,8 @@ class _CudaPrefetcher:
     def __init__(self, loader, device):
         self.loader, self.device = loader, device
         self.quiet = getattr(loader, "quiet", False)
+        self.raw = bool(getattr(loader, "mofo_raw_frames", False))      # batches of raw uint8 frames (transforms.RawClipLoader)
+        self.pre = getattr(loader, "preprocessor", None)
         self.slots = [{}, {}]           # per slot: field index -> device tensor
         self.consumed = [None, None]    # per slot: event after the consumer's work (compute stream)
 
@@ -113,6 +115,19 @@ class _CudaPrefetcher:
             return None
         if self.consumed[slot] is not None:
             stream.wait_event(self.consumed[slot])
+        if self.raw:
+            # raw uint8 frames [B,T,H,W,3] + boxes + crops: H2D of the frames, then crop / resize / normalise / box transform
+            # (mofo_clip_preprocess) on the copy stream, into this slot's clip buffer
+            frames = self._stage(slot, 0, videos, stream)
+            B, T = frames.shape[0], frames.shape[1]
+            clip = self.slots[slot].get("clip")
+            if clip is None or clip.shape[0] != B or clip.shape[2] != T:
+                clip = torch.empty(B, 3, T, self.pre.size, self.pre.size, dtype=torch.float32, device=self.device)
+                self.slots[slot]["clip"] = clip
+            with torch.cuda.stream(stream):
+                vid, boxes = self.pre(frames, bbox, mask, out=clip)
+                boxes.record_stream(torch.cuda.current_stream(self.device))
+            return vid, boxes, None
         return self._stage(slot, 0, videos, stream), bbox, self._stage(slot, 2, mask, stream)
 
     def __iter__(self):
@@ -133,7 +148,7 @@ class _CudaPrefetcher:
             i += 1
 
 
-def fused_step(core, optimizer, loss_scaler, sync, videos, vis_idx, msk_idx, normalize_target=True, max_norm=0):
+def fused_step(core, optimizer, loss_scaler, sync, videos, vis_idx, msk_idx, normalize_target=True, max_norm=0, return_sq=False):
     """One fused training step on device-resident inputs: forward + target/MSE + backward (CUDA graphs), the gradient
     exchange overlapped with backward, gradient norm and the optimizer update.  Returns (loss, grad_norm) as CUDA tensors
     without synchronising.  With ``FusedAdamW`` and no clipping the update runs stage by stage on the exchange stream
@@ -160,8 +175,10 @@ def fused_step(core, optimizer, loss_scaler, sync, videos, vis_idx, msk_idx, nor
     sync.finish()
     if not fused_opt:
         return loss, None
+    # return_sq: the SQUARED norm comes back when the scaler can provide it (no clipping) - the engine's pipelined path
+    # takes the root on the host instead of launching a one-element sqrt kernel every step
     grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=None, arena=arena, loss_guard=True,
-                            staged_sq_norm=acc)
+                            staged_sq_norm=acc, return_sq=return_sq and not clip)
     return loss, grad_norm
 
 
@@ -211,10 +228,10 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
             log_writer.set_step()
 
     def flush(p):
-        ev, pin, rest = p
+        ev, pin, rest, squared = p
         ev.synchronize()
         core.check_mask_rows(int(pin[2]))        # the reference raises on that step (x[~mask].reshape, modeling_pretrain.py:90)
-        record(float(pin[0]), float(pin[1]), *rest)
+        record(float(pin[0]), math.sqrt(max(float(pin[1]), 0.0)) if squared else float(pin[1]), *rest)
 
     def group_stats():
         min_lr, max_lr = 10., 0.
@@ -255,7 +272,9 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
                 _, vis_idx, msk_idx = masks_from_bbox(bbox, videos.device, grid, *gpu_mask_ratios)
             else:
                 vis_idx, msk_idx = core.indices_from_mask(bool_masked_pos)
-            loss, grad_norm = fused_step(core, optimizer, loss_scaler, sync, videos, vis_idx, msk_idx, normlize_target, max_norm)
+            sq = pipelined and not (max_norm is not None and max_norm > 0)
+            loss, grad_norm = fused_step(core, optimizer, loss_scaler, sync, videos, vis_idx, msk_idx, normlize_target, max_norm,
+                                         return_sq=sq)
             if getattr(optimizer, "fused_mofo", False):
                 # the fused optimizer skips the update on the device when the loss is not finite, so the whole step
                 # (incl. the parameter update) is enqueued before the single host read of the loss
@@ -266,7 +285,7 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
                     if core._bad_rows is not None:
                         pinned[slot][2:3].copy_(core._bad_rows, non_blocking=True)
                     events[slot].record()
-                    mine = (events[slot], pinned[slot], (loss_scaler.state_dict()["scale"],) + group_stats())
+                    mine = (events[slot], pinned[slot], (loss_scaler.state_dict()["scale"],) + group_stats(), sq)
                     if pending is not None:
                         flush(pending)              # step i-1's loss / grad norm: the device is busy with step i
                     pending = mine

@@ -62,7 +62,10 @@ class TubeMaskingGenerator_BB:
         rng_words: uint32 [B,W] raw MT19937 words per clip (numpy array or CUDA int32/uint32 tensor).
         Returns (mask uint8 [B,N], vis_idx int32 [B,N_vis], msk_idx int32 [B,N_mask], words_used int32 [B]) on device."""
         dev = torch.device(self.device)
-        bb_t = torch.as_tensor(np.asarray(bb.cpu() if isinstance(bb, torch.Tensor) else bb, dtype=np.float64))
+        if isinstance(bb, torch.Tensor) and bb.is_cuda:            # already on the device: no host round trip
+            bb_t = bb.to(torch.float64)
+        else:
+            bb_t = torch.as_tensor(np.asarray(bb.cpu() if isinstance(bb, torch.Tensor) else bb, dtype=np.float64))
         if bb_t.dim() == 3:
             bb_t = bb_t[:, 0, :]
         bb_t = bb_t.contiguous().to(dev, non_blocking=True)

@@ -478,7 +478,7 @@ class _Runner:
         # decoder.norm on the masked rows; visible rows receive zero gradient from the head
         dxA = self.buf("bwd.dec.dxA", (B * N, Dd), f32); dxA16 = self.buf("bwd.dec.dxA16", (B * N, Dd), bf)
         dxB = self.buf("bwd.dec.dxB", (B * N, Dd), f32); dxB16 = self.buf("bwd.dec.dxB16", (B * N, Dd), bf)
-        dxA.zero_(); dxA16.zero_()
+        _lib.zero_rows(dxA, dxA16, B, N, Nv, Dd)          # visible rows: no gradient from the head (masked rows: LN-bwd below)
         _lib.layernorm_bwd(dhd, self.x_dec_out, m.decoder.norm.weight, self.buf("dec.mean", (B * Nm,), f32),
                            self.buf("dec.rstd", (B * Nm,), f32), None, B * Nm, Dd, dxA, dxA16, g["decoder.norm.weight"],
                            g["decoder.norm.bias"], group_rows=Nm, in_group_rows=N, in_row_offset=Nv)

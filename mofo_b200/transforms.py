@@ -89,3 +89,24 @@ class ClipPreprocessor:
         boxes_out = torch.empty(B, T, 4, dtype=torch.float64, device=dev)
         _lib.clip_preprocess(frames_d, crops_t.to(dev, non_blocking=True), boxes_d, self.size, out, boxes_out)
         return out, boxes_out
+
+
+class RawClipLoader:
+    """Marks a loader of RAW batches ``(frames_u8 [B,T,H,W,3] (pinned host), boxes [B,T,4], crops int [B,4] | None)`` for
+    ``train_one_epoch_BB``: the engine's prefetcher copies the uint8 frames to the GPU and runs ``mofo_clip_preprocess`` on
+    its copy stream while the previous step computes, then generates the masks from the transformed boxes on the GPU
+    (``mofo_gpu_masks``).  Nothing but uint8 frames, boxes and four crop integers per clip crosses PCIe."""
+
+    mofo_gpu_masks = True
+    mofo_raw_frames = True
+
+    def __init__(self, loader, preprocessor: ClipPreprocessor, mask_ratios=(0.9, 0.75)):
+        self.loader, self.preprocessor = loader, preprocessor
+        self.mofo_mask_ratios = mask_ratios
+        self.quiet = getattr(loader, "quiet", False)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        return iter(self.loader)

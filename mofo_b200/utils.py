@@ -161,13 +161,13 @@ class NativeScalerWithGradNormCount:
         self._scale = 1.0
 
     def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True,
-                 arena=None, loss_guard=False, staged_sq_norm=None):
+                 arena=None, loss_guard=False, staged_sq_norm=None, return_sq=False):
         """``arena``: the model's flat gradient arena when the gradients were produced by the fused step (the engine
         passes it); otherwise ``loss.backward()`` runs autograd through the model's kernel backward.
         ``staged_sq_norm``: the squared-norm accumulator of ``FusedAdamW.begin_staged`` when the update already ran stage
         by stage behind the gradient exchange (mofo_b200/dp.py); only the norm is finished here."""
         if staged_sq_norm is not None:
-            return staged_sq_norm.sqrt()[0]
+            return staged_sq_norm if return_sq else staged_sq_norm.sqrt()[0]
         if arena is None:
             loss.backward(create_graph=create_graph)
         if not update_grad:
@@ -177,7 +177,7 @@ class NativeScalerWithGradNormCount:
             # no clip coefficient to derive first: the optimizer kernel accumulates sum(g^2) while it reads the gradients
             acc = torch.zeros(1, dtype=torch.float32, device=arena.device)
             optimizer.step(loss_guard=loss.detach().reshape(-1)[:1] if loss_guard else None, sq_norm_out=acc)
-            return acc.sqrt()[0]
+            return acc if return_sq else acc.sqrt()[0]        # return_sq: the caller takes the root on the host
         if arena is not None:
             acc = torch.zeros(1, dtype=torch.float32, device=arena.device)
             _lib.sq_norm_f32(arena, acc)

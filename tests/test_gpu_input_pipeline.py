@@ -73,3 +73,55 @@ def test_raw_frames_to_fused_step():
     assert np.array_equal(mask.cpu().numpy(), want_mask.astype(np.uint8))
     loss2 = model.pretrain_step(torch.from_numpy(want_vid).to(dev), torch.from_numpy(want_mask).bool().to(dev)).item()
     assert abs(loss - loss2) <= 1e-6 * abs(loss2)
+
+
+def test_raw_clip_loader_drives_the_engine():
+    """RawClipLoader: raw uint8 frames + boxes -> (GPU preprocessing on a side stream) -> train_one_epoch_BB with GPU masks;
+    same losses as the engine fed the oracle-preprocessed clips and the oracle's masks through a plain loader."""
+    from mofo_b200 import engine_for_pretraining as eng
+    from mofo_b200 import modeling_pretrain as mp
+    from mofo_b200 import transforms as tr
+    from mofo_b200 import utils as U
+    from mofo_b200.optim_factory import FusedAdamW
+    from oracle import mask_oracle as mo
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(8)
+    B, T, H, W = 2, 16, 240, 320
+    raw = []
+    for _ in range(3):
+        frames = torch.from_numpy(rng.integers(0, 256, (B, T, H, W, 3), dtype=np.uint8)).pin_memory()
+        x1 = rng.integers(0, 150, B).astype(np.float64); y1 = rng.integers(0, 100, B).astype(np.float64)
+        boxes = np.repeat(np.stack([x1, y1, x1 + 90, y1 + 110], 1)[:, None, :], T, 1)
+        crops = np.array([[27, 15, 210, 180], [40, 0, 240, 240]], dtype=np.int32)
+        raw.append((frames, boxes, crops))
+
+    def run(loader):
+        torch.manual_seed(0)
+        model = mp.create_model("pretrain_mae_small_patch16_224", pretrained=False, drop_path_rate=0.0, drop_block_rate=None, decoder_depth=4).to(dev)
+        opt = FusedAdamW([{"params": list(model.parameters()), "weight_decay": 0.05, "lr_scale": 1.0}], lr=1e-4, betas=(0.9, 0.95))
+        log = []
+
+        class Log:
+            def update(self, head="x", **kw):
+                if "loss" in kw:
+                    log.append(kw["loss"])
+
+            def set_step(self):
+                pass
+        eng.train_one_epoch_BB(model, loader, opt, dev, 0, U.NativeScalerWithGradNormCount(), max_norm=None, patch_size=16,
+                               normlize_target=True, log_writer=Log(), start_steps=0)
+        return log
+
+    class Quiet(list):
+        quiet = True
+    got = run(tr.RawClipLoader(Quiet(raw), tr.ClipPreprocessor(224)))
+    plain = Quiet()
+    for frames, boxes, crops in raw:
+        vids, masks = [], []
+        for b in range(B):
+            v, bo = io.preprocess_clip(frames[b].numpy(), boxes[b], tuple(int(c) for c in crops[b]))
+            vids.append(v); masks.append(mo.tube_mask_bb(bo[0], mo.mt19937_words(10, 800), (8, 14, 14))[0])
+        plain.append((torch.from_numpy(np.stack(vids)), torch.zeros(B, T, 4, dtype=torch.long), torch.from_numpy(np.stack(masks)).double()))
+    want = run(plain)
+    assert len(got) == len(want) == 3
+    assert all(abs(a - b) <= 2e-5 * abs(b) for a, b in zip(got, want)), (got, want)
