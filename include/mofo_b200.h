@@ -81,7 +81,9 @@ int mofo_gather_tubes(const float* video, const int32_t* idx, int B, int n_idx, 
  *                   out1 bf16 = gelu_erf(u)  (Mlp.forward fc1 + nn.GELU, modeling_finetune.py:45-46);
  *                   out0 bf16 = gelu_erf'(u) (kept for backward in place of u: same erf/exp evaluation, so the
  *                   backward epilogue is a single multiply)
- *   BIAS_RESID_F32  out0 f32 = acc + bias[n] + resid[m,n]  (residual add of Block.forward, :218-219)
+ *   BIAS_RESID_F32  out0 f32 = acc + bias[n] + resid[m,n]  (residual add of Block.forward, :218-219); with row_scale
+ *                   (f32, one value per group of group_rows rows = per clip): out0 = resid + row_scale[m / group_rows] *
+ *                   (acc + bias[n]) - DropPath on the residual branch (modeling_finetune.py:20-31, 218-219)
  *   PLAIN_BF16      out0 bf16 = acc
  *   GELU_BWD_BF16   out0 bf16 = acc * aux_bf16[m,n], aux = the gelu_erf'(u) saved by BIAS_GELU_BF16 (backward through nn.GELU)
  *   BIAS_POS_F32    out0 f32 [row' , n] = acc + bias[n] + pos[row_idx[m], n]; row' = (m / group_rows) *
@@ -102,7 +104,7 @@ enum {
 int mofo_gemm_tn(const mofo_bf16* A, int lda, const mofo_bf16* B, int ldb, int M, int N, int K, int epilogue,
                  const float* bias, const float* resid, int ldr, const mofo_bf16* aux_bf16, int ldaux,
                  const float* pos, const int32_t* row_idx, int group_rows, int out_group_rows, void* out0, int ldo0,
-                 void* out1, int ldo1, void* stream);
+                 void* out1, int ldo1, const float* row_scale, void* stream);
 
 /* mofo_gemm_wgrad: dW[N,K] += dY[M,N]^T · X[M,K]   (f32 accumulate into dW with red.global.add; dW must hold the
  * running sum, e.g. a zeroed slice of the gradient arena).  Replaces the weight-gradient GEMM of every nn.Linear /
@@ -139,14 +141,17 @@ int mofo_attn_bwd(const mofo_bf16* qkv, const mofo_bf16* out, const mofo_bf16* o
  * fwd: y bf16 [M,D] (dense), mean/rstd f32 [M].
  * bwd: dx = LN'(dy) (+ dres[row] if dres != NULL) written to dx_f32 / dx_bf16 at the mapped x rows (either may be
  *      NULL); dgamma/dbeta f32 [D] (16-byte aligned) are accumulated (+=) with one 16-byte vector reduction per
- *      4 columns per CTA.
+ *      4 columns per CTA.  bf16_row_scale (may be NULL; f32, one value per group of group_rows logical rows): the bf16
+ *      copy is written as bf16(scale * dx) while dx_f32 stays unscaled - the gradient entering a DropPath-scaled
+ *      residual branch (the branch's GEMMs read the bf16 copy, the residual path the f32 one).
  */
 int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int D, float eps,
                        int group_rows, int in_group_rows, int in_row_offset, mofo_bf16* y, float* mean, float* rstd,
                        void* stream);
 int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                        const float* dres, int M, int D, int group_rows, int in_group_rows, int in_row_offset,
-                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, void* stream);
+                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, const float* bf16_row_scale,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (6) Decoder input assembly, masked rows (modeling_pretrain.py:260-263): for each clip b and masked slot j,
@@ -170,7 +175,8 @@ int mofo_zero_rows(float* x_f32, mofo_bf16* x_bf16, int groups, int group_rows, 
  * f32 and / or bf16 [B*N, D] (either may be NULL) - the gradient entering the last transformer block.
  */
 int mofo_token_mean_fwd(const float* x, int B, int N, int D, float* pooled, void* stream);
-int mofo_token_mean_bwd(const float* dpooled, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16, void* stream);
+int mofo_token_mean_bwd(const float* dpooled, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16,
+                        const float* bf16_row_scale /* f32 [B] or NULL: bf16 copy = bf16(scale[b] * dx) */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (7) Target + loss (engine_for_pretraining.py:258-304): un-normalise with ImageNet mean/std (:260-265), patchify

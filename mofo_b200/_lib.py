@@ -26,17 +26,17 @@ SIGNATURES = {
     "mofo_tube_mask_plain": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
     "mofo_mask_indices": ([_P, _I, _I, _I, _P, _P, _P, _P], C.c_int),
     "mofo_gather_tubes": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
-    "mofo_gemm_tn": ([_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P, _I, _P], C.c_int),
+    "mofo_gemm_tn": ([_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P, _I, _P, _P], C.c_int),
     "mofo_gemm_wgrad": ([_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P], C.c_int),
     "mofo_attn_fwd": ([_P, _I, _I, _I, _F, _P, _P, _P, _P], C.c_int),
     "mofo_attn_bwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
     "mofo_layernorm_fwd": ([_P, _P, _P, _I, _I, _F, _I, _I, _I, _P, _P, _P, _P], C.c_int),
-    "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], C.c_int),
+    "mofo_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
     "mofo_decoder_assemble_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_decoder_assemble_bwd": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
     "mofo_zero_rows": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
     "mofo_token_mean_fwd": ([_P, _I, _I, _I, _P, _P], C.c_int),
-    "mofo_token_mean_bwd": ([_P, _I, _I, _I, _P, _P, _P], C.c_int),
+    "mofo_token_mean_bwd": ([_P, _I, _I, _I, _P, _P, _P, _P], C.c_int),
     "mofo_target_mse": ([_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P], C.c_int),
     "mofo_cast_weight": ([_P, _I, _I, _P, _P, _P], C.c_int),
     "mofo_pack_qkv_bias": ([_P, _P, _I, _P, _P], C.c_int),
@@ -171,7 +171,7 @@ def gather_tubes(video, idx, out=None):
 
 
 def gemm_tn(A, Bm, epilogue, out0, out1=None, bias=None, resid=None, aux=None, pos=None, row_idx=None,
-            group_rows=0, out_group_rows=0, M=None):
+            group_rows=0, out_group_rows=0, M=None, row_scale=None):
     """out0 = epi(A[M,K] @ Bm[N,K]^T).  A/Bm bf16 row-major (last dim contiguous)."""
     M = A.shape[0] if M is None else M
     K = A.shape[1]
@@ -186,7 +186,7 @@ def gemm_tn(A, Bm, epilogue, out0, out1=None, bias=None, resid=None, aux=None, p
                                resid.stride(0) if resid is not None else 0, _ptr(aux),
                                aux.stride(0) if aux is not None else 0, _ptr(pos), _ptr(row_idx), group_rows,
                                out_group_rows, _ptr(out0), out0.stride(0), _ptr(out1),
-                               out1.stride(0) if out1 is not None else 0, _stream()), "mofo_gemm_tn")
+                               out1.stride(0) if out1 is not None else 0, _ptr(row_scale), _stream()), "mofo_gemm_tn")
     if t is not None:
         e1.record()
         t.events.append((e0, e1)); t.flops += 2.0 * M * N * K
@@ -230,11 +230,12 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, M, D, eps=1e-6, group_rows=0, i
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres, M, D, dx_f32, dx_bf16, dgamma, dbeta, group_rows=0,
-                  in_group_rows=0, in_row_offset=0):
+                  in_group_rows=0, in_row_offset=0, bf16_row_scale=None):
     g = group_rows if group_rows > 0 else M
     ig = in_group_rows if in_group_rows > 0 else M
     _check(load().mofo_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), M, D, g, ig,
-                                     in_row_offset, _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _stream()),
+                                     in_row_offset, _ptr(dx_f32), _ptr(dx_bf16), _ptr(dgamma), _ptr(dbeta), _ptr(bf16_row_scale),
+                                     _stream()),
            "mofo_layernorm_bwd")
 
 
@@ -258,8 +259,9 @@ def token_mean_fwd(x, B, N, D, pooled):
     return pooled
 
 
-def token_mean_bwd(dpooled, B, N, D, dx_f32, dx_bf16):
-    _check(load().mofo_token_mean_bwd(_ptr(dpooled), B, N, D, _ptr(dx_f32), _ptr(dx_bf16), _stream()), "mofo_token_mean_bwd")
+def token_mean_bwd(dpooled, B, N, D, dx_f32, dx_bf16, bf16_row_scale=None):
+    _check(load().mofo_token_mean_bwd(_ptr(dpooled), B, N, D, _ptr(dx_f32), _ptr(dx_bf16), _ptr(bf16_row_scale), _stream()),
+           "mofo_token_mean_bwd")
 
 
 def target_mse(video, msk_idx, pred, loss_partials, loss, dpred, normalize_target=True, grad_scale=1.0,

@@ -50,6 +50,7 @@ struct EpiParams {
   int ldo0;
   void* out1;
   int ldo1;
+  const float* row_scale;    // BIAS_RESID_F32 only: out = resid + row_scale[m / group_rows] * (acc + bias)   (DropPath)
 };
 
 // erf-form GELU (nn.GELU default).  erf by Abramowitz-Stegun 7.1.25 (3-term, |abs err| <= 2.5e-5, below bf16
@@ -182,6 +183,13 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, uint32_t stg
         v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
       }
     }
+  }
+  if (EPI == MOFO_EPI_BIAS_RESID_F32 && ep.row_scale != nullptr) {
+    // stochastic depth (modeling_finetune.py:28, 218-219): the residual BRANCH of sample b is scaled by mask_b / keep_prob
+    const int grow = min(row_base + lane, M - 1);
+    const float sc = __ldg(ep.row_scale + grow / ep.group_rows);
+#pragma unroll
+    for (int e = 0; e < COLS; ++e) v[e] *= sc;
   }
   auto out_row = [&](int grow) -> size_t {
     return EPI == MOFO_EPI_BIAS_POS_F32
@@ -887,13 +895,14 @@ extern "C" {
 int mofo_gemm_tn(const mofo_bf16* A, int lda, const mofo_bf16* B, int ldb, int M, int N, int K, int epilogue,
                  const float* bias, const float* resid, int ldr, const mofo_bf16* aux_bf16, int ldaux, const float* pos,
                  const int32_t* row_idx, int group_rows, int out_group_rows, void* out0, int ldo0, void* out1, int ldo1,
-                 void* stream) {
+                 const float* row_scale, void* stream) {
   MOFO_CHECK_ARG(A && B && out0, "gemm_tn: null pointer");
+  MOFO_CHECK_ARG(!row_scale || (epilogue == MOFO_EPI_BIAS_RESID_F32 && group_rows > 0), "gemm_tn: row_scale needs BIAS_RESID_F32 and group_rows");
   MOFO_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0, "gemm_tn: M=%d N=%d K=%d (need K%%8==0, N%%8==0)", M, N, K);
   MOFO_CHECK_ARG(lda >= K && ldb >= K && lda % 8 == 0 && ldb % 8 == 0, "gemm_tn: bad leading dimensions lda=%d ldb=%d", lda, ldb);
   MOFO_CHECK_ARG(ldo0 % 8 == 0 && (reinterpret_cast<uintptr_t>(out0) & 15) == 0, "gemm_tn: out0 must be 16-B aligned with ld%%8==0");
   EpiParams ep{bias, resid, ldr, reinterpret_cast<const __nv_bfloat16*>(aux_bf16), ldaux, pos, row_idx,
-               group_rows > 0 ? group_rows : M, out_group_rows > 0 ? out_group_rows : M, out0, ldo0, out1, ldo1};
+               group_rows > 0 ? group_rows : M, out_group_rows > 0 ? out_group_rows : M, out0, ldo0, out1, ldo1, row_scale};
   switch (epilogue) {
     case MOFO_EPI_BIAS_GELU_BF16:
       MOFO_CHECK_ARG(out1 && ldo1 % 8 == 0, "gemm_tn: BIAS_GELU needs out1"); break;

@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres, int M, int D,
     int group_rows, int in_group_rows, int in_row_offset, float* __restrict__ dx_f32,
-    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    const float* __restrict__ bf16_row_scale) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float red[];  // [warps / SPLIT][2*D]
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
     }
     s1 /= D;
     s2 /= D;
+    const float bsc = bf16_row_scale ? __ldg(bf16_row_scale + m / group_rows) : 1.0f;   // DropPath scale of the consuming branch
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       int ch = ch0 + lane + i * 32;
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(
         if (dres) { o.x += rres[i].x; o.y += rres[i].y; o.z += rres[i].z; o.w += rres[i].w; }
         if (dx_f32) reinterpret_cast<float4*>(dx_f32 + xrow * D)[ch] = o;
         if (dx_bf16) {
-          uint2 p; p.x = pack_bf16(o.x, o.y); p.y = pack_bf16(o.z, o.w);
+          uint2 p; p.x = pack_bf16(o.x * bsc, o.y * bsc); p.y = pack_bf16(o.z * bsc, o.w * bsc);
           reinterpret_cast<uint2*>(dx_bf16 + xrow * D)[ch] = p;
         }
       }
@@ -528,7 +530,8 @@ __global__ void token_mean_fwd_kernel(const float* __restrict__ x, int N, int D,
 // dx[b, n, :] = dpooled[b, :] / N for every token n (f32 and / or bf16 copy), 16 bytes per thread and iteration
 __global__ void __launch_bounds__(256) token_mean_bwd_kernel(const float* __restrict__ dpooled, int N, int D, float inv_n,
                                                              int64_t total4, float* __restrict__ dx_f32,
-                                                             __nv_bfloat16* __restrict__ dx_bf16) {
+                                                             __nv_bfloat16* __restrict__ dx_bf16,
+                                                             const float* __restrict__ bf16_row_scale) {
   pdl_wait();
   pdl_trigger();
   const int C4 = D >> 2;
@@ -540,7 +543,8 @@ __global__ void __launch_bounds__(256) token_mean_bwd_kernel(const float* __rest
     v.x *= inv_n; v.y *= inv_n; v.z *= inv_n; v.w *= inv_n;
     if (dx_f32) reinterpret_cast<float4*>(dx_f32)[i] = v;
     if (dx_bf16) {
-      uint2 p; p.x = pack_bf16(v.x, v.y); p.y = pack_bf16(v.z, v.w);
+      const float sc = bf16_row_scale ? __ldg(bf16_row_scale + b) : 1.0f;
+      uint2 p; p.x = pack_bf16(v.x * sc, v.y * sc); p.y = pack_bf16(v.z * sc, v.w * sc);
       reinterpret_cast<uint2*>(dx_bf16)[i] = p;
     }
   }
@@ -622,14 +626,17 @@ __global__ void __launch_bounds__(128) target_mse_kernel(const float* __restrict
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float var = ((sh3[1][0][c] + sh3[1][1][c]) + (sh3[1][2][c] + sh3[1][3][c])) * (1.0f / 511.0f);   // unbiased (:270)
-      sd[c] = sqrtf(var) + 1e-6f;
+      // one correctly rounded reciprocal per (tube, channel) instead of 12 IEEE divisions per thread (the kernel was
+      // instruction-bound: issue slots 81 % busy, the divisions ~40 % of them); (x - mu) * (1 / sd) is within 1 ulp of
+      // the reference's (x - mu) / sd
+      sd[c] = __frcp_rn(sqrtf(var) + 1e-6f);
     }
   }
   float l[12];                                           // feature order: l[e*3 + c] = label of pixel pbase+e, channel c  (:276)
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) l[e * 3 + c] = normalize_target ? __fdiv_rn(xv[c][e] - mu[c], sd[c]) : xv[c][e];
+    for (int c = 0; c < 3; ++c) l[e * 3 + c] = normalize_target ? (xv[c][e] - mu[c]) * sd[c] : xv[c][e];
   }
   if (labels_out) {
 #pragma unroll
@@ -955,7 +962,8 @@ int mofo_layernorm_fwd(const float* x, const float* gamma, const float* beta, in
 
 int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                        const float* dres, int M, int D, int group_rows, int in_group_rows, int in_row_offset,
-                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, void* stream) {
+                       float* dx_f32, mofo_bf16* dx_bf16, float* dgamma, float* dbeta, const float* bf16_row_scale,
+                       void* stream) {
   MOFO_CHECK_ARG(dy && x && gamma && mean && rstd && dgamma && dbeta, "layernorm_bwd: null pointer");
   MOFO_CHECK_ARG(((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0,
                  "layernorm_bwd: dgamma / dbeta must be 16-byte aligned");
@@ -976,7 +984,7 @@ int mofo_layernorm_bwd(const mofo_bf16* dy, const float* x, const float* gamma, 
     MOFO_CUDA(launch_pdl(layernorm_bwd_kernel<NCH, SPLIT>, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), \
                          reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, M, D, group_rows,     \
                          in_group_rows, in_row_offset, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma,      \
-                         dbeta));                                                                                      \
+                         dbeta, bf16_row_scale));                                                                      \
   } while (0)
   if (split == 1) {
     if (nch <= 1) MOFO_LN_BWD(1, 1);
@@ -1052,14 +1060,15 @@ int mofo_token_mean_fwd(const float* x, int B, int N, int D, float* pooled, void
   return MOFO_OK;
 }
 
-int mofo_token_mean_bwd(const float* dpooled, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16, void* stream) {
+int mofo_token_mean_bwd(const float* dpooled, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16,
+                        const float* bf16_row_scale, void* stream) {
   MOFO_CHECK_ARG(dpooled && (dx_f32 || dx_bf16), "token_mean_bwd: null pointer");
   MOFO_CHECK_ARG(B > 0 && N > 0 && D > 0 && D % 4 == 0, "token_mean_bwd: bad shape B=%d N=%d D=%d", B, N, D);
   const int64_t total4 = static_cast<int64_t>(B) * N * (D >> 2);
   int64_t blocks = (total4 + 255) / 256;
   if (blocks > 16L * sm_count()) blocks = 16L * sm_count();
   MOFO_CUDA(launch_pdl(token_mean_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-                       dpooled, N, D, 1.0f / N, total4, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16)));
+                       dpooled, N, D, 1.0f / N, total4, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), bf16_row_scale));
   return MOFO_OK;
 }
 

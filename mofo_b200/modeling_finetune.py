@@ -14,9 +14,11 @@ token mean pooling (``mofo_token_mean_fwd/bwd``), ``fc_norm`` and the classifier
 one ``autograd.Function`` whose backward is the manual kernel backward, so the reference's ``engine_for_finetuning``
 (criterion on the logits, ``loss_scaler(loss, optimizer, ...)``) drives it unchanged.  No CPU / eager fallback.
 
-Not implemented (raises): DropPath > 0 (the finetuning recipe's 0.1), dropout, ``init_values`` > 0, learnable position
-embedding, ``use_mean_pooling=False``; the box-focused classifier ``VisionTransformer_BB_focused`` (:422-635) is out of
-scope of this round.
+DropPath (the finetuning recipe's 0.1, modeling_finetune.py:20-31): the per-sample keep / scale factor of each residual
+branch rides in the residual GEMM's epilogue (``row_scale``) and, in backward, on the bf16 gradient copy the branch's
+GEMMs read (``bf16_row_scale`` of the LayerNorm backward / token-mean backward).
+Not implemented (raises): dropout, ``init_values`` > 0, learnable position embedding, ``use_mean_pooling=False``; the
+box-focused classifier ``VisionTransformer_BB_focused`` (:422-635) is out of scope of this round.
 """
 from __future__ import annotations
 
@@ -127,8 +129,16 @@ class _FtRunner(_Runner):
         pe = m.patch_embed.proj
         _lib.gemm_tn(A_pe, wc["pe"][0], _lib.EPI_BIAS_POS_F32, xe, bias=pe.bias, pos=self.pos, row_idx=idx, group_rows=N,
                      out_group_rows=N)
+        # DropPath (modeling_finetune.py:20-31, 343-349): per block i and branch, sample b keeps its residual branch with
+        # probability 1 - dpr[i] and the kept branches are scaled by 1 / keep_prob; one [2*depth, B] draw per forward
+        self.dp = None
+        if m.training and m.drop_path_rate > 0.0:
+            keep = 1.0 - torch.tensor(m.dpr, dtype=f32, device=self.device).repeat_interleave(2)[:, None]     # [2*depth, 1]
+            u = m._drop_path_uniform(2 * len(m.blocks), B, self.device)
+            self.dp = ((keep + u).floor_() / keep).contiguous()        # timm drop_path: floor(keep + U[0,1)) / keep
         for i, blk in enumerate(m.blocks):
-            xe = self._block_fwd(f"blk{i}", blk, xe, B * N, N, B, D)
+            dp = (self.dp[2 * i], self.dp[2 * i + 1]) if self.dp is not None else None
+            xe = self._block_fwd(f"blk{i}", blk, xe, B * N, N, B, D, dp=dp)
         self.x_out = xe
         # norm = Identity, fc_norm(x.mean(1)), head  (:398-401, 405-406)
         pooled = self.buf("pooled", (B, D), f32)
@@ -167,11 +177,14 @@ class _FtRunner(_Runner):
                            self.buf("fc.rstd", (B,), f32), None, B, D, dpooled, None, g["fc_norm.weight"], g["fc_norm.bias"])
         dxA = self.buf("bwd.dxA", (B * N, D), f32); dxA16 = self.buf("bwd.dxA16", (B * N, D), bf)
         dxB = self.buf("bwd.dxB", (B * N, D), f32); dxB16 = self.buf("bwd.dxB16", (B * N, D), bf)
-        _lib.token_mean_bwd(dpooled, B, N, D, dxA, dxA16)
         nb = len(m.blocks)
+        dp = self.dp
+        _lib.token_mean_bwd(dpooled, B, N, D, dxA, dxA16, bf16_row_scale=dp[2 * nb - 1] if dp is not None else None)
         for i in range(nb - 1, -1, -1):
             x_in = self.buf("x0", (B * N, D), f32) if i == 0 else self.buf(f"blk{i - 1}.xo", (B * N, D), f32)
-            self._block_bwd(f"blk{i}", m.blocks[i], g, x_in, dxA, dxA16, dxB, dxB16, B * N, N, B, D)
+            self._block_bwd(f"blk{i}", m.blocks[i], g, x_in, dxA, dxA16, dxB, dxB16, B * N, N, B, D,
+                            dp_attn=dp[2 * i] if dp is not None else None,
+                            dp_prev_mlp=dp[2 * i - 1] if (dp is not None and i > 0) else None)
         A_pe = self.buf("A_pe", (B * N, 1536), bf)
         self._wgrad((), dxA16, A_pe, g["patch_embed.proj.weight"], dbias=g["patch_embed.proj.bias"])
         self._join_side()
@@ -204,7 +217,7 @@ class VisionTransformer(nn.Module):
                  tubelet_size=2, use_mean_pooling=True):
         super().__init__()
         unsupported = dict(patch_size=(patch_size, 16), in_chans=(in_chans, 3), qk_scale=(qk_scale, None), drop_rate=(drop_rate, 0.),
-                           attn_drop_rate=(attn_drop_rate, 0.), drop_path_rate=(drop_path_rate, 0.), init_values=(init_values, 0.),
+                           attn_drop_rate=(attn_drop_rate, 0.), init_values=(init_values, 0.),
                            use_learnable_pos_emb=(use_learnable_pos_emb, False), tubelet_size=(tubelet_size, 2),
                            use_mean_pooling=(use_mean_pooling, True))
         for k, (v, want) in unsupported.items():
@@ -215,6 +228,8 @@ class VisionTransformer(nn.Module):
         self.num_classes = num_classes
         self.num_features = self.embed_dim = embed_dim
         self.tubelet_size = tubelet_size
+        self.drop_path_rate = float(drop_path_rate)
+        self.dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]      # stochastic depth decay rule (:343)
         self.patch_embed = _PatchEmbed(img_size, patch_size, in_chans, embed_dim, num_frames=all_frames, tubelet_size=tubelet_size)
         self.pos_embed = get_sinusoid_encoding_table(self.patch_embed.num_patches, embed_dim)   # attribute, not a buffer (:338-340)
         self.pos_drop = nn.Dropout(p=drop_rate)
@@ -241,6 +256,10 @@ class VisionTransformer(nn.Module):
 
     def get_num_layers(self):
         return len(self.blocks)
+
+    def _drop_path_uniform(self, n, B, device):
+        """U[0,1) draws behind the DropPath masks, [n, B] (tests substitute a fixed tensor to compare with the reference)."""
+        return torch.rand(n, B, dtype=torch.float32, device=device)
 
     @torch.jit.ignore
     def no_weight_decay(self):

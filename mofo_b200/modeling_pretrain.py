@@ -351,7 +351,8 @@ class _Runner:
         cast("head", m.decoder.head.weight)
 
     # ---- forward ------------------------------------------------------------------------------------------
-    def _block_fwd(self, pre, blk, x, M, S, B, D):
+    def _block_fwd(self, pre, blk, x, M, S, B, D, dp=None):
+        """``dp``: None, or (s1, s2) f32 [B] DropPath scales (mask_b / keep_prob) of the attention / MLP branches."""
         H = blk.attn.num_heads
         bf, f32 = torch.bfloat16, torch.float32
         wc = self.wcache
@@ -364,14 +365,16 @@ class _Runner:
         olo = self.buf(pre + ".olo", (M, D), bf) if S > _lib.ATTN_SINGLE_PASS_MAX_S else None
         _lib.attn_fwd(qkv, B, S, H, blk.attn.scale, o, lse, out_lo=olo)
         xm = self.buf(pre + ".xm", (M, D), f32)
-        _lib.gemm_tn(o, wc[pre + ".proj"][0], _lib.EPI_BIAS_RESID_F32, xm, bias=blk.attn.proj.bias, resid=x)
+        _lib.gemm_tn(o, wc[pre + ".proj"][0], _lib.EPI_BIAS_RESID_F32, xm, bias=blk.attn.proj.bias, resid=x,
+                     row_scale=dp[0] if dp else None, group_rows=S if dp else 0)
         h2 = self.buf(pre + ".h2", (M, D), bf); mean2 = self.buf(pre + ".mean2", (M,), f32); rstd2 = self.buf(pre + ".rstd2", (M,), f32)
         _lib.layernorm_fwd(xm, blk.norm2.weight, blk.norm2.bias, h2, mean2, rstd2, M, D, blk.norm2.eps)
         Dh = blk.mlp.fc1.weight.shape[0]
         u = self.buf(pre + ".u", (M, Dh), bf); a = self.buf(pre + ".a", (M, Dh), bf)
         _lib.gemm_tn(h2, wc[pre + ".fc1"][0], _lib.EPI_BIAS_GELU_BF16, u, out1=a, bias=blk.mlp.fc1.bias)
         xo = self.buf(pre + ".xo", (M, D), f32)
-        _lib.gemm_tn(a, wc[pre + ".fc2"][0], _lib.EPI_BIAS_RESID_F32, xo, bias=blk.mlp.fc2.bias, resid=xm)
+        _lib.gemm_tn(a, wc[pre + ".fc2"][0], _lib.EPI_BIAS_RESID_F32, xo, bias=blk.mlp.fc2.bias, resid=xm,
+                     row_scale=dp[1] if dp else None, group_rows=S if dp else 0)
         return xo
 
     def forward(self, x, vis_idx, msk_idx):
@@ -414,8 +417,11 @@ class _Runner:
         return pred
 
     # ---- backward -----------------------------------------------------------------------------------------
-    def _block_bwd(self, pre, blk, g, x_in, dxA, dxA16, dxB, dxB16, M, S, B, D):
-        """dxA/dxA16 hold d(loss)/d(block output) (f32 + bf16).  On return they hold d(loss)/d(block input)."""
+    def _block_bwd(self, pre, blk, g, x_in, dxA, dxA16, dxB, dxB16, M, S, B, D, dp_attn=None, dp_prev_mlp=None):
+        """dxA/dxA16 hold d(loss)/d(block output) (f32 + bf16).  On return they hold d(loss)/d(block input).
+        DropPath: dxA16 must arrive already scaled by THIS block's MLP-branch scale (the producer applies it);
+        ``dp_attn`` = this block's attention-branch scale (applied to dxB16 by norm2's backward), ``dp_prev_mlp`` = the
+        MLP-branch scale of the block that runs next in backward (applied to the dxA16 this call leaves behind)."""
         H = blk.attn.num_heads
         bf, f32 = torch.bfloat16, torch.float32
         wc = self.wcache
@@ -438,7 +444,8 @@ class _Runner:
         # norm2 (+ residual gradient)
         self._before_write(dxB16)                                # previous block's proj wgrad
         _lib.layernorm_bwd(dh, xm, blk.norm2.weight, mean2, rstd2, dxA, M, D, dxB, dxB16, g[name + ".norm2.weight"],
-                           g[name + ".norm2.bias"])
+                           g[name + ".norm2.bias"], group_rows=S if dp_attn is not None else 0,
+                           in_group_rows=S if dp_attn is not None else 0, bf16_row_scale=dp_attn)
         # proj
         self._wgrad((dxB16,), dxB16, o, g[name + ".attn.proj.weight"], dbias=g[name + ".attn.proj.bias"])
         do = self.buf("bwd.do", (M, D), bf)
@@ -457,7 +464,8 @@ class _Runner:
         # norm1 (+ residual gradient)
         self._before_write(dxA16)                                # this block's fc2 wgrad
         _lib.layernorm_bwd(dh, x_in, blk.norm1.weight, mean1, rstd1, dxB, M, D, dxA, dxA16, g[name + ".norm1.weight"],
-                           g[name + ".norm1.bias"])
+                           g[name + ".norm1.bias"], group_rows=S if dp_prev_mlp is not None else 0,
+                           in_group_rows=S if dp_prev_mlp is not None else 0, bf16_row_scale=dp_prev_mlp)
 
     def backward(self, dpred, g, stage_done=None):
         """dpred bf16 [B*Nm, 1536]; g: name -> fp32 tensor that the parameter gradient is ACCUMULATED into.

@@ -41,7 +41,7 @@ def test_version_and_error_string(lib):
 def test_argument_validation_without_gpu(lib):
     # invalid arguments are rejected on the host before any CUDA call
     cdll = lib.load()
-    rc = cdll.mofo_gemm_tn(None, 0, None, 0, 0, 0, 0, 0, None, None, 0, None, 0, None, None, 0, 0, None, 0, None, 0, None)
+    rc = cdll.mofo_gemm_tn(None, 0, None, 0, 0, 0, 0, 0, None, None, 0, None, 0, None, None, 0, 0, None, 0, None, 0, None, None)
     assert rc == -1 and b"null" in cdll.mofo_last_error()
     rc = cdll.mofo_tube_mask_bb(None, None, 0, 0, 8, 14, 14, 176, 0.75, None, None, None, None, None)
     assert rc == -1

@@ -74,6 +74,67 @@ def test_classifier_step_matches_reference(name, B, classes, init_scale):
             bad.append((n, e, r))
     print("worst gradient:", worst)
     assert not bad, bad[:8]
-    # eval / no_grad forward returns the same logits
+    # eval / no_grad forward returns the same logits (the token mean is reduced with fp32 atomics: last-bit differences)
     with torch.no_grad():
-        assert torch.equal(ours(x), logits.detach())
+        assert rel(ours(x), logits.detach()) < 1e-6
+
+
+def test_classifier_drop_path_matches_reference_with_the_same_draws():
+    """DropPath 0.1 (the finetuning recipe): with the SAME uniform draws behind the per-sample keep masks, logits and every
+    gradient match the reference (fp32 truth, bf16-autocast calibration).  The reference's drop_path (timm semantics:
+    floor(keep + U) / keep per sample) is fed the draws our model uses."""
+    refrun = _refrun()
+    ref = refrun.load()
+    from mofo_b200 import modeling_finetune as mf
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(5)
+    name, B, classes = "vit_small_patch16_224", 6, 174
+    kw = dict(num_classes=classes, all_frames=16, tubelet_size=2, drop_rate=0.0, drop_path_rate=0.3, attn_drop_rate=0.0,
+              use_mean_pooling=True, init_scale=1.0)
+    ref_model = getattr(ref.modeling_finetune, name)(pretrained=False, **kw).to(dev).train()
+    ours = mf.create_model(name, pretrained=False, drop_block_rate=None, **kw)
+    ours.load_state_dict(ref_model.state_dict(), strict=True)
+    ours = ours.to(dev).train()
+    depth = len(ours.blocks)
+    U = torch.rand(2 * depth, B, device=dev)
+    ours._drop_path_uniform = lambda n, b, d: U.clone()
+    dpr = ours.dpr
+    calls = {}
+
+    def fixed_drop_path(x, drop_prob=0., training=False):
+        if drop_prob == 0. or not training:
+            return x
+        i = min(range(depth), key=lambda k: abs(dpr[k] - drop_prob))          # block index from its (unique) rate
+        j = calls.get(i, 0); calls[i] = j + 1                                   # 0 = attention branch, 1 = MLP branch
+        keep = 1.0 - drop_prob
+        mask = (keep + U[2 * i + (j % 2)]).floor()
+        return x.div(keep) * mask.to(x.dtype).view(-1, *([1] * (x.ndim - 1)))
+    orig = ref.modeling_finetune.drop_path
+    ref.modeling_finetune.drop_path = fixed_drop_path
+    try:
+        x = refrun.synthetic_batches(B, 1, seed=13, device=dev)[0][0]
+        y = torch.randint(0, classes, (B,), device=dev)
+        calls.clear(); l32, loss32, g32 = _ref_step(ref_model, x, y, amp=False)
+        calls.clear(); l16, loss16, g16 = _ref_step(ref_model, x, y, amp=True)
+    finally:
+        ref.modeling_finetune.drop_path = orig
+    assert (U[2:] + (1.0 - torch.tensor(dpr, device=dev).repeat_interleave(2)[2:, None]) < 1.0).any(), "no branch was dropped"
+    logits = ours(x)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300)).item()
+    e, r = rel(logits.detach(), l32), rel(l16, l32)
+    print(f"drop_path 0.3: logits rel {e:.3e} (reference bf16 {r:.3e})")
+    assert e <= max(2e-2, 2.5 * r)
+    bad = []
+    for n, p in ours.named_parameters():
+        ee, rr = rel(p.grad, g32[n]), rel(g16[n], g32[n])
+        if ee > max(3e-2, 2.5 * rr):
+            bad.append((n, ee, rr))
+    assert not bad, bad[:8]
+    ours.eval()
+    with torch.no_grad():
+        a, b = ours(x), ours(x)
+    assert rel(a, b) < 1e-6                        # no DropPath in eval mode (fp32 atomics in the token mean: last bits)

@@ -105,7 +105,10 @@ def test_finetune_classifier_schema_matches_reference():
     om.load_state_dict(sd, strict=True)
     assert om.no_weight_decay() == rm.no_weight_decay() and om.get_num_layers() == rm.get_num_layers()
     assert torch.equal(om.pos_embed, rm.pos_embed)
+    dp = mf.create_model("vit_small_patch16_224", num_classes=174, drop_path_rate=0.1)           # the finetuning recipe's DropPath
+    rp = ref.modeling_finetune.vit_small_patch16_224(pretrained=False, num_classes=174, drop_path_rate=0.1)
+    assert [round(v, 6) for v in dp.dpr] == [round(b.drop_path.drop_prob if hasattr(b.drop_path, "drop_prob") else 0.0, 6) for b in rp.blocks]
     with pytest.raises(NotImplementedError):
-        mf.create_model("vit_small_patch16_224", num_classes=174, drop_path_rate=0.1)
+        mf.create_model("vit_small_patch16_224", num_classes=174, drop_rate=0.1)
     with pytest.raises(RuntimeError):
         om(torch.zeros(1, 3, 16, 224, 224))
