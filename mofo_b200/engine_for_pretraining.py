@@ -86,8 +86,9 @@ class _CudaPrefetcher:
     copy into a slot waits for an event recorded on the compute stream once the step that consumed the slot's previous
     content has been enqueued."""
 
-    def __init__(self, loader, device):
+    def __init__(self, loader, device, mask_fn=None):
         self.loader, self.device = loader, device
+        self.mask_fn = mask_fn          # GPU-mask mode: (videos, bbox) -> (vis_idx, msk_idx), run on the copy stream one batch ahead
         self.quiet = getattr(loader, "quiet", False)
         self.raw = bool(getattr(loader, "mofo_raw_frames", False))      # batches of raw uint8 frames (transforms.RawClipLoader)
         self.pre = getattr(loader, "preprocessor", None)
@@ -127,8 +128,23 @@ class _CudaPrefetcher:
             with torch.cuda.stream(stream):
                 vid, boxes = self.pre(frames, bbox, mask, out=clip)
                 boxes.record_stream(torch.cuda.current_stream(self.device))
-            return vid, boxes, None
-        return self._stage(slot, 0, videos, stream), bbox, self._stage(slot, 2, mask, stream)
+            return vid, boxes, self._masks_ahead(vid, boxes, stream)
+        vid = self._stage(slot, 0, videos, stream)
+        if self.mask_fn is not None:
+            return vid, bbox, self._masks_ahead(vid, bbox, stream)
+        return vid, bbox, self._stage(slot, 2, mask, stream)
+
+    def _masks_ahead(self, vid, bbox, stream):
+        """GPU-mask mode: the (sequential, ~45 us) mask kernel of the NEXT batch runs on the copy stream beside the current
+        step instead of at the head of its own step."""
+        if self.mask_fn is None or not (isinstance(vid, torch.Tensor) and vid.is_cuda):
+            return None
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(stream):
+            vis_idx, msk_idx = self.mask_fn(vid, bbox)
+            for t in (vis_idx, msk_idx):
+                t.record_stream(main)
+        return ("mofo_idx", vis_idx, msk_idx)
 
     def __iter__(self):
         stream = torch.cuda.Stream(device=self.device)
@@ -244,8 +260,13 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
                 weight_decay_value = group["weight_decay"]
         return max_lr, min_lr, weight_decay_value
 
+    def gpu_mask_fn(videos, bbox):
+        pe = core.encoder.patch_embed
+        grid = (videos.shape[2] // pe.tubelet_size, videos.shape[3] // pe.patch_size[0], videos.shape[4] // pe.patch_size[1])
+        return masks_from_bbox(bbox, videos.device, grid, *gpu_mask_ratios)[1:]
+
     if torch.device(device).type == "cuda":
-        data_loader = _CudaPrefetcher(data_loader, torch.device(device))
+        data_loader = _CudaPrefetcher(data_loader, torch.device(device), mask_fn=gpu_mask_fn if gpu_masks else None)
     for step, batch in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
         it = start_steps + step                                                         # :230
         if lr_schedule_values is not None or wd_schedule_values is not None:
@@ -266,10 +287,12 @@ def train_one_epoch_BB(model: torch.nn.Module, data_loader: Iterable, optimizer:
             if gpu_masks:
                 # opt-in (MOFO_GPU_MASKS=1 or data_loader.mofo_gpu_masks): the loader's mask is ignored and the masks are
                 # generated on the GPU from the batch's boxes - lets the DataLoader keep num_workers > 0 with a no-op
-                # mask transform (CUDA cannot run in forked workers), see masks_from_bbox
-                pe = core.encoder.patch_embed
-                grid = (videos.shape[2] // pe.tubelet_size, videos.shape[3] // pe.patch_size[0], videos.shape[4] // pe.patch_size[1])
-                _, vis_idx, msk_idx = masks_from_bbox(bbox, videos.device, grid, *gpu_mask_ratios)
+                # mask transform (CUDA cannot run in forked workers), see masks_from_bbox; the prefetcher has normally
+                # produced them one batch ahead on the copy stream
+                if isinstance(bool_masked_pos, tuple) and bool_masked_pos[0] == "mofo_idx":
+                    vis_idx, msk_idx = bool_masked_pos[1], bool_masked_pos[2]
+                else:
+                    vis_idx, msk_idx = gpu_mask_fn(videos, bbox)
             else:
                 vis_idx, msk_idx = core.indices_from_mask(bool_masked_pos)
             sq = pipelined and not (max_norm is not None and max_norm > 0)
