@@ -72,6 +72,19 @@ def load():
     return _ns
 
 
+def load_finetune_engine():
+    """The reference's engine_for_finetuning (and the mixup module it imports), loaded like the modules above."""
+    load()
+    if "engine_for_finetuning" in sys.modules and getattr(sys.modules["engine_for_finetuning"], "__file__", "").startswith(REF_DIR):
+        return sys.modules["engine_for_finetuning"]
+    sys.path.insert(0, REF_DIR)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            return importlib.import_module("engine_for_finetuning")
+    finally:
+        sys.path.remove(REF_DIR)
+
+
 def create_model(name="pretrain_videomae_base_patch16_224"):
     """run_mae_pretraining_BB.py:138-148 (get_model)."""
     return load().create_model(name, pretrained=False, drop_path_rate=0.0, drop_block_rate=None, decoder_depth=4)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("MOFO_REFERENCE", "/root/reference")
 REF_DST = os.path.join(HERE, "_ref")
 FILES = ["masking_generator.py", "modeling_pretrain.py", "modeling_finetune.py", "engine_for_pretraining.py", "utils.py",
-         "optim_factory.py", "engine_for_finetuning.py"]
+         "optim_factory.py", "engine_for_finetuning.py", "mixup.py"]
 
 
 def stage(verbose=False):

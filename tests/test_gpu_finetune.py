@@ -138,3 +138,52 @@ def test_classifier_drop_path_matches_reference_with_the_same_draws():
     with torch.no_grad():
         a, b = ours(x), ours(x)
     assert rel(a, b) < 1e-6                        # no DropPath in eval mode (fp32 atomics in the token mean: last bits)
+
+
+def test_reference_finetuning_engine_drives_the_b200_classifier():
+    """Drop-in at the engine level: the reference's OWN engine_for_finetuning.train_one_epoch (fp16 autocast,
+    GradScaler-based loss scaler, soft-target cross-entropy, its own create_optimizer) runs unchanged on the B200 classifier,
+    and the loss trajectory follows the same engine driving the reference's classifier from the same weights."""
+    import types
+    refrun = _refrun()
+    ref = refrun.load()
+    eng = refrun.load_finetune_engine()
+    from mofo_b200 import modeling_finetune as mf
+    from timm.loss import SoftTargetCrossEntropy
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(11)
+    name, B, classes = "vit_small_patch16_224", 4, 174
+    kw = dict(num_classes=classes, all_frames=16, tubelet_size=2, drop_rate=0.0, drop_path_rate=0.0, attn_drop_rate=0.0,
+              use_mean_pooling=True, init_scale=1.0)
+    ref_model = getattr(ref.modeling_finetune, name)(pretrained=False, **kw).to(dev)
+    ours = mf.create_model(name, pretrained=False, drop_block_rate=None, **kw)
+    ours.load_state_dict(ref_model.state_dict(), strict=True)
+    ours = ours.to(dev)
+    xs = [b[0] for b in refrun.synthetic_batches(B, 2, seed=17, device=dev)]
+    g = torch.Generator().manual_seed(3)
+    ys = [torch.randint(0, classes, (B,), generator=g) for _ in range(2)]
+    steps = 6
+
+    def mixup_fn(samples, targets):            # stands in for timm's Mixup: label smoothing only (the engine needs soft targets)
+        return samples, torch.nn.functional.one_hot(targets, classes).float() * 0.9 + 0.1 / classes
+    loader = [(xs[i % 2], ys[i % 2], None, None) for i in range(steps)]
+    args = types.SimpleNamespace(data_set="SSV2")
+
+    def run(model):
+        losses = refrun.LossLog()
+        opt = refrun.create_optimizer(model, lr=2e-4)
+        scaler = refrun.make_scaler(dev)
+        with refrun._quiet():
+            eng.train_one_epoch(model, SoftTargetCrossEntropy(), loader, opt, dev, 0, scaler, args, max_norm=None, model_ema=None,
+                                mixup_fn=mixup_fn, log_writer=None, start_steps=0, lr_schedule_values=None, wd_schedule_values=None,
+                                num_training_steps_per_epoch=steps, update_freq=1)
+        return model
+    # per-step losses through a forward hook on the criterion is not available: compare the trained weights' behaviour instead
+    run(ref_model); run(ours)
+    ref_model.eval(); ours.eval()
+    with torch.no_grad():
+        a = ref_model(xs[0]).float(); b = ours(xs[0])
+    la = torch.nn.functional.cross_entropy(a, ys[0].to(dev)).item(); lb = torch.nn.functional.cross_entropy(b, ys[0].to(dev)).item()
+    print(f"after {steps} steps of the reference finetuning engine: eval loss reference {la:.4f}, ours {lb:.4f}")
+    assert abs(la - lb) <= 3e-2 * abs(la)
+    assert ((a - b).norm() / a.norm()).item() < 0.1
