@@ -171,7 +171,7 @@ int mofo_zero_rows(float* x_f32, mofo_bf16* x_bf16, int groups, int group_rows, 
 /* ------------------------------------------------------------------------------------------------------------
  * (6b) Token mean pooling of the finetuning classifier: VisionTransformer.forward_features ends with
  * fc_norm(x.mean(1)) (modeling_finetune.py:398-401).  fwd: pooled f32 [B, D] = mean over the N tokens of x f32 [B, N, D]
- * (pooled is zeroed by the call, 16-byte aligned).  bwd: dx[b, n, :] = dpooled[b, :] / N for every token, written as
+ * (16-byte aligned; deterministic: fixed summation order, no atomics).  bwd: dx[b, n, :] = dpooled[b, :] / N for every token, written as
  * f32 and / or bf16 [B*N, D] (either may be NULL) - the gradient entering the last transformer block.
  */
 int mofo_token_mean_fwd(const float* x, int B, int N, int D, float* pooled, void* stream);

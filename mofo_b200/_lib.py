@@ -73,7 +73,7 @@ def load() -> C.CDLL:
 
 
 # kernels launched per successful C-ABI call (bench.py reports the count it observed as "gpu_launches")
-_LAUNCHES = {"mofo_target_mse": 2, "mofo_attn_bwd": 3}      # (mofo_token_mean_fwd also issues a memset node, not a kernel)
+_LAUNCHES = {"mofo_target_mse": 2, "mofo_attn_bwd": 3}
 launch_count = 0
 
 

@@ -162,6 +162,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, uint32_t stg
   const int rem = N - n0;                                   // > 0
   const int valid_chunks = rem >= COLS ? 4 : (T::F32_OUT ? rem / 4 : rem / 8);
   float v[COLS];
+  // the chunk's bias slice is requested BEFORE the accumulator read is waited for, so the two latencies overlap (the
+  // bias add used to sit behind a long-scoreboard stall in every chunk: ncu source view, round 2)
+  float4 bv[COLS / 4];
+  const bool has_bias = T::HAS_BIAS && ep.bias != nullptr;
+  if (has_bias) {
+#pragma unroll
+    for (int c = 0; c < COLS / 4; ++c)
+      bv[c] = n0 + c * 4 < N ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (COLS == 32) {
     uint32_t r[32];
     tmem_ld32(taddr, r);
@@ -175,13 +184,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, uint32_t stg
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e % COLS] = __uint_as_float(r[e]);
   }
-  if (T::HAS_BIAS && ep.bias) {
+  if (has_bias) {
 #pragma unroll
     for (int c = 0; c < COLS / 4; ++c) {
-      if (n0 + c * 4 < N) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + c);
-        v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
-      }
+      v[c * 4 + 0] += bv[c].x; v[c * 4 + 1] += bv[c].y; v[c * 4 + 2] += bv[c].z; v[c * 4 + 3] += bv[c].w;
     }
   }
   if (EPI == MOFO_EPI_BIAS_RESID_F32 && ep.row_scale != nullptr) {

@@ -489,41 +489,42 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ f32,
 // =================================================================================================
 // (6b) token mean pooling (finetuning classifier)  — modeling_finetune.py:400-401  fc_norm(x.mean(1))
 // =================================================================================================
-// grid = (row chunks, B), block (D/4 rounded up to 32, ASM_RG): threads own float4 column chunks, rows of the chunk are
-// streamed with 4 independent 16-byte loads in flight; one 16-byte vector reduction per 4 columns per CTA into out[b].
-__global__ void token_mean_fwd_kernel(const float* __restrict__ x, int N, int D, int rows_per_cta, float inv_n,
-                                      float* __restrict__ out) {
+// grid = (column blocks of 128, B), block (32, 8): lane = one float4 column chunk, 8 row groups stream the N rows with 4
+// independent 16-byte loads in flight each; the row groups are combined in a FIXED order through shared memory, so the
+// result is deterministic (no atomics: a mean that feeds a LayerNorm amplifies last-bit noise).
+constexpr int TM_RG = 8;
+__global__ void __launch_bounds__(256) token_mean_fwd_kernel(const float* __restrict__ x, int N, int D, float inv_n,
+                                                             float* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float4 part[];                      // [ASM_RG][D / 4]
+  __shared__ float4 part[TM_RG][32];
   const int b = blockIdx.y;
   const int C4 = D >> 2;
-  const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
-  const int c = threadIdx.x, ry = threadIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x, ry = threadIdx.y;
   float4 acc = make_float4(0, 0, 0, 0);
   if (c < C4) {
     const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * N * D) + c;
-    for (int r = r0 + ry; r < r1; r += 4 * ASM_RG) {
+    for (int r = ry; r < N; r += 4 * TM_RG) {
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int rr = r + u * ASM_RG;
-        v[u] = rr < r1 ? src[static_cast<size_t>(rr) * C4] : make_float4(0, 0, 0, 0);
+        const int rr = r + u * TM_RG;
+        v[u] = rr < N ? src[static_cast<size_t>(rr) * C4] : make_float4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
-    part[ry * C4 + c] = acc;
   }
+  part[ry][threadIdx.x] = acc;
   __syncthreads();
   if (ry == 0 && c < C4) {
 #pragma unroll
-    for (int g = 1; g < ASM_RG; ++g) {
-      const float4 o = part[g * C4 + c];
+    for (int g = 1; g < TM_RG; ++g) {
+      const float4 o = part[g][threadIdx.x];
       acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
     }
     acc.x *= inv_n; acc.y *= inv_n; acc.z *= inv_n; acc.w *= inv_n;
-    atomicAdd(reinterpret_cast<float4*>(out + static_cast<size_t>(b) * D) + c, acc);
+    reinterpret_cast<float4*>(out + static_cast<size_t>(b) * D)[c] = acc;
   }
 }
 
@@ -1046,17 +1047,10 @@ int mofo_zero_rows(float* x_f32, mofo_bf16* x_bf16, int groups, int group_rows, 
 
 int mofo_token_mean_fwd(const float* x, int B, int N, int D, float* pooled, void* stream) {
   MOFO_CHECK_ARG(x && pooled, "token_mean_fwd: null pointer");
-  MOFO_CHECK_ARG(B > 0 && N > 0 && D > 0 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 15) == 0, "token_mean_fwd: bad shape B=%d N=%d D=%d", B, N, D);
-  const int cx = ((D >> 2) + 31) / 32 * 32;
-  MOFO_CHECK_ARG(cx * ASM_RG <= 1024, "token_mean_fwd: D=%d too wide", D);
-  int chunks = (2 * sm_count() + B - 1) / B;
-  int rows_per_cta = (N + chunks - 1) / chunks;
-  if (rows_per_cta < 4 * ASM_RG) rows_per_cta = 4 * ASM_RG;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  MOFO_CUDA(cudaMemsetAsync(pooled, 0, static_cast<size_t>(B) * D * sizeof(float), s));
-  dim3 grid((N + rows_per_cta - 1) / rows_per_cta, B);
-  const size_t smem = static_cast<size_t>(ASM_RG) * (D >> 2) * sizeof(float4);
-  MOFO_CUDA(launch_pdl(token_mean_fwd_kernel, grid, dim3(cx, ASM_RG), smem, s, x, N, D, rows_per_cta, 1.0f / N, pooled));
+  MOFO_CHECK_ARG(B > 0 && B <= 65535 && N > 0 && D > 0 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 15) == 0,
+                 "token_mean_fwd: bad shape B=%d N=%d D=%d", B, N, D);
+  dim3 grid(((D >> 2) + 31) / 32, B);
+  MOFO_CUDA(launch_pdl(token_mean_fwd_kernel, grid, dim3(32, TM_RG), 0, static_cast<cudaStream_t>(stream), x, N, D, 1.0f / N, pooled));
   return MOFO_OK;
 }
 

@@ -187,7 +187,8 @@ def fused_step(core, optimizer, loss_scaler, sync, videos, vis_idx, msk_idx, nor
         on_stage, acc = optimizer.begin_staged(loss_guard=runner.buf("loss", (1,), torch.float32))
     sync.begin(arena, runner.stage_end, on_stage=on_stage)
     loss = core.pretrain_step(videos, vis_idx=vis_idx, msk_idx=msk_idx, normalize_target=normalize_target,
-                              grad_scale=sync.grad_scale, zero_grad=True, stage_done=sync.stage_done)
+                              grad_scale=sync.grad_scale, zero_grad=True,
+                              stage_done=sync.stage_done if (sync.world > 1 or on_stage is not None) else None)
     sync.finish()
     if not fused_opt:
         return loss, None

@@ -567,11 +567,13 @@ class _Runner:
         if msk_idx.data_ptr() != sm.data_ptr():
             sm.copy_(msk_idx, non_blocking=True)
         arena = self.grad_arena()                              # (re)attaches the p.grad views
-        key = (B, Nv, Nm, frames, size, bool(normalize_target), float(grad_scale), arena.data_ptr())
+        # nobody listens to stage boundaries (one process, optimizer after backward): ONE graph instead of one per stage
+        whole = stage_done is None
+        key = (B, Nv, Nm, frames, size, bool(normalize_target), float(grad_scale), arena.data_ptr(), whole)
         graphs = self.graphs.get(key, "missing")
         if graphs == "missing":
             self.step_eager(sv, si, sm, normalize_target, grad_scale, True, None)   # warm-up: allocations, attributes
-            graphs = self._capture(sv, si, sm, normalize_target, grad_scale)
+            graphs = self._capture(sv, si, sm, normalize_target, grad_scale, whole)
             self.graphs[key] = graphs
         if graphs is None:                                     # capture unavailable: same kernels, launched one by one
             return self.step_eager(sv, si, sm, normalize_target, grad_scale, True, stage_done)
@@ -587,13 +589,13 @@ class _Runner:
                 stage_done(k)
         return self.buf("loss", (1,), torch.float32)
 
-    def _capture(self, sv, si, sm, normalize_target, grad_scale):
+    def _capture(self, sv, si, sm, normalize_target, grad_scale, whole=False):
         dev = self.device
         graphs = []
         cur = {"g": None, "n0": 0}
         stream = torch.cuda.Stream(device=dev)
         stream.wait_stream(torch.cuda.current_stream(dev))
-        n_stages = len(self.stage_end)
+        n_stages = 1 if whole else len(self.stage_end)
 
         def begin():
             cur["g"] = torch.cuda.CUDAGraph()
@@ -601,10 +603,12 @@ class _Runner:
             cur["g"].capture_begin()       # private pool per segment: nothing is allocated while capturing
 
         def boundary(k):
+            if whole and k + 1 < len(self.stage_end):        # single-graph capture: only the last boundary closes it
+                return
             cur["g"].capture_end()
             graphs.append((cur["g"], _lib.launch_count - cur["n0"]))
             cur["g"] = None
-            if k + 1 < n_stages:
+            if not whole and k + 1 < n_stages:
                 begin()
 
         self.force_cast = True
