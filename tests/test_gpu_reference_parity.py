@@ -9,7 +9,7 @@ baseline/setup_ref.py; its own train_one_epoch_BB, optimizer factory and scaler 
     each aggregate <= 2.5x the reference's OWN deviation under bf16 autocast (floors: 1/4 of the absolute tolerance);
   * 20-step loss trajectory: reference fp32 vs our engine, both driven by the reference's create_optimizer with a
     table-driven learning rate (engine_for_pretraining.py:230-236).
-The measured numbers are written to gpurun_out/parity_reference.json.
+The measured numbers are written to gpurun_out/parity_reference_<model>_b<B>.json.
 """
 import json
 import os
@@ -84,7 +84,7 @@ def _check(ours, ref_bf16, tag, report):
     report[tag] = {"ours_vs_ref_fp32": ours, "ref_bf16_vs_ref_fp32": ref_bf16}
     print(tag, json.dumps(report[tag]))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "parity_reference.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", report.get("file", "parity_reference.json")), "w") as f:     # also on the way to a failure
         json.dump(report, f, indent=1)
     # aggregates: absolute tolerances of SURVEY 8c, and <= 2.5x the reference's own bf16-autocast deviation (with floors)
     for k in ("loss_rel", "out_rel", "gnorm_rel"):
@@ -104,14 +104,15 @@ def _check(ours, ref_bf16, tag, report):
     assert not bad, (tag, bad[:8])
 
 
-@pytest.mark.parametrize("name,B", [("pretrain_videomae_base_patch16_224", 32)])
+@pytest.mark.parametrize("name,B", [("pretrain_videomae_base_patch16_224", 32), ("pretrain_mae_small_patch16_224", 8),
+                                    ("pretrain_videomae_large_patch16_224", 8)])
 def test_full_step_vs_reference_at_init_and_after_20_steps(name, B):
     refrun = _refrun()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     ref_model = refrun.create_model(name).to(dev)
     batches = refrun.synthetic_batches(B, 2, seed=77, device=dev)
-    report = {"config": f"{name}, B={B}, reference fp32 with TF32 off; tolerances SURVEY 8c"}
+    report = {"config": f"{name}, B={B}, reference fp32 with TF32 off; tolerances SURVEY 8c", "file": f"parity_reference_{name}_b{B}.json"}
 
     def one_round(tag):
         r32 = refrun.single_step(ref_model, batches[0], dev, "fp32")
@@ -162,7 +163,7 @@ def test_full_step_vs_reference_at_init_and_after_20_steps(name, B):
 
     one_round("after_20_reference_steps")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "parity_reference.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", f"parity_reference_{name}_b{B}.json"), "w") as f:
         json.dump(report, f, indent=1)
 
 
