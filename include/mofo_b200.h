@@ -116,6 +116,13 @@ int mofo_gemm_tn(const mofo_bf16* A, int lda, const mofo_bf16* B, int ldb, int M
 int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, int M, int N, int K, float* dW,
                     int ldw, float* dbias, int dbias_skip_lo, int dbias_skip_hi, void* stream);
 
+/* mofo_gemm_wgrad_grouped: n (1..4) independent mofo_gemm_wgrad problems that share the reduction length M, in ONE launch
+ * (HOST arrays of n device pointers / sizes; dbias, dbias_skip_lo, dbias_skip_hi may be NULL).  The four weight gradients of
+ * a transformer block (fc2, fc1, proj, qkv) are independent and off the backward critical path.  Needs K[i] % 192 == 0. */
+int mofo_gemm_wgrad_grouped(int n, const mofo_bf16* const* dY, const int* ldy, const mofo_bf16* const* X, const int* ldx, int M,
+                            const int* N, const int* K, float* const* dW, const int* ldw, float* const* dbias,
+                            const int* dbias_skip_lo, const int* dbias_skip_hi, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (4) Fused multi-head attention, head_dim 64 (every registry model, modeling_pretrain.py:268-338).
  * Replaces Attention.forward lines modeling_finetune.py:85-95 (split heads, q*scale, softmax(q k^T), attn @ v,

@@ -28,6 +28,7 @@ SIGNATURES = {
     "mofo_gather_tubes": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_gemm_tn": ([_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _P, _I, _P, _I, _P, _P], C.c_int),
     "mofo_gemm_wgrad": ([_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P], C.c_int),
+    "mofo_gemm_wgrad_grouped": ([_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "mofo_attn_fwd": ([_P, _I, _I, _I, _F, _P, _P, _P, _P], C.c_int),
     "mofo_attn_bwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P], C.c_int),
     "mofo_layernorm_fwd": ([_P, _P, _P, _I, _I, _F, _I, _I, _I, _P, _P, _P, _P], C.c_int),
@@ -205,6 +206,29 @@ def gemm_wgrad(dY, X, dW, M=None, dbias=None, skip=(0, 0)):
 
 
 ATTN_SINGLE_PASS_MAX_S = 192      # sequences up to this length run the single-pass kernels (no out_lo, no delta pass)
+
+
+def gemm_wgrad_grouped(problems, M):
+    """problems: list (<= 4) of (dY, X, dW, dbias | None, (skip_lo, skip_hi)); every problem reduces over the same M rows.
+    One launch; falls back to individual mofo_gemm_wgrad calls when a shape does not fit the grouped kernel."""
+    n = len(problems)
+    if n == 0:
+        return
+    if n > 4 or any(X.shape[1] % 192 != 0 for _, X, _, _, _ in problems):
+        for dY, X, dW, dbias, skip in problems:
+            gemm_wgrad(dY, X, dW, M=M, dbias=dbias, skip=skip)
+        return
+    P_, I_ = C.c_void_p * n, C.c_int * n
+    for dY, X, dW, _, _ in problems:
+        assert dY.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dW.dtype == torch.float32
+        assert dY.stride(1) == 1 and X.stride(1) == 1 and dW.stride(-1) == 1 and dW.numel() == dY.shape[1] * X.shape[1]
+    _check(load().mofo_gemm_wgrad_grouped(
+        n, P_(*[_ptr(p[0]) for p in problems]), I_(*[p[0].stride(0) for p in problems]),
+        P_(*[_ptr(p[1]) for p in problems]), I_(*[p[1].stride(0) for p in problems]), M,
+        I_(*[p[0].shape[1] for p in problems]), I_(*[p[1].shape[1] for p in problems]),
+        P_(*[_ptr(p[2]) for p in problems]), I_(*[p[1].shape[1] for p in problems]),
+        P_(*[_ptr(p[3]) for p in problems]), I_(*[p[4][0] for p in problems]), I_(*[p[4][1] for p in problems]), _stream()),
+        "mofo_gemm_wgrad_grouped")
 
 
 def attn_fwd(qkv, B, S, H, scale, out, lse, out_lo=None):

@@ -604,9 +604,9 @@ struct WgCfg {
 };
 
 template <int BNW, int NT>
-__global__ void __launch_bounds__(WG_THREADS, 1)
-gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
-                  float* __restrict__ dW, int ldw, int kb_per_split, float* __restrict__ dbias, int skip_lo, int skip_hi) {
+__device__ __forceinline__ void wgrad_body(const CUtensorMap& tmY, const CUtensorMap& tmX, int M, int N, int K,
+                                           float* __restrict__ dW, int ldw, int kb_per_split, float* __restrict__ dbias,
+                                           int skip_lo, int skip_hi, int tile_idx, int split_idx) {
   using Cfg = WgCfg<BNW, NT>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BIAS_COL = NT * BNW;                    // first TMEM column of the bias-gradient accumulators
@@ -623,9 +623,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform role
   const int num_k = (K + BNW - 1) / BNW;
-  const int n_blk = blockIdx.x / num_k, k_blk = blockIdx.x % num_k;      // n_blk counts (NT*128)-row blocks
+  const int n_blk = tile_idx / num_k, k_blk = tile_idx % num_k;          // n_blk counts (NT*128)-row blocks
   const int kblocks_total = (M + BK - 1) / BK;
-  const int kb0 = blockIdx.y * kb_per_split;
+  const int kb0 = split_idx * kb_per_split;
   const int kb1 = min(kblocks_total, kb0 + kb_per_split);
   const int nkb = kb1 - kb0;   // >= 1 by construction of the grid
   // bias gradient = column sums of dY = dY^T · 1: one extra N=16 MMA per K-step against an all-ones tile, issued by
@@ -743,6 +743,40 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == WG_EPI_WARPS + 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BNW, int NT>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
+                  float* __restrict__ dW, int ldw, int kb_per_split, float* __restrict__ dbias, int skip_lo, int skip_hi) {
+  wgrad_body<BNW, NT>(tmY, tmX, M, N, K, dW, ldw, kb_per_split, dbias, skip_lo, skip_hi, blockIdx.x, blockIdx.y);
+}
+
+// Grouped launch: up to WG_MAX_GROUP independent weight-gradient problems with the same reduction length M in ONE grid
+// (blockIdx.x walks the concatenated tile lists, blockIdx.y the common M split).  The four weight gradients of a transformer
+// block are independent of each other and off the backward critical path; launched one by one at M = 5120 (the encoder)
+// each pays its own ramp-up / drain (~7 us of a ~25 us kernel) on a half-filled machine.
+constexpr int WG_MAX_GROUP = 4;
+struct WgProblem {
+  CUtensorMap tmY, tmX;
+  float* dW;
+  float* dbias;
+  int N, K, ldw, skip_lo, skip_hi, tile0;       // tile0: first blockIdx.x of this problem
+};
+struct WgGroup {
+  WgProblem p[WG_MAX_GROUP];
+  int n, M, kb_per_split;
+};
+
+template <int BNW>
+__global__ void __launch_bounds__(WG_THREADS, 1) gemm_wgrad_grouped_kernel(const __grid_constant__ WgGroup g) {
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < WG_MAX_GROUP; ++i)
+    if (i < g.n && static_cast<int>(blockIdx.x) >= g.p[i].tile0) pi = i;
+  const WgProblem& q = g.p[pi];
+  wgrad_body<BNW, 1>(q.tmY, q.tmX, g.M, q.N, q.K, q.dW, q.ldw, g.kb_per_split, q.dbias, q.skip_lo, q.skip_hi,
+                     static_cast<int>(blockIdx.x) - q.tile0, blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -971,6 +1005,48 @@ int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, i
   if (K % 256 == 0) return launch_wgrad<256, 1>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
   if (K % 192 == 0) return launch_wgrad<192, 1>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
   return launch_wgrad<128, 1>(tY, tX, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, s);
+}
+
+int mofo_gemm_wgrad_grouped(int n, const mofo_bf16* const* dY, const int* ldy, const mofo_bf16* const* X, const int* ldx, int M,
+                            const int* N, const int* K, float* const* dW, const int* ldw, float* const* dbias,
+                            const int* dbias_skip_lo, const int* dbias_skip_hi, void* stream) {
+  MOFO_CHECK_ARG(n >= 1 && n <= WG_MAX_GROUP && dY && X && N && K && dW && ldy && ldx && ldw && M > 0, "gemm_wgrad_grouped: bad argument (1..%d problems)", WG_MAX_GROUP);
+  constexpr int BNW = 192;
+  static WgGroup g;                      // ~1.3 KB: filled on the host, passed by value as the kernel parameter
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    MOFO_CHECK_ARG(dY[i] && X[i] && dW[i] && N[i] > 0 && K[i] > 0 && N[i] % 8 == 0 && K[i] % BNW == 0,
+                   "gemm_wgrad_grouped: problem %d: N=%d K=%d (need N%%8==0, K%%192==0)", i, N[i], K[i]);
+    MOFO_CHECK_ARG(ldy[i] >= N[i] && ldx[i] >= K[i] && ldy[i] % 8 == 0 && ldx[i] % 8 == 0 && ldw[i] >= K[i] && ldw[i] % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(dW[i]) & 15) == 0, "gemm_wgrad_grouped: problem %d: bad leading dimension / alignment", i);
+    int rc = get_tmap(&g.p[i].tmY, dY[i], M, N[i], ldy[i], 64);
+    if (rc) return rc;
+    rc = get_tmap(&g.p[i].tmX, X[i], M, K[i], ldx[i], 64);
+    if (rc) return rc;
+    g.p[i].dW = dW[i]; g.p[i].dbias = dbias ? dbias[i] : nullptr;
+    g.p[i].N = N[i]; g.p[i].K = K[i]; g.p[i].ldw = ldw[i];
+    g.p[i].skip_lo = dbias_skip_lo ? dbias_skip_lo[i] : 0; g.p[i].skip_hi = dbias_skip_hi ? dbias_skip_hi[i] : 0;
+    g.p[i].tile0 = tiles;
+    tiles += ((N[i] + 127) / 128) * (K[i] / BNW);
+  }
+  g.n = n; g.M = M;
+  const int kblocks = (M + BK - 1) / BK;
+  int splits = (2 * sm_count()) / tiles;                    // ~2 waves of equal-sized work items
+  if (splits < 1) splits = 1;
+  if (splits > kblocks) splits = kblocks;
+  g.kb_per_split = (kblocks + splits - 1) / splits;
+  splits = (kblocks + g.kb_per_split - 1) / g.kb_per_split;
+  using Cfg = WgCfg<BNW, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MOFO_CUDA(cudaFuncSetAttribute(gemm_wgrad_grouped_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  MOFO_CUDA(launch_pdl(gemm_wgrad_grouped_kernel<BNW>, dim3(tiles, splits), dim3(WG_THREADS), Cfg::SMEM_BYTES,
+                       static_cast<cudaStream_t>(stream), g));
+  return MOFO_OK;
 }
 
 }  // extern "C"

@@ -172,6 +172,9 @@ class _Runner:
         # tails.  Measured on B200 (B=32 ViT-B): 13.31 -> 13.27 ms/step, i.e. within run-to-run noise - a wgrad CTA
         # needs ~190 KB of shared memory and rarely finds an SM to co-reside on - so it is opt-in: MOFO_SIDE_WGRAD=1.
         self.side_wgrad = os.environ.get("MOFO_SIDE_WGRAD", "0") == "1"
+        # the four weight gradients of a block (fc2, fc1, proj, qkv) in ONE grouped launch at the end of the block's backward
+        # (their inputs are all still alive there); MOFO_GROUPED_WGRAD=0 launches them one by one where they arise
+        self.grouped_wgrad = os.environ.get("MOFO_GROUPED_WGRAD", "1") == "1" and not self.side_wgrad
         self._side = None
         self._side_dirty = False
         self._readers = {}          # data_ptr of a scratch tensor -> event after the side-stream wgrad that reads it
@@ -432,13 +435,21 @@ class _Runner:
         xm = self.buf(pre + ".xm", (M, D), f32)
         h2 = self.buf(pre + ".h2", (M, D), bf); mean2 = self.buf(pre + ".mean2", (M,), f32); rstd2 = self.buf(pre + ".rstd2", (M,), f32)
         u = self.buf(pre + ".u", (M, Dh), bf); a = self.buf(pre + ".a", (M, Dh), bf)
+        grouped = self.grouped_wgrad
+        wg = []                      # (dY, X, dW, dbias, skip) of this block, launched together below when grouped
+
+        def wgrad(reads, dY, X, dW, dbias=None, skip=(0, 0)):
+            if grouped:
+                wg.append((dY, X, dW, dbias, skip))
+            else:
+                self._wgrad(reads, dY, X, dW, dbias=dbias, skip=skip)
         # fc2
-        self._wgrad((dxA16,), dxA16, a, g[name + ".mlp.fc2.weight"], dbias=g[name + ".mlp.fc2.bias"])
+        wgrad((dxA16,), dxA16, a, g[name + ".mlp.fc2.weight"], dbias=g[name + ".mlp.fc2.bias"])
         du = self.buf("bwd.du", (M, Dh), bf)
         self._before_write(du)                                   # previous block's fc1 wgrad reads it
         _lib.gemm_tn(dxA16, wc[pre + ".fc2"][1], _lib.EPI_GELU_BWD_BF16, du, aux=u)
         # fc1
-        self._wgrad((du,), du, h2, g[name + ".mlp.fc1.weight"], dbias=g[name + ".mlp.fc1.bias"])
+        wgrad((du,), du, h2, g[name + ".mlp.fc1.weight"], dbias=g[name + ".mlp.fc1.bias"])
         dh = self.buf("bwd.dh", (M, D), bf)
         _lib.gemm_tn(du, wc[pre + ".fc1"][1], _lib.EPI_PLAIN_BF16, dh)
         # norm2 (+ residual gradient)
@@ -447,7 +458,7 @@ class _Runner:
                            g[name + ".norm2.bias"], group_rows=S if dp_attn is not None else 0,
                            in_group_rows=S if dp_attn is not None else 0, bf16_row_scale=dp_attn)
         # proj
-        self._wgrad((dxB16,), dxB16, o, g[name + ".attn.proj.weight"], dbias=g[name + ".attn.proj.bias"])
+        wgrad((dxB16,), dxB16, o, g[name + ".attn.proj.weight"], dbias=g[name + ".attn.proj.bias"])
         do = self.buf("bwd.do", (M, D), bf)
         _lib.gemm_tn(dxB16, wc[pre + ".proj"][1], _lib.EPI_PLAIN_BF16, do)
         # attention
@@ -459,8 +470,12 @@ class _Runner:
         # q_bias / v_bias gradients: column sums of dqkv[:, :D] and dqkv[:, 2D:], written through a [3D] window whose
         # first D floats are q_bias.grad and whose last D floats are v_bias.grad (see _make_arena: a D-float gap sits
         # between them in the arena so the window is contiguous); the K third is skipped.
-        self._wgrad((dqkv,), dqkv, h1, g[name + ".attn.qkv.weight"], dbias=g[name + ".attn.q_bias"], skip=(D, 2 * D))
+        wgrad((dqkv,), dqkv, h1, g[name + ".attn.qkv.weight"], dbias=g[name + ".attn.q_bias"], skip=(D, 2 * D))
         _lib.gemm_tn(dqkv, wc[pre + ".qkv"][1], _lib.EPI_PLAIN_BF16, dh)
+        if grouped:
+            # every operand of the four weight gradients is still alive here: dxA16 (this block's output gradient) is only
+            # overwritten by the norm1 backward below, du / dxB16 / dqkv by the NEXT block's backward
+            _lib.gemm_wgrad_grouped(wg, M)
         # norm1 (+ residual gradient)
         self._before_write(dxA16)                                # this block's fc2 wgrad
         _lib.layernorm_bwd(dh, x_in, blk.norm1.weight, mean1, rstd1, dxB, M, D, dxA, dxA16, g[name + ".norm1.weight"],

@@ -119,3 +119,30 @@ def test_gemm_rejects_bad_args(lib):
     out = torch.empty(64, 64, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(lib.MofoError):
         lib.gemm_tn(A, B, lib.EPI_PLAIN_BF16, out)      # K % 8 != 0
+
+
+@pytest.mark.parametrize("M,D", [(5120, 768), (6272, 384), (320, 192)])
+def test_gemm_wgrad_grouped_matches_individual_calls(lib, M, D):
+    """The four weight gradients of a transformer block in one grouped launch (fc2, fc1, proj, qkv with its skipped bias window)."""
+    torch.manual_seed(M + D)
+    t = lambda *s: torch.randn(*s, device="cuda").bfloat16()
+    dx, a, du, h2, dxb, o, dqkv, h1 = t(M, D), t(M, 4 * D), t(M, 4 * D), t(M, D), t(M, D), t(M, D), t(M, 3 * D), t(M, D)
+    shapes = [(D, 4 * D), (4 * D, D), (D, D), (3 * D, D)]
+    skips = [(0, 0), (0, 0), (0, 0), (D, 2 * D)]
+    pairs = [(dx, a), (du, h2), (dxb, o), (dqkv, h1)]
+    want_w = [torch.zeros(n, k, device="cuda") for n, k in shapes]; want_b = [torch.zeros(n, device="cuda") for n, _ in shapes]
+    for (dY, X), w, b, sk in zip(pairs, want_w, want_b, skips):
+        lib.gemm_wgrad(dY, X, w, dbias=b, skip=sk)
+    got_w = [torch.zeros(n, k, device="cuda") for n, k in shapes]; got_b = [torch.zeros(n, device="cuda") for n, _ in shapes]
+    lib.gemm_wgrad_grouped([(dY, X, w, b, sk) for (dY, X), w, b, sk in zip(pairs, got_w, got_b, skips)], M)
+    for i in range(4):
+        assert rel(got_w[i], want_w[i]) < 1e-5, i
+        assert rel(got_b[i], want_b[i]) < 1e-5, i
+        ref = pairs[i][0].float().t() @ pairs[i][1].float()
+        assert rel(got_w[i], ref) < 2e-5
+    assert got_b[3][D:2 * D].abs().max().item() == 0
+    # a shape the grouped kernel does not take (K % 192 != 0) falls back to individual launches
+    dY2, X2 = t(256, 128), t(256, 128)
+    w2 = torch.zeros(128, 128, device="cuda")
+    lib.gemm_wgrad_grouped([(dY2, X2, w2, None, (0, 0))], 256)
+    assert rel(w2, dY2.float().t() @ X2.float()) < 2e-5
