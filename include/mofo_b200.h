@@ -181,9 +181,17 @@ int mofo_zero_rows(float* x_f32, mofo_bf16* x_bf16, int groups, int group_rows, 
  * (16-byte aligned; deterministic: fixed summation order, no atomics).  bwd: dx[b, n, :] = dpooled[b, :] / N for every token, written as
  * f32 and / or bf16 [B*N, D] (either may be NULL) - the gradient entering the last transformer block.
  */
-int mofo_token_mean_fwd(const float* x, int B, int N, int D, float* pooled, void* stream);
-int mofo_token_mean_bwd(const float* dpooled, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16,
+int mofo_token_mean_fwd(const float* x, const float* weights /* f32 [B,N] or NULL (= 1/N) */, int B, int N, int D, float* pooled,
+                        void* stream);
+int mofo_token_mean_bwd(const float* dpooled, const float* weights, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16,
                         const float* bf16_row_scale /* f32 [B] or NULL: bf16 copy = bf16(scale[b] * dx) */, void* stream);
+
+/* (6c) Box-focused pooling of VisionTransformer_BB_focused (modeling_finetune.py:589-630 and 555-585): inbox u8 [B, N] = the
+ * tokens whose tube touches the per-frame box (boxes int64 [B, frames, 4] = x1,y1,x2,y2 with Python-slice semantics) - the
+ * closed form of the reference's all-ones Conv3d over a painted clip - and weights f32 [B, N] (may be NULL) such that
+ * sum_n weights[b,n] * x[b,n,:] is the pooled feature: mode 0 ('org') the plain mean, mode 1 ('weighted_mean')
+ * (mean_in + 0.5 * mean_out) / 2, the plain mean when no token is in the box. */
+int mofo_box_tokens(const int64_t* boxes, int B, int frames, int size, int mode, uint8_t* inbox, float* weights, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (7) Target + loss (engine_for_pretraining.py:258-304): un-normalise with ImageNet mean/std (:260-265), patchify

@@ -36,8 +36,9 @@ SIGNATURES = {
     "mofo_decoder_assemble_fwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "mofo_decoder_assemble_bwd": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
     "mofo_zero_rows": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
-    "mofo_token_mean_fwd": ([_P, _I, _I, _I, _P, _P], C.c_int),
-    "mofo_token_mean_bwd": ([_P, _I, _I, _I, _P, _P, _P, _P], C.c_int),
+    "mofo_token_mean_fwd": ([_P, _P, _I, _I, _I, _P, _P], C.c_int),
+    "mofo_token_mean_bwd": ([_P, _P, _I, _I, _I, _P, _P, _P, _P], C.c_int),
+    "mofo_box_tokens": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
     "mofo_target_mse": ([_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P], C.c_int),
     "mofo_cast_weight": ([_P, _I, _I, _P, _P, _P], C.c_int),
     "mofo_pack_qkv_bias": ([_P, _P, _I, _P, _P], C.c_int),
@@ -277,15 +278,26 @@ def zero_rows(x_f32, x_bf16, groups, group_rows, n_zero, D):
     _check(load().mofo_zero_rows(_ptr(x_f32), _ptr(x_bf16), groups, group_rows, n_zero, D, _stream()), "mofo_zero_rows")
 
 
-def token_mean_fwd(x, B, N, D, pooled):
-    """pooled f32 [B, D] = mean over tokens of x f32 [B*N, D]."""
-    _check(load().mofo_token_mean_fwd(_ptr(x), B, N, D, _ptr(pooled), _stream()), "mofo_token_mean_fwd")
+def token_mean_fwd(x, B, N, D, pooled, weights=None):
+    """pooled f32 [B, D] = sum_n weights[b, n] * x[b*N + n] (weights None: the plain mean over tokens)."""
+    _check(load().mofo_token_mean_fwd(_ptr(x), _ptr(weights), B, N, D, _ptr(pooled), _stream()), "mofo_token_mean_fwd")
     return pooled
 
 
-def token_mean_bwd(dpooled, B, N, D, dx_f32, dx_bf16, bf16_row_scale=None):
-    _check(load().mofo_token_mean_bwd(_ptr(dpooled), B, N, D, _ptr(dx_f32), _ptr(dx_bf16), _ptr(bf16_row_scale), _stream()),
-           "mofo_token_mean_bwd")
+def token_mean_bwd(dpooled, B, N, D, dx_f32, dx_bf16, bf16_row_scale=None, weights=None):
+    _check(load().mofo_token_mean_bwd(_ptr(dpooled), _ptr(weights), B, N, D, _ptr(dx_f32), _ptr(dx_bf16), _ptr(bf16_row_scale),
+                                      _stream()), "mofo_token_mean_bwd")
+
+
+def box_tokens(boxes, frames, size, mode, want_weights=True):
+    """boxes int64 [B, frames, 4] (CUDA) -> (inbox u8 [B, N], weights f32 [B, N] | None)."""
+    assert boxes.dtype == torch.int64 and boxes.is_cuda and boxes.is_contiguous() and boxes.shape[1:] == (frames, 4)
+    B = boxes.shape[0]
+    N = (frames // 2) * (size // 16) ** 2
+    inbox = torch.empty(B, N, dtype=torch.uint8, device=boxes.device)
+    weights = torch.empty(B, N, dtype=torch.float32, device=boxes.device) if want_weights else None
+    _check(load().mofo_box_tokens(_ptr(boxes), B, frames, size, mode, _ptr(inbox), _ptr(weights), _stream()), "mofo_box_tokens")
+    return inbox, weights
 
 
 def target_mse(video, msk_idx, pred, loss_partials, loss, dpred, normalize_target=True, grad_scale=1.0,

@@ -493,8 +493,8 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ f32,
 // independent 16-byte loads in flight each; the row groups are combined in a FIXED order through shared memory, so the
 // result is deterministic (no atomics: a mean that feeds a LayerNorm amplifies last-bit noise).
 constexpr int TM_RG = 8;
-__global__ void __launch_bounds__(256) token_mean_fwd_kernel(const float* __restrict__ x, int N, int D, float inv_n,
-                                                             float* __restrict__ out) {
+__global__ void __launch_bounds__(256) token_mean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wts, int N,
+                                                             int D, float inv_n, float* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
   __shared__ float4 part[TM_RG][32];
@@ -504,15 +504,21 @@ __global__ void __launch_bounds__(256) token_mean_fwd_kernel(const float* __rest
   float4 acc = make_float4(0, 0, 0, 0);
   if (c < C4) {
     const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * N * D) + c;
+    const float* wb = wts ? wts + static_cast<size_t>(b) * N : nullptr;     // per-token weights (box-focused pooling) or plain mean
     for (int r = ry; r < N; r += 4 * TM_RG) {
       float4 v[4];
+      float wv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int rr = r + u * TM_RG;
         v[u] = rr < N ? src[static_cast<size_t>(rr) * C4] : make_float4(0, 0, 0, 0);
+        wv[u] = rr < N ? (wb ? __ldg(wb + rr) : inv_n) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+      for (int u = 0; u < 4; ++u) {
+        acc.x = fmaf(wv[u], v[u].x, acc.x); acc.y = fmaf(wv[u], v[u].y, acc.y);
+        acc.z = fmaf(wv[u], v[u].z, acc.z); acc.w = fmaf(wv[u], v[u].w, acc.w);
+      }
     }
   }
   part[ry][threadIdx.x] = acc;
@@ -523,14 +529,13 @@ __global__ void __launch_bounds__(256) token_mean_fwd_kernel(const float* __rest
       const float4 o = part[g][threadIdx.x];
       acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
     }
-    acc.x *= inv_n; acc.y *= inv_n; acc.z *= inv_n; acc.w *= inv_n;
     reinterpret_cast<float4*>(out + static_cast<size_t>(b) * D)[c] = acc;
   }
 }
 
 // dx[b, n, :] = dpooled[b, :] / N for every token n (f32 and / or bf16 copy), 16 bytes per thread and iteration
-__global__ void __launch_bounds__(256) token_mean_bwd_kernel(const float* __restrict__ dpooled, int N, int D, float inv_n,
-                                                             int64_t total4, float* __restrict__ dx_f32,
+__global__ void __launch_bounds__(256) token_mean_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ wts,
+                                                             int N, int D, float inv_n, int64_t total4, float* __restrict__ dx_f32,
                                                              __nv_bfloat16* __restrict__ dx_bf16,
                                                              const float* __restrict__ bf16_row_scale) {
   pdl_wait();
@@ -541,13 +546,64 @@ __global__ void __launch_bounds__(256) token_mean_bwd_kernel(const float* __rest
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int b = static_cast<int>(i / per_clip), c = static_cast<int>(i % C4);
     float4 v = __ldg(reinterpret_cast<const float4*>(dpooled + static_cast<size_t>(b) * D) + c);
-    v.x *= inv_n; v.y *= inv_n; v.z *= inv_n; v.w *= inv_n;
+    const float wn = wts ? __ldg(wts + i / C4) : inv_n;          // i / C4 = b * N + n
+    v.x *= wn; v.y *= wn; v.z *= wn; v.w *= wn;
     if (dx_f32) reinterpret_cast<float4*>(dx_f32)[i] = v;
     if (dx_bf16) {
       const float sc = bf16_row_scale ? __ldg(bf16_row_scale + b) : 1.0f;
       uint2 p; p.x = pack_bf16(v.x * sc, v.y * sc); p.y = pack_bf16(v.z * sc, v.w * sc);
       reinterpret_cast<uint2*>(dx_bf16)[i] = p;
     }
+  }
+}
+
+// =================================================================================================
+// (6c) tokens inside the motion box (box-focused classifier)  — modeling_finetune.py:589-630, 555-585
+// =================================================================================================
+// The reference paints the box of every frame into an all-zero clip, runs an all-ones Conv3d (patch_yab) over it, averages
+// the (identical) channels, clamps to [0,1] and casts to bool: a tube is "in the box" iff ANY pixel of either of its two
+// frames lies inside that frame's box.  Closed form: per frame j, [16h, 16h+16) x [16w, 16w+16) intersects the slice
+// [y1:y2) x [x1:x2) (Python slice semantics: negative bounds count from the end, all bounds clamp to [0, size]).
+// weights (fusing 'weighted_mean', :571-572): (mean_in * 1 + mean_out * 0.5) / 2 -> 0.5 / n_in for tokens in the box,
+// 0.25 / n_out for the others; no token in the box -> plain mean (:560-562); fusing 'org' (mode 0): plain mean.  n_out = 0
+// gives NaN in the reference (mean of an empty selection) and here.
+__device__ __forceinline__ int py_slice_bound(long long v, int size) {
+  if (v < 0) { v += size; if (v < 0) v = 0; }
+  if (v > size) v = size;
+  return static_cast<int>(v);
+}
+__global__ void __launch_bounds__(256) box_tokens_kernel(const long long* __restrict__ boxes, int frames, int size, int mode,
+                                                         uint8_t* __restrict__ inbox, float* __restrict__ weights) {
+  __shared__ int cnt_s[8];
+  __shared__ int n_in_s;
+  const int b = blockIdx.x;
+  const int hw = size >> 4, N = (frames >> 1) * hw * hw;
+  int cnt = 0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const int t = n / (hw * hw), h = (n / hw) % hw, w = n % hw;
+    bool in = false;
+#pragma unroll
+    for (int p0 = 0; p0 < 2; ++p0) {
+      const long long* bb = boxes + (static_cast<size_t>(b) * frames + 2 * t + p0) * 4;
+      const int x1 = py_slice_bound(bb[0], size), y1 = py_slice_bound(bb[1], size);
+      const int x2 = py_slice_bound(bb[2], size), y2 = py_slice_bound(bb[3], size);
+      in = in || (max(16 * h, y1) < min(16 * h + 16, y2) && max(16 * w, x1) < min(16 * w + 16, x2));
+    }
+    inbox[static_cast<size_t>(b) * N + n] = in ? 1 : 0;
+    cnt += in ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) cnt_s[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) { int s = 0; for (int i = 0; i < (blockDim.x >> 5); ++i) s += cnt_s[i]; n_in_s = s; }
+  __syncthreads();
+  if (weights == nullptr) return;
+  const int n_in = n_in_s, n_out = N - n_in;
+  const float w_in = (mode == 0 || n_in == 0) ? 1.0f / N : __fdiv_rn(0.5f, static_cast<float>(n_in));
+  const float w_out = (mode == 0 || n_in == 0) ? 1.0f / N : (n_out == 0 ? __int_as_float(0x7fc00000) : __fdiv_rn(0.25f, static_cast<float>(n_out)));
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const bool in = inbox[static_cast<size_t>(b) * N + n] != 0;
+    weights[static_cast<size_t>(b) * N + n] = (n_out == 0 && mode != 0 && n_in != 0) ? __int_as_float(0x7fc00000) : (in ? w_in : w_out);
   }
 }
 
@@ -1033,6 +1089,14 @@ int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk,
   return MOFO_OK;
 }
 
+int mofo_box_tokens(const int64_t* boxes, int B, int frames, int size, int mode, uint8_t* inbox, float* weights, void* stream) {
+  MOFO_CHECK_ARG(boxes && inbox, "box_tokens: null pointer");
+  MOFO_CHECK_ARG(B > 0 && frames > 0 && frames % 2 == 0 && size > 0 && size % 16 == 0 && (mode == 0 || mode == 1), "box_tokens: bad argument");
+  box_tokens_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(boxes), frames, size, mode, inbox, weights);
+  MOFO_LAUNCH_CHECK("box_tokens_kernel");
+  return MOFO_OK;
+}
+
 int mofo_zero_rows(float* x_f32, mofo_bf16* x_bf16, int groups, int group_rows, int n_zero, int D, void* stream) {
   MOFO_CHECK_ARG(x_f32 || x_bf16, "zero_rows: null pointer");
   MOFO_CHECK_ARG(groups > 0 && group_rows > 0 && n_zero >= 0 && n_zero <= group_rows && D > 0 && D % 4 == 0, "zero_rows: bad shape");
@@ -1045,16 +1109,16 @@ int mofo_zero_rows(float* x_f32, mofo_bf16* x_bf16, int groups, int group_rows, 
   return MOFO_OK;
 }
 
-int mofo_token_mean_fwd(const float* x, int B, int N, int D, float* pooled, void* stream) {
+int mofo_token_mean_fwd(const float* x, const float* weights, int B, int N, int D, float* pooled, void* stream) {
   MOFO_CHECK_ARG(x && pooled, "token_mean_fwd: null pointer");
   MOFO_CHECK_ARG(B > 0 && B <= 65535 && N > 0 && D > 0 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(pooled) & 15) == 0,
                  "token_mean_fwd: bad shape B=%d N=%d D=%d", B, N, D);
   dim3 grid(((D >> 2) + 31) / 32, B);
-  MOFO_CUDA(launch_pdl(token_mean_fwd_kernel, grid, dim3(32, TM_RG), 0, static_cast<cudaStream_t>(stream), x, N, D, 1.0f / N, pooled));
+  MOFO_CUDA(launch_pdl(token_mean_fwd_kernel, grid, dim3(32, TM_RG), 0, static_cast<cudaStream_t>(stream), x, weights, N, D, 1.0f / N, pooled));
   return MOFO_OK;
 }
 
-int mofo_token_mean_bwd(const float* dpooled, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16,
+int mofo_token_mean_bwd(const float* dpooled, const float* weights, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16,
                         const float* bf16_row_scale, void* stream) {
   MOFO_CHECK_ARG(dpooled && (dx_f32 || dx_bf16), "token_mean_bwd: null pointer");
   MOFO_CHECK_ARG(B > 0 && N > 0 && D > 0 && D % 4 == 0, "token_mean_bwd: bad shape B=%d N=%d D=%d", B, N, D);
@@ -1062,7 +1126,7 @@ int mofo_token_mean_bwd(const float* dpooled, int B, int N, int D, float* dx_f32
   int64_t blocks = (total4 + 255) / 256;
   if (blocks > 16L * sm_count()) blocks = 16L * sm_count();
   MOFO_CUDA(launch_pdl(token_mean_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream),
-                       dpooled, N, D, 1.0f / N, total4, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), bf16_row_scale));
+                       dpooled, weights, N, D, 1.0f / N, total4, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), bf16_row_scale));
   return MOFO_OK;
 }
 

@@ -31,7 +31,8 @@ import torch.nn as nn
 from . import _lib
 from .modeling_pretrain import _Block, _PatchEmbed, _Runner, _trunc_normal_, get_sinusoid_encoding_table
 
-__all__ = ["VisionTransformer", "vit_small_patch16_224", "vit_base_patch16_224", "vit_large_patch16_224", "create_model"]
+__all__ = ["VisionTransformer", "VisionTransformer_BB_focused", "vit_small_patch16_224", "vit_base_patch16_224",
+           "vit_base_patch16_224_BB_focused", "vit_large_patch16_224", "create_model"]
 
 
 class _FtRunner(_Runner):
@@ -49,9 +50,13 @@ class _FtRunner(_Runner):
             self.arena = None; self.arena_views = None; self.scratch_arena = None
             self.pos = self.m.pos_embed[0].to(device).contiguous()
 
+    def _named(self):
+        skip = getattr(self.m, "_unused_prefixes", ())
+        return [(n, p) for n, p in self.m.named_parameters() if not n.startswith(skip)] if skip else list(self.m.named_parameters())
+
     def backward_order(self):
         m = self.m
-        names = dict(m.named_parameters())
+        names = dict(self._named())
         order, stage_of = [], {}
 
         def add(prefix, stage):
@@ -108,10 +113,12 @@ class _FtRunner(_Runner):
         hb[:C].copy_(m.head.bias.detach())
 
     # ---- forward ------------------------------------------------------------------------------------------
-    def forward(self, x):
+    def forward(self, x, pool_weights=None):
+        """``pool_weights``: None (mean over tokens, :400) or f32 [B, N] per-token weights of the box-focused pooling."""
         m = self.m
         self._ensure_device(x.device)
         self.prepare_weights()
+        self.pool_weights = pool_weights
         bf, f32 = torch.bfloat16, torch.float32
         B = x.shape[0]
         N = m.patch_embed.num_patches
@@ -142,7 +149,7 @@ class _FtRunner(_Runner):
         self.x_out = xe
         # norm = Identity, fc_norm(x.mean(1)), head  (:398-401, 405-406)
         pooled = self.buf("pooled", (B, D), f32)
-        _lib.token_mean_fwd(xe, B, N, D, pooled)
+        _lib.token_mean_fwd(xe, B, N, D, pooled, weights=pool_weights)
         hn = self.buf("fc.hn", (B, D), bf); mean = self.buf("fc.mean", (B,), f32); rstd = self.buf("fc.rstd", (B,), f32)
         _lib.layernorm_fwd(pooled, m.fc_norm.weight, m.fc_norm.bias, hn, mean, rstd, B, D, m.fc_norm.eps)
         logits = self.buf("logits", (B, self.c_pad), f32)
@@ -179,7 +186,8 @@ class _FtRunner(_Runner):
         dxB = self.buf("bwd.dxB", (B * N, D), f32); dxB16 = self.buf("bwd.dxB16", (B * N, D), bf)
         nb = len(m.blocks)
         dp = self.dp
-        _lib.token_mean_bwd(dpooled, B, N, D, dxA, dxA16, bf16_row_scale=dp[2 * nb - 1] if dp is not None else None)
+        _lib.token_mean_bwd(dpooled, B, N, D, dxA, dxA16, bf16_row_scale=dp[2 * nb - 1] if dp is not None else None,
+                            weights=self.pool_weights)
         for i in range(nb - 1, -1, -1):
             x_in = self.buf("x0", (B * N, D), f32) if i == 0 else self.buf(f"blk{i - 1}.xo", (B * N, D), f32)
             self._block_bwd(f"blk{i}", m.blocks[i], g, x_in, dxA, dxA16, dxB, dxB16, B * N, N, B, D,
@@ -192,8 +200,8 @@ class _FtRunner(_Runner):
 
 class _FtForwardFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner, x, *params):
-        logits = runner.forward(x)
+    def forward(ctx, runner, x, pool_weights, *params):
+        logits = runner.forward(x, pool_weights)
         ctx.runner = runner
         return logits[:, :runner.m.num_classes].clone()
 
@@ -205,7 +213,7 @@ class _FtForwardFn(torch.autograd.Function):
         arena, views = r.scratch_arena
         arena.zero_()
         r.backward(dlogits.float().contiguous(), views)
-        return (None, None) + tuple(views[n] for n, _ in r.m.named_parameters())
+        return (None, None, None) + tuple(views[n] for n, _ in r._named())
 
 
 class VisionTransformer(nn.Module):
@@ -279,11 +287,97 @@ class VisionTransformer(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("mofo_b200.VisionTransformer runs on CUDA (sm_100a) only; there is no CPU path")
         x = x.float().contiguous()
+        return self._run(x, None)
+
+    def _run(self, x, pool_weights):
         r = self._runner
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return _FtForwardFn.apply(r, x, *self.parameters())
+            return _FtForwardFn.apply(r, x, pool_weights, *[p for _, p in r._named()])
         with torch.no_grad():
-            return r.forward(x)[:, :self.num_classes].clone()
+            return r.forward(x, pool_weights)[:, :self.num_classes].clone()
+
+
+# ---- parameter holders of the box-focused classifier's fusing modules (names / shapes / init of modeling_finetune.py:100-191,
+# 264-303): present so that state_dict round-trips with the reference; their forward paths ('soft_attn', 'MCA') are not built
+class _SoftAttention(nn.Module):
+    def __init__(self, feature_dim, step_dim, bias=True):
+        super().__init__()
+        weight = torch.zeros(feature_dim, 1)
+        nn.init.kaiming_uniform_(weight)
+        self.weight = nn.Parameter(weight)
+        if bias:
+            self.b = nn.Parameter(torch.zeros(step_dim))
+
+
+class _CrossAttention(nn.Module):
+    def __init__(self, dim, num_heads, qkv_bias):
+        super().__init__()
+        self.q = nn.Linear(dim, dim, bias=False)
+        self.kv = nn.Linear(dim, dim * 2, bias=False)
+        if qkv_bias:
+            self.q_bias = nn.Parameter(torch.zeros(dim))
+            self.v_bias = nn.Parameter(torch.zeros(dim))
+        self.proj = nn.Linear(dim, dim)
+
+
+class _MCA(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio, qkv_bias, norm_layer):
+        super().__init__()
+        from .modeling_pretrain import _Mlp
+        self.norm1 = norm_layer(dim)
+        self.attn = _CrossAttention(dim, num_heads, qkv_bias)
+        self.norm2 = norm_layer(dim)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+
+
+class VisionTransformer_BB_focused(VisionTransformer):
+    """Box-focused classifier (modeling_finetune.py:422-635), ``forward(x, BB)`` with ``BB`` int [B, frames, 4].
+
+    Built: the token-in-box predicate (closed form of the reference's all-ones ``patch_yab`` Conv3d over a painted clip,
+    ``mofo_box_tokens``, integer-exact) and the fusing methods ``'org'`` and ``'weighted_mean'`` (the constructor default) as a
+    per-token weighted pooling inside the same kernel pipeline.  ``'soft_attn'`` and ``'MCA'`` (cross-attention with 256-wide
+    heads over ragged token sets, the finetuning script's default) raise ``NotImplementedError``; their parameters are held so
+    that checkpoints round-trip."""
+
+    _unused_prefixes = ("soft_att_local", "soft_att_global", "local_MCA", "global_MCA", "patch_yab")
+
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
+                 mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.,
+                 norm_layer=nn.LayerNorm, init_values=0., use_learnable_pos_emb=False, init_scale=0., all_frames=16,
+                 tubelet_size=2, use_mean_pooling=True, fusing_method='weighted_mean'):
+        if fusing_method not in ("org", "weighted_mean"):
+            raise NotImplementedError(f"mofo_b200 box-focused classifier implements fusing_method 'org' and 'weighted_mean' (got {fusing_method!r})")
+        super().__init__(img_size, patch_size, in_chans, num_classes, embed_dim, depth, num_heads, mlp_ratio, qkv_bias, qk_scale,
+                         drop_rate, attn_drop_rate, drop_path_rate, norm_layer, init_values, use_learnable_pos_emb, 1.0,
+                         all_frames, tubelet_size, use_mean_pooling)
+        self.fusing_method = fusing_method
+        self.in_chans = in_chans
+        self.soft_att_local = _SoftAttention(embed_dim, 1)
+        self.soft_att_global = _SoftAttention(embed_dim, 1)
+        self.local_MCA = nn.ModuleList([_MCA(embed_dim, 3, mlp_ratio, qkv_bias, norm_layer)])
+        self.global_MCA = nn.ModuleList([_MCA(embed_dim, 3, mlp_ratio, qkv_bias, norm_layer)])
+        for mod in (self.local_MCA, self.global_MCA):
+            mod.apply(self._init_weights)
+        self.head.weight.data.mul_(init_scale)          # the base constructor ran with init_scale 1 (:504-505 scale AFTER all inits)
+        self.head.bias.data.mul_(init_scale)
+        self.patch_yab = nn.Conv3d(in_chans, embed_dim, kernel_size=(tubelet_size, patch_size, patch_size),
+                                   stride=(tubelet_size, patch_size, patch_size))
+        self.patch_yab.weight.data.fill_(1)
+        self.patch_yab.bias.data.fill_(0)
+        self._runner = _FtRunner(self)
+
+    def tokens_in_box(self, BB, frames, size):
+        """bool [B, N]: what the reference's ``x_patch_yabide`` holds (:589-630)."""
+        bb = torch.as_tensor(BB).to(device=self.head.weight.device, dtype=torch.int64).contiguous()
+        return _lib.box_tokens(bb, frames, size, 0, want_weights=False)[0].bool()
+
+    def forward(self, x, BB):
+        if not x.is_cuda:
+            raise RuntimeError("mofo_b200.VisionTransformer_BB_focused runs on CUDA (sm_100a) only; there is no CPU path")
+        x = x.float().contiguous()
+        bb = torch.as_tensor(BB).to(device=x.device, dtype=torch.int64).contiguous()
+        _, weights = _lib.box_tokens(bb, x.shape[2], x.shape[3], 0 if self.fusing_method == "org" else 1)
+        return self._run(x, weights)
 
 
 _REGISTRY = {}
@@ -309,6 +403,12 @@ def vit_small_patch16_224(pretrained=False, **kwargs):
 def vit_base_patch16_224(pretrained=False, **kwargs):
     return VisionTransformer(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True,
                              norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+@_register
+def vit_base_patch16_224_BB_focused(pretrained=False, **kwargs):
+    return VisionTransformer_BB_focused(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                                        norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
 
 
 @_register

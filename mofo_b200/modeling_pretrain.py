@@ -281,8 +281,12 @@ class _Runner:
         assert len(order) == len(names)
         return order, stage_of, last + 1
 
+    def _named(self):
+        """(name, parameter) pairs the kernels produce gradients for (subclasses exclude parameters their path never touches)."""
+        return list(self.m.named_parameters())
+
     def _make_arena(self):
-        params = dict(self.m.named_parameters())
+        params = dict(self._named())
         order, stage_of, n_stages = self.backward_order()
         total = sum((params[n].numel() + 3) // 4 * 4 * (2 if n.endswith(".attn.q_bias") else 1) for n in order)  # 16-B aligned
         arena = torch.zeros(total, dtype=torch.float32, device=self.device)
@@ -303,7 +307,7 @@ class _Runner:
         directly usable for bucketed NCCL all-reduce)."""
         if self.arena is None:
             self.arena, self.arena_views = self._make_arena()
-        for n, p in self.m.named_parameters():
+        for n, p in self._named():
             v = self.arena_views[n]
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v

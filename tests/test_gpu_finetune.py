@@ -187,3 +187,72 @@ def test_reference_finetuning_engine_drives_the_b200_classifier():
     print(f"after {steps} steps of the reference finetuning engine: eval loss reference {la:.4f}, ours {lb:.4f}")
     assert abs(la - lb) <= 3e-2 * abs(la)
     assert ((a - b).norm() / a.norm()).item() < 0.1
+
+
+@pytest.mark.parametrize("fusing", ["weighted_mean", "org"])
+def test_box_focused_classifier_matches_reference(fusing):
+    """VisionTransformer_BB_focused.forward(x, BB): the token-in-box predicate is bit-equal to the reference's patch_yab
+    construction (all-ones Conv3d over a painted clip), logits and gradients follow the reference; parameters of the fusing
+    modules that the chosen method never touches get no gradient on either side."""
+    refrun = _refrun()
+    ref = refrun.load()
+    from mofo_b200 import modeling_finetune as mf
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(21)
+    B, classes = 4, 97
+    kw = dict(num_classes=classes, all_frames=16, tubelet_size=2, drop_rate=0.0, drop_path_rate=0.0, attn_drop_rate=0.0,
+              use_mean_pooling=True, init_scale=1.0, fusing_method=fusing)
+    ref_model = ref.modeling_finetune.vit_base_patch16_224_BB_focused(pretrained=False, **kw).to(dev).train()
+    ours = mf.create_model("vit_base_patch16_224_BB_focused", pretrained=False, drop_block_rate=None, **kw)
+    ours.load_state_dict(ref_model.state_dict(), strict=True)
+    ours = ours.to(dev).train()
+    x = refrun.synthetic_batches(B, 1, seed=19, device=dev)[0][0]
+    y = torch.randint(0, classes, (B,), device=dev)
+    g = torch.Generator().manual_seed(4)
+    x1 = torch.randint(0, 150, (B, 16, 1), generator=g); y1 = torch.randint(0, 150, (B, 16, 1), generator=g)
+    BB = torch.cat([x1, y1, x1 + torch.randint(1, 74, (B, 16, 1), generator=g), y1 + torch.randint(1, 74, (B, 16, 1), generator=g)], 2)
+    BB[1] = torch.tensor([10, 10, 10, 40])                       # empty box: no token inside -> plain mean (:560-562)
+    BB[2, :, :] = torch.tensor([0, 0, 224, 100])
+    BB = BB.to(dev)
+    # the reference's predicate, as modeling_finetune.py:589-630 builds it
+    with torch.no_grad():
+        x_new = torch.zeros_like(x)
+        for i in range(B):
+            for j in range(16):
+                x_new[i, :, j, BB[i, j, 1]:BB[i, j, 3], BB[i, j, 0]:BB[i, j, 2]] = 1
+        want = torch.clamp(ref_model.patch_yab(x_new).flatten(2).transpose(1, 2).mean(2), 0, 1).type(torch.bool)
+    got = ours.tokens_in_box(BB, 16, 224)
+    assert torch.equal(got, want)
+    assert int(want[1].sum()) == 0 and 0 < int(want[0].sum()) < 1568
+
+    def ref_step(amp):
+        ref_model.zero_grad(set_to_none=True)
+        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                logits = ref_model(x, BB)
+                loss = torch.nn.functional.cross_entropy(logits.float(), y)
+            loss.backward()
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        return logits.detach().float(), {n: (p.grad.detach().clone() if p.grad is not None else None) for n, p in ref_model.named_parameters()}
+    l32, g32 = ref_step(False)
+    l16, g16 = ref_step(True)
+    logits = ours(x, BB)
+    torch.nn.functional.cross_entropy(logits, y).backward()
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300)).item()
+    e, r = rel(logits.detach(), l32), rel(l16, l32)
+    print(f"box-focused ({fusing}): logits rel {e:.3e} (reference bf16 {r:.3e})")
+    assert e <= max(2e-2, 2.5 * r)
+    bad = []
+    for n, p in ours.named_parameters():
+        if g32[n] is None:
+            assert p.grad is None, n
+            continue
+        ee, rr = rel(p.grad, g32[n]), rel(g16[n], g32[n])
+        if ee > max(3e-2, 2.5 * rr):
+            bad.append((n, ee, rr))
+    assert not bad, bad[:8]

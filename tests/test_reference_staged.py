@@ -112,3 +112,22 @@ def test_finetune_classifier_schema_matches_reference():
         mf.create_model("vit_small_patch16_224", num_classes=174, drop_rate=0.1)
     with pytest.raises(RuntimeError):
         om(torch.zeros(1, 3, 16, 224, 224))
+
+
+def test_box_focused_classifier_schema_matches_reference():
+    """VisionTransformer_BB_focused (modeling_finetune.py:422-635): all 196 state_dict keys (incl. the fusing modules whose
+    forward paths are not built) in the reference's order and shapes; unsupported fusing methods are refused."""
+    refrun = _refrun()
+    ref = refrun.load()
+    from mofo_b200 import modeling_finetune as mf
+    kw = dict(num_classes=97, all_frames=16, tubelet_size=2, drop_path_rate=0.1, use_mean_pooling=True, init_scale=0.001)
+    rm = ref.modeling_finetune.vit_base_patch16_224_BB_focused(pretrained=False, fusing_method="weighted_mean", **kw)
+    om = mf.create_model("vit_base_patch16_224_BB_focused", pretrained=False, drop_block_rate=None, fusing_method="weighted_mean", **kw)
+    sd = rm.state_dict()
+    assert list(sd.keys()) == list(om.state_dict().keys())
+    assert all(tuple(sd[k].shape) == tuple(v.shape) for k, v in om.state_dict().items())
+    om.load_state_dict(sd, strict=True)
+    assert torch.equal(om.patch_yab.weight, torch.ones_like(om.patch_yab.weight))
+    for bad in ("MCA", "soft_attn"):
+        with pytest.raises(NotImplementedError):
+            mf.create_model("vit_base_patch16_224_BB_focused", num_classes=97, fusing_method=bad)
