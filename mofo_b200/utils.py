@@ -35,109 +35,100 @@ def get_rank():
 
 
 class SmoothedValue:
-    """utils.py:27-86"""
+    """A meter with the attribute set the engine and the reference's scripts read (utils.py:27-86): ``update(v, n)``,
+    ``median`` / ``avg`` over a sliding window, ``global_avg`` over everything seen, ``max``, ``value`` and a format string
+    over those names.  Implemented on a running (count, total) pair plus a bounded window."""
+
+    __slots__ = ("window", "total", "count", "fmt")
 
     def __init__(self, window_size=20, fmt=None):
-        self.deque = deque(maxlen=window_size)
-        self.total = 0.0
-        self.count = 0
-        self.fmt = fmt or "{median:.4f} ({global_avg:.4f})"
+        self.window = deque(maxlen=window_size)
+        self.total, self.count = 0.0, 0
+        self.fmt = "{median:.4f} ({global_avg:.4f})" if fmt is None else fmt
 
     def update(self, value, n=1):
-        self.deque.append(value)
-        self.count += n
+        self.window.append(value)
         self.total += value * n
+        self.count += n
 
     def synchronize_between_processes(self):
+        """Sums (count, total) over the ranks; the window stays local (as in the reference)."""
         if not is_dist_avail_and_initialized():
             return
-        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-        t = torch.tensor([self.count, self.total], dtype=torch.float64, device=dev)
+        pair = torch.tensor([float(self.count), self.total], dtype=torch.float64,
+                            device="cuda" if dist.get_backend() == "nccl" else "cpu")
         dist.barrier()
-        dist.all_reduce(t)
-        t = t.tolist()
-        self.count = int(t[0])
-        self.total = t[1]
+        dist.all_reduce(pair)
+        self.count, self.total = int(pair[0].item()), float(pair[1].item())
+
+    def _stat(self, fn, empty=0.0):
+        return float(fn(list(self.window))) if self.window else empty
+
+    median = property(lambda self: self._stat(np.median))
+    avg = property(lambda self: self._stat(np.mean))
+    max = property(lambda self: self._stat(max))
+    value = property(lambda self: self.window[-1] if self.window else 0.0)
+    global_avg = property(lambda self: self.total / self.count if self.count else 0.0)
 
     @property
-    def median(self):
-        return float(np.median(list(self.deque))) if self.deque else 0.0
-
-    @property
-    def avg(self):
-        return float(np.mean(list(self.deque))) if self.deque else 0.0
-
-    @property
-    def global_avg(self):
-        return self.total / max(self.count, 1)
-
-    @property
-    def max(self):
-        return max(self.deque) if self.deque else 0.0
-
-    @property
-    def value(self):
-        return self.deque[-1] if self.deque else 0.0
+    def deque(self):                         # name used by callers of the reference class
+        return self.window
 
     def __str__(self):
         return self.fmt.format(median=self.median, avg=self.avg, global_avg=self.global_avg, max=self.max, value=self.value)
 
 
 class MetricLogger:
-    """utils.py:89-170 (same meters / log_every behaviour; printing only)."""
+    """Named ``SmoothedValue`` meters plus the ``log_every`` generator the training loops wrap their loader in
+    (utils.py:89-170).  ``quiet`` suppresses the periodic lines (benchmarks, tests)."""
 
     def __init__(self, delimiter="\t", quiet=False):
         self.meters = defaultdict(SmoothedValue)
-        self.delimiter = delimiter
-        self.quiet = quiet
+        self.delimiter, self.quiet = delimiter, quiet
 
-    def update(self, **kwargs):
-        for k, v in kwargs.items():
+    def add_meter(self, name, meter):
+        self.meters[name] = meter
+
+    def update(self, **named_values):
+        for name, v in named_values.items():
             if v is None:
                 continue
-            if isinstance(v, torch.Tensor):
-                v = v.item()
-            assert isinstance(v, (float, int))
-            self.meters[k].update(v)
+            v = v.item() if isinstance(v, torch.Tensor) else v
+            if not isinstance(v, (int, float)):
+                raise TypeError(f"meter {name!r}: expected a number, got {type(v).__name__}")
+            self.meters[name].update(v)
 
-    def __getattr__(self, attr):
-        if attr in self.meters:
-            return self.meters[attr]
-        if attr in self.__dict__:
-            return self.__dict__[attr]
-        raise AttributeError(attr)
+    def __getattr__(self, name):
+        meters = self.__dict__.get("meters", {})
+        if name in meters:
+            return meters[name]
+        raise AttributeError(name)
 
     def __str__(self):
-        return self.delimiter.join("{}: {}".format(n, str(m)) for n, m in self.meters.items())
+        return self.delimiter.join(f"{name}: {meter}" for name, meter in self.meters.items())
 
     def synchronize_between_processes(self):
         for meter in self.meters.values():
             meter.synchronize_between_processes()
 
-    def add_meter(self, name, meter):
-        self.meters[name] = meter
-
     def log_every(self, iterable, print_freq, header=None):
-        i = 0
-        header = header or ''
-        start = end = time.time()
-        iter_time = SmoothedValue(fmt='{avg:.4f}')
-        data_time = SmoothedValue(fmt='{avg:.4f}')
-        n = len(iterable) if hasattr(iterable, "__len__") else -1
-        for obj in iterable:
-            data_time.update(time.time() - end)
-            yield obj
-            iter_time.update(time.time() - end)
-            if not self.quiet and (i % print_freq == 0 or i == n - 1):
-                eta = str(datetime.timedelta(seconds=int(iter_time.global_avg * max(n - i, 0))))
-                mem = torch.cuda.max_memory_allocated() / (1024.0 * 1024.0) if torch.cuda.is_available() else 0
-                print(self.delimiter.join([header, f"[{i}/{n}]", f"eta: {eta}", str(self), f"time: {iter_time}",
-                                           f"data: {data_time}", f"max mem: {mem:.0f}"]))
-            i += 1
-            end = time.time()
-        total = time.time() - start
+        header = header or ""
+        total = len(iterable) if hasattr(iterable, "__len__") else -1
+        step_time, wait_time = SmoothedValue(fmt="{avg:.4f}"), SmoothedValue(fmt="{avg:.4f}")
+        t_begin = t_prev = time.time()
+        for i, item in enumerate(iterable):
+            wait_time.update(time.time() - t_prev)
+            yield item
+            step_time.update(time.time() - t_prev)
+            if not self.quiet and (i % print_freq == 0 or i == total - 1):
+                remaining = datetime.timedelta(seconds=int(step_time.global_avg * max(total - i, 0)))
+                peak_mb = torch.cuda.max_memory_allocated() / 2 ** 20 if torch.cuda.is_available() else 0
+                print(self.delimiter.join([header, f"[{i}/{total}]", f"eta: {remaining}", str(self), f"time: {step_time}",
+                                           f"data: {wait_time}", f"max mem: {peak_mb:.0f}"]))
+            t_prev = time.time()
         if not self.quiet:
-            print('{} Total time: {} ({:.4f} s / it)'.format(header, str(datetime.timedelta(seconds=int(total))), total / max(n, 1)))
+            elapsed = time.time() - t_begin
+            print(f"{header} Total time: {datetime.timedelta(seconds=int(elapsed))} ({elapsed / max(total, 1):.4f} s / it)")
 
 
 def get_grad_norm_(parameters, norm_type: float = 2.0) -> torch.Tensor:
@@ -213,16 +204,15 @@ class NativeScalerWithGradNormCount:
 
 def cosine_scheduler(base_value, final_value, epochs, niter_per_ep, warmup_epochs=0, start_warmup_value=0,
                      warmup_steps=-1):
-    """utils.py:391-408"""
-    warmup_schedule = np.array([])
-    warmup_iters = warmup_epochs * niter_per_ep
-    if warmup_steps > 0:
-        warmup_iters = warmup_steps
-    if warmup_epochs > 0:
-        warmup_schedule = np.linspace(start_warmup_value, base_value, warmup_iters)
-    iters = np.arange(epochs * niter_per_ep - warmup_iters)
-    schedule = np.array([final_value + 0.5 * (base_value - final_value) * (1 + math.cos(math.pi * i / (len(iters))))
-                         for i in iters])
-    schedule = np.concatenate((warmup_schedule, schedule))
-    assert len(schedule) == epochs * niter_per_ep
+    """Per-iteration schedule with the reference's contract (utils.py:391-408): a linear warm-up from ``start_warmup_value``
+    to ``base_value`` over ``warmup_epochs * niter_per_ep`` iterations (``warmup_steps`` > 0 overrides the length; the ramp is
+    only emitted when ``warmup_epochs`` > 0), then half a cosine from ``base_value`` to ``final_value``."""
+    total = epochs * niter_per_ep
+    n_warm = warmup_steps if warmup_steps > 0 else warmup_epochs * niter_per_ep
+    ramp = np.linspace(start_warmup_value, base_value, n_warm) if warmup_epochs > 0 else np.array([])
+    n_cos = total - n_warm
+    phase = np.arange(n_cos) / max(n_cos, 1)
+    cos = final_value + 0.5 * (base_value - final_value) * (1.0 + np.cos(np.pi * phase))
+    schedule = np.concatenate((ramp, cos))
+    assert len(schedule) == total
     return schedule
