@@ -190,7 +190,8 @@ int mofo_token_mean_bwd(const float* dpooled, const float* weights, int B, int N
  * tokens whose tube touches the per-frame box (boxes int64 [B, frames, 4] = x1,y1,x2,y2 with Python-slice semantics) - the
  * closed form of the reference's all-ones Conv3d over a painted clip - and weights f32 [B, N] (may be NULL) such that
  * sum_n weights[b,n] * x[b,n,:] is the pooled feature: mode 0 ('org') the plain mean, mode 1 ('weighted_mean')
- * (mean_in + 0.5 * mean_out) / 2, the plain mean when no token is in the box. */
+ * (mean_in + 0.5 * mean_out) / 2, mode 2 ('soft_attn' as written, :282-303: its broadcast reduces to) mean_in + mean_out;
+ * the plain mean when no token is in the box. */
 int mofo_box_tokens(const int64_t* boxes, int B, int frames, int size, int mode, uint8_t* inbox, float* weights, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -564,9 +564,13 @@ __global__ void __launch_bounds__(256) token_mean_bwd_kernel(const float* __rest
 // the (identical) channels, clamps to [0,1] and casts to bool: a tube is "in the box" iff ANY pixel of either of its two
 // frames lies inside that frame's box.  Closed form: per frame j, [16h, 16h+16) x [16w, 16w+16) intersects the slice
 // [y1:y2) x [x1:x2) (Python slice semantics: negative bounds count from the end, all bounds clamp to [0, size]).
-// weights (fusing 'weighted_mean', :571-572): (mean_in * 1 + mean_out * 0.5) / 2 -> 0.5 / n_in for tokens in the box,
+// weights (fusing 'weighted_mean', mode 1, :571-572): (mean_in * 1 + mean_out * 0.5) / 2 -> 0.5 / n_in for tokens in the box,
 // 0.25 / n_out for the others; no token in the box -> plain mean (:560-562); fusing 'org' (mode 0): plain mean.  n_out = 0
 // gives NaN in the reference (mean of an empty selection) and here.
+// mode 2 = fusing 'soft_attn' (:573-574) AS WRITTEN: SoftAttention.forward (:282-303) multiplies x [n, c] by a [n, 1, 1], which
+// broadcasts to [n, n, c]; summing dim 1 and then taking .mean(0) leaves (sum_i a_i) * mean_j x_j, and the a_i are
+// normalised to sum to 1 - so the module returns the plain mean of its token set and the fused feature is
+// mean_in + mean_out (weights 1 / n_in and 1 / n_out); its own parameters receive a mathematically zero gradient.
 __device__ __forceinline__ int py_slice_bound(long long v, int size) {
   if (v < 0) { v += size; if (v < 0) v = 0; }
   if (v > size) v = size;
@@ -599,8 +603,9 @@ __global__ void __launch_bounds__(256) box_tokens_kernel(const long long* __rest
   __syncthreads();
   if (weights == nullptr) return;
   const int n_in = n_in_s, n_out = N - n_in;
-  const float w_in = (mode == 0 || n_in == 0) ? 1.0f / N : __fdiv_rn(0.5f, static_cast<float>(n_in));
-  const float w_out = (mode == 0 || n_in == 0) ? 1.0f / N : (n_out == 0 ? __int_as_float(0x7fc00000) : __fdiv_rn(0.25f, static_cast<float>(n_out)));
+  const float num_in = mode == 2 ? 1.0f : 0.5f, num_out = mode == 2 ? 1.0f : 0.25f;
+  const float w_in = (mode == 0 || n_in == 0) ? 1.0f / N : __fdiv_rn(num_in, static_cast<float>(n_in));
+  const float w_out = (mode == 0 || n_in == 0) ? 1.0f / N : (n_out == 0 ? __int_as_float(0x7fc00000) : __fdiv_rn(num_out, static_cast<float>(n_out)));
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     const bool in = inbox[static_cast<size_t>(b) * N + n] != 0;
     weights[static_cast<size_t>(b) * N + n] = (n_out == 0 && mode != 0 && n_in != 0) ? __int_as_float(0x7fc00000) : (in ? w_in : w_out);
@@ -1091,7 +1096,7 @@ int mofo_decoder_assemble_bwd(const float* dx_full, int B, int n_vis, int n_msk,
 
 int mofo_box_tokens(const int64_t* boxes, int B, int frames, int size, int mode, uint8_t* inbox, float* weights, void* stream) {
   MOFO_CHECK_ARG(boxes && inbox, "box_tokens: null pointer");
-  MOFO_CHECK_ARG(B > 0 && frames > 0 && frames % 2 == 0 && size > 0 && size % 16 == 0 && (mode == 0 || mode == 1), "box_tokens: bad argument");
+  MOFO_CHECK_ARG(B > 0 && frames > 0 && frames % 2 == 0 && size > 0 && size % 16 == 0 && mode >= 0 && mode <= 2, "box_tokens: bad argument");
   box_tokens_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(boxes), frames, size, mode, inbox, weights);
   MOFO_LAUNCH_CHECK("box_tokens_kernel");
   return MOFO_OK;

@@ -334,19 +334,22 @@ class VisionTransformer_BB_focused(VisionTransformer):
     """Box-focused classifier (modeling_finetune.py:422-635), ``forward(x, BB)`` with ``BB`` int [B, frames, 4].
 
     Built: the token-in-box predicate (closed form of the reference's all-ones ``patch_yab`` Conv3d over a painted clip,
-    ``mofo_box_tokens``, integer-exact) and the fusing methods ``'org'`` and ``'weighted_mean'`` (the constructor default) as a
-    per-token weighted pooling inside the same kernel pipeline.  ``'soft_attn'`` and ``'MCA'`` (cross-attention with 256-wide
-    heads over ragged token sets, the finetuning script's default) raise ``NotImplementedError``; their parameters are held so
-    that checkpoints round-trip."""
+    ``mofo_box_tokens``, integer-exact) and the fusing methods ``'org'``, ``'weighted_mean'`` (the constructor default) and
+    ``'soft_attn'`` as a per-token weighted pooling inside the same kernel pipeline.  (``'soft_attn'`` as the reference WRITES
+    it reduces to mean_in + mean_out: SoftAttention's [n,c] * [n,1,1] broadcast followed by sum(1).mean(0) leaves
+    (sum_i a_i) * mean(x) with sum_i a_i = 1, so its own parameters get a mathematically zero gradient - none here.)
+    ``'MCA'`` (cross-attention with 256-wide heads over ragged per-clip token sets, the finetuning script's default) raises
+    ``NotImplementedError``; its parameters are held so that checkpoints round-trip."""
 
     _unused_prefixes = ("soft_att_local", "soft_att_global", "local_MCA", "global_MCA", "patch_yab")
+    _FUSING = {"org": 0, "weighted_mean": 1, "soft_attn": 2}     # -> mofo_box_tokens mode
 
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
                  mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.,
                  norm_layer=nn.LayerNorm, init_values=0., use_learnable_pos_emb=False, init_scale=0., all_frames=16,
                  tubelet_size=2, use_mean_pooling=True, fusing_method='weighted_mean'):
-        if fusing_method not in ("org", "weighted_mean"):
-            raise NotImplementedError(f"mofo_b200 box-focused classifier implements fusing_method 'org' and 'weighted_mean' (got {fusing_method!r})")
+        if fusing_method not in self._FUSING:
+            raise NotImplementedError(f"mofo_b200 box-focused classifier implements fusing_method {sorted(self._FUSING)} (got {fusing_method!r})")
         super().__init__(img_size, patch_size, in_chans, num_classes, embed_dim, depth, num_heads, mlp_ratio, qkv_bias, qk_scale,
                          drop_rate, attn_drop_rate, drop_path_rate, norm_layer, init_values, use_learnable_pos_emb, 1.0,
                          all_frames, tubelet_size, use_mean_pooling)
@@ -376,7 +379,7 @@ class VisionTransformer_BB_focused(VisionTransformer):
             raise RuntimeError("mofo_b200.VisionTransformer_BB_focused runs on CUDA (sm_100a) only; there is no CPU path")
         x = x.float().contiguous()
         bb = torch.as_tensor(BB).to(device=x.device, dtype=torch.int64).contiguous()
-        _, weights = _lib.box_tokens(bb, x.shape[2], x.shape[3], 0 if self.fusing_method == "org" else 1)
+        _, weights = _lib.box_tokens(bb, x.shape[2], x.shape[3], self._FUSING[self.fusing_method])
         return self._run(x, weights)
 
 

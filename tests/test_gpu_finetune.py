@@ -189,7 +189,7 @@ def test_reference_finetuning_engine_drives_the_b200_classifier():
     assert ((a - b).norm() / a.norm()).item() < 0.1
 
 
-@pytest.mark.parametrize("fusing", ["weighted_mean", "org"])
+@pytest.mark.parametrize("fusing", ["weighted_mean", "org", "soft_attn"])
 def test_box_focused_classifier_matches_reference(fusing):
     """VisionTransformer_BB_focused.forward(x, BB): the token-in-box predicate is bit-equal to the reference's patch_yab
     construction (all-ones Conv3d over a painted clip), logits and gradients follow the reference; parameters of the fusing
@@ -251,6 +251,9 @@ def test_box_focused_classifier_matches_reference(fusing):
     for n, p in ours.named_parameters():
         if g32[n] is None:
             assert p.grad is None, n
+            continue
+        if n.startswith("soft_att"):                 # 'soft_attn': a mathematically zero gradient (rounding noise in the reference)
+            assert p.grad is None and g32[n].abs().max().item() < 1e-6, (n, g32[n].abs().max().item())
             continue
         ee, rr = rel(p.grad, g32[n]), rel(g16[n], g32[n])
         if ee > max(3e-2, 2.5 * rr):

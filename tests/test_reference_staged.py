@@ -128,6 +128,6 @@ def test_box_focused_classifier_schema_matches_reference():
     assert all(tuple(sd[k].shape) == tuple(v.shape) for k, v in om.state_dict().items())
     om.load_state_dict(sd, strict=True)
     assert torch.equal(om.patch_yab.weight, torch.ones_like(om.patch_yab.weight))
-    for bad in ("MCA", "soft_attn"):
+    for bad in ("MCA",):
         with pytest.raises(NotImplementedError):
             mf.create_model("vit_base_patch16_224_BB_focused", num_classes=97, fusing_method=bad)
