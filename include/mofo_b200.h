@@ -186,6 +186,18 @@ int mofo_token_mean_fwd(const float* x, const float* weights /* f32 [B,N] or NUL
 int mofo_token_mean_bwd(const float* dpooled, const float* weights, int B, int N, int D, float* dx_f32, mofo_bf16* dx_bf16,
                         const float* bf16_row_scale /* f32 [B] or NULL: bf16 copy = bf16(scale[b] * dx) */, void* stream);
 
+/* (6d) Key-masked softmax for the cross attention of VisionTransformer_BB_focused, fusing 'MCA' (modeling_finetune.py:100-160,
+ * 575-583): queries = the tokens in the box, keys / values = the tokens outside it, 3 heads of embed_dim / 3 (256).  The
+ * score and value products run as mofo_gemm_tn / mofo_gemm_wgrad calls on per-clip, per-head views; these two kernels sit
+ * between them.  fwd: P bf16 [B * rows_per_b, Nk] = softmax over k of scale * S f32 (`q * self.scale`, :150) restricted to
+ * the keys with key_allowed u8 [B, Nk] != 0, exactly 0 elsewhere.  bwd: dS = scale * P * (dP - sum_k P * dP).
+ * Nk % 4 == 0, Nk <= 2048.  mofo_cast_f32_bf16: strided f32 -> bf16 copy (the f32 dK / dV the wgrad kernel accumulates -> the
+ * bf16 operand of the next GEMM). */
+int mofo_masked_softmax_fwd(const float* S, const uint8_t* key_allowed, int B, int rows_per_b, int Nk, float scale, mofo_bf16* P,
+                            void* stream);
+int mofo_masked_softmax_bwd(const mofo_bf16* P, const float* dP, int64_t rows, int Nk, float scale, mofo_bf16* dS, void* stream);
+int mofo_cast_f32_bf16(const float* src, int lds, int M, int N, mofo_bf16* dst, int ldd, void* stream);
+
 /* (6c) Box-focused pooling of VisionTransformer_BB_focused (modeling_finetune.py:589-630 and 555-585): inbox u8 [B, N] = the
  * tokens whose tube touches the per-frame box (boxes int64 [B, frames, 4] = x1,y1,x2,y2 with Python-slice semantics) - the
  * closed form of the reference's all-ones Conv3d over a painted clip - and weights f32 [B, N] (may be NULL) such that

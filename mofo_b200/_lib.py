@@ -39,6 +39,9 @@ SIGNATURES = {
     "mofo_token_mean_fwd": ([_P, _P, _I, _I, _I, _P, _P], C.c_int),
     "mofo_token_mean_bwd": ([_P, _P, _I, _I, _I, _P, _P, _P, _P], C.c_int),
     "mofo_box_tokens": ([_P, _I, _I, _I, _I, _P, _P, _P], C.c_int),
+    "mofo_masked_softmax_fwd": ([_P, _P, _I, _I, _I, _F, _P, _P], C.c_int),
+    "mofo_masked_softmax_bwd": ([_P, _P, C.c_int64, _I, _F, _P, _P], C.c_int),
+    "mofo_cast_f32_bf16": ([_P, _I, _I, _I, _P, _I, _P], C.c_int),
     "mofo_target_mse": ([_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P], C.c_int),
     "mofo_cast_weight": ([_P, _I, _I, _P, _P, _P], C.c_int),
     "mofo_pack_qkv_bias": ([_P, _P, _I, _P, _P], C.c_int),
@@ -200,8 +203,13 @@ def gemm_wgrad(dY, X, dW, M=None, dbias=None, skip=(0, 0)):
     M = dY.shape[0] if M is None else M
     N, K = dY.shape[1], X.shape[1]
     assert dY.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dW.dtype == torch.float32
-    assert dY.stride(1) == 1 and X.stride(1) == 1 and dW.stride(-1) == 1 and dW.numel() == N * K
-    _check(load().mofo_gemm_wgrad(_ptr(dY), dY.stride(0), _ptr(X), X.stride(0), M, N, K, _ptr(dW), K, _ptr(dbias),
+    assert dY.stride(1) == 1 and X.stride(1) == 1 and dW.stride(-1) == 1
+    ldw = K
+    if dW.dim() == 2 and dW.shape == (N, K):           # may be a column slice of a wider f32 matrix
+        ldw = dW.stride(0)
+    else:
+        assert dW.numel() == N * K and dW.is_contiguous()
+    _check(load().mofo_gemm_wgrad(_ptr(dY), dY.stride(0), _ptr(X), X.stride(0), M, N, K, _ptr(dW), ldw, _ptr(dbias),
                                   skip[0], skip[1], _stream()), "mofo_gemm_wgrad")
     return dW
 
@@ -298,6 +306,34 @@ def box_tokens(boxes, frames, size, mode, want_weights=True):
     weights = torch.empty(B, N, dtype=torch.float32, device=boxes.device) if want_weights else None
     _check(load().mofo_box_tokens(_ptr(boxes), B, frames, size, mode, _ptr(inbox), _ptr(weights), _stream()), "mofo_box_tokens")
     return inbox, weights
+
+
+def masked_softmax_fwd(S, key_allowed, scale, P):
+    """P bf16 [B, ..., Nq, Nk] = softmax_k(scale * S) over the keys with key_allowed u8 [B, Nk] != 0 (0 elsewhere); S f32, same shape."""
+    B, Nk = key_allowed.shape
+    assert S.dtype == torch.float32 and P.dtype == torch.bfloat16 and key_allowed.dtype == torch.uint8
+    assert S.is_contiguous() and P.is_contiguous() and key_allowed.is_contiguous() and S.shape == P.shape and S.shape[0] == B and S.shape[-1] == Nk
+    _check(load().mofo_masked_softmax_fwd(_ptr(S), _ptr(key_allowed), B, S.numel() // (B * Nk), Nk, float(scale), _ptr(P), _stream()),
+           "mofo_masked_softmax_fwd")
+    return P
+
+
+def masked_softmax_bwd(P, dP, scale, dS):
+    """dS bf16 = scale * P * (dP - sum_k P * dP) row by row; P bf16, dP f32, all [..., Nk] contiguous."""
+    assert P.dtype == torch.bfloat16 and dP.dtype == torch.float32 and dS.dtype == torch.bfloat16
+    assert P.is_contiguous() and dP.is_contiguous() and dS.is_contiguous() and P.shape == dP.shape == dS.shape
+    Nk = P.shape[-1]
+    _check(load().mofo_masked_softmax_bwd(_ptr(P), _ptr(dP), P.numel() // Nk, Nk, float(scale), _ptr(dS), _stream()), "mofo_masked_softmax_bwd")
+    return dS
+
+
+def cast_f32_bf16(src, dst):
+    """dst bf16 [M, N] = src f32 [M, N]; either may be a column slice (row stride > N)."""
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.shape == dst.shape and src.dim() == 2
+    assert src.stride(1) == 1 and dst.stride(1) == 1
+    _check(load().mofo_cast_f32_bf16(_ptr(src), src.stride(0), src.shape[0], src.shape[1], _ptr(dst), dst.stride(0), _stream()),
+           "mofo_cast_f32_bf16")
+    return dst
 
 
 def target_mse(video, msk_idx, pred, loss_partials, loss, dpred, normalize_target=True, grad_scale=1.0,

@@ -487,6 +487,128 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ f32,
 }
 
 // =================================================================================================
+// (6d) key-masked softmax of the box-focused classifier's cross attention  - modeling_finetune.py:125-160 (CrossAttention:
+// queries = tokens in the box, keys / values = tokens outside it; 3 heads of 256, so the score rows do not fit the 64-wide
+// attention kernels and the products run as tcgen05 GEMMs with these two kernels between them)
+// =================================================================================================
+// One CTA of 128 threads per score row; a thread owns up to MS_CHUNKS float4 column chunks (Nk <= 2048, Nk % 4 == 0), so a
+// row is read once, reduced in registers / two block reductions, and written once.
+constexpr int MS_THREADS = 128, MS_CHUNKS = 4;
+
+template <bool MAX>
+__device__ __forceinline__ float ms_block_reduce(float v, float* red) {
+  v = MAX ? warp_max(v) : warp_sum(v);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();                                   // red may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < MS_THREADS / 32; ++i) r = MAX ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+// P[row, k] = softmax_k(scale * S[row, k]) over the keys with allowed[b, k] != 0, exactly 0 elsewhere; rows = B * rows_per_b
+__global__ void __launch_bounds__(MS_THREADS) masked_softmax_fwd_kernel(const float* __restrict__ S, const uint8_t* __restrict__ allowed,
+                                                                        int rows_per_b, int Nk, float scale,
+                                                                        __nv_bfloat16* __restrict__ P) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[MS_THREADS / 32];
+  const size_t row = blockIdx.x;
+  const int b = static_cast<int>(row / rows_per_b);
+  const float4* src = reinterpret_cast<const float4*>(S + row * Nk);
+  const uchar4* al = reinterpret_cast<const uchar4*>(allowed + static_cast<size_t>(b) * Nk);
+  const int C4 = Nk >> 2;
+  float4 v[MS_CHUNKS];
+  const float ninf = __int_as_float(0xff800000);
+  float mx = ninf;
+#pragma unroll
+  for (int i = 0; i < MS_CHUNKS; ++i) {
+    const int c = threadIdx.x + i * MS_THREADS;
+    v[i] = make_float4(ninf, ninf, ninf, ninf);
+    if (c < C4) {
+      const float4 x = src[c];
+      const uchar4 a = __ldg(al + c);
+      v[i].x = a.x ? x.x * scale : ninf; v[i].y = a.y ? x.y * scale : ninf;
+      v[i].z = a.z ? x.z * scale : ninf; v[i].w = a.w ? x.w * scale : ninf;
+    }
+    mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+  }
+  mx = ms_block_reduce<true>(mx, red);
+  if (mx == ninf) mx = 0.f;                          // no key allowed (the host never passes such a row): all-zero row, no NaN
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MS_CHUNKS; ++i) {
+    v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx); v[i].z = expf(v[i].z - mx); v[i].w = expf(v[i].w - mx);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  sum = ms_block_reduce<false>(sum, red);
+  const float inv = sum > 0.f ? __fdividef(1.0f, sum) : 0.f;
+  uint2* dst = reinterpret_cast<uint2*>(P + row * Nk);
+#pragma unroll
+  for (int i = 0; i < MS_CHUNKS; ++i) {
+    const int c = threadIdx.x + i * MS_THREADS;
+    if (c < C4) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x * inv, v[i].y * inv), hi = __floats2bfloat162_rn(v[i].z * inv, v[i].w * inv);
+      dst[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+  }
+}
+
+// dS[row, k] = scale * P * (dP - sum_k P * dP)   (softmax backward with the 1/sqrt(d) of `q * scale` folded in)
+__global__ void __launch_bounds__(MS_THREADS) masked_softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP,
+                                                                        int Nk, float scale, __nv_bfloat16* __restrict__ dS) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[MS_THREADS / 32];
+  const size_t row = blockIdx.x;
+  const uint2* ps = reinterpret_cast<const uint2*>(P + row * Nk);
+  const float4* ds = reinterpret_cast<const float4*>(dP + row * Nk);
+  const int C4 = Nk >> 2;
+  float4 p[MS_CHUNKS], g[MS_CHUNKS];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < MS_CHUNKS; ++i) {
+    const int c = threadIdx.x + i * MS_THREADS;
+    p[i] = make_float4(0, 0, 0, 0); g[i] = make_float4(0, 0, 0, 0);
+    if (c < C4) {
+      const uint2 w = ps[c];
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+      const float2 bb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+      p[i] = make_float4(a.x, a.y, bb.x, bb.y);
+      g[i] = ds[c];
+    }
+    dot += (p[i].x * g[i].x + p[i].y * g[i].y) + (p[i].z * g[i].z + p[i].w * g[i].w);
+  }
+  dot = ms_block_reduce<false>(dot, red);
+  uint2* dst = reinterpret_cast<uint2*>(dS + row * Nk);
+#pragma unroll
+  for (int i = 0; i < MS_CHUNKS; ++i) {
+    const int c = threadIdx.x + i * MS_THREADS;
+    if (c < C4) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(scale * p[i].x * (g[i].x - dot), scale * p[i].y * (g[i].y - dot));
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(scale * p[i].z * (g[i].z - dot), scale * p[i].w * (g[i].w - dot));
+      dst[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+  }
+}
+
+// dst bf16 [M, N] (row stride ldd) = src f32 [M, N] (row stride lds); 4 elements per thread
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, int lds, int64_t total4, int N4,
+                                                            __nv_bfloat16* __restrict__ dst, int ldd) {
+  pdl_wait();
+  pdl_trigger();
+  for (int64_t i = blockIdx.x * 256L + threadIdx.x; i < total4; i += gridDim.x * 256L) {
+    const int64_t r = i / N4;
+    const int c = static_cast<int>(i - r * N4) * 4;
+    const float4 x = *reinterpret_cast<const float4*>(src + r * lds + c);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+    *reinterpret_cast<uint2*>(dst + r * ldd + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+  }
+}
+
+// =================================================================================================
 // (6b) token mean pooling (finetuning classifier)  — modeling_finetune.py:400-401  fc_norm(x.mean(1))
 // =================================================================================================
 // grid = (column blocks of 128, B), block (32, 8): lane = one float4 column chunk, 8 row groups stream the N rows with 4
@@ -1132,6 +1254,39 @@ int mofo_token_mean_bwd(const float* dpooled, const float* weights, int B, int N
   if (blocks > 16L * sm_count()) blocks = 16L * sm_count();
   MOFO_CUDA(launch_pdl(token_mean_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream),
                        dpooled, weights, N, D, 1.0f / N, total4, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16), bf16_row_scale));
+  return MOFO_OK;
+}
+
+int mofo_masked_softmax_fwd(const float* S, const uint8_t* key_allowed, int B, int rows_per_b, int Nk, float scale, mofo_bf16* P,
+                            void* stream) {
+  MOFO_CHECK_ARG(S && key_allowed && P, "masked_softmax_fwd: null pointer");
+  MOFO_CHECK_ARG(B > 0 && rows_per_b > 0 && Nk > 0 && Nk % 4 == 0 && Nk <= 4 * MS_THREADS * MS_CHUNKS &&
+                 static_cast<int64_t>(B) * rows_per_b < (1LL << 31) && (reinterpret_cast<uintptr_t>(S) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(P) & 7) == 0 && (reinterpret_cast<uintptr_t>(key_allowed) & 3) == 0,
+                 "masked_softmax_fwd: bad shape B=%d rows=%d Nk=%d (Nk %% 4 == 0, <= %d)", B, rows_per_b, Nk, 4 * MS_THREADS * MS_CHUNKS);
+  MOFO_CUDA(launch_pdl(masked_softmax_fwd_kernel, dim3(static_cast<unsigned>(B) * rows_per_b), dim3(MS_THREADS), 0,
+                       static_cast<cudaStream_t>(stream), S, key_allowed, rows_per_b, Nk, scale, reinterpret_cast<__nv_bfloat16*>(P)));
+  return MOFO_OK;
+}
+
+int mofo_masked_softmax_bwd(const mofo_bf16* P, const float* dP, int64_t rows, int Nk, float scale, mofo_bf16* dS, void* stream) {
+  MOFO_CHECK_ARG(P && dP && dS, "masked_softmax_bwd: null pointer");
+  MOFO_CHECK_ARG(rows > 0 && rows < (1LL << 31) && Nk > 0 && Nk % 4 == 0 && Nk <= 4 * MS_THREADS * MS_CHUNKS &&
+                 (reinterpret_cast<uintptr_t>(dP) & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 7) == 0 &&
+                 (reinterpret_cast<uintptr_t>(dS) & 7) == 0, "masked_softmax_bwd: bad shape rows=%lld Nk=%d", static_cast<long long>(rows), Nk);
+  MOFO_CUDA(launch_pdl(masked_softmax_bwd_kernel, dim3(static_cast<unsigned>(rows)), dim3(MS_THREADS), 0, static_cast<cudaStream_t>(stream),
+                       reinterpret_cast<const __nv_bfloat16*>(P), dP, Nk, scale, reinterpret_cast<__nv_bfloat16*>(dS)));
+  return MOFO_OK;
+}
+
+int mofo_cast_f32_bf16(const float* src, int lds, int M, int N, mofo_bf16* dst, int ldd, void* stream) {
+  MOFO_CHECK_ARG(src && dst && M > 0 && N > 0 && N % 4 == 0 && lds >= N && ldd >= N && lds % 4 == 0 && ldd % 4 == 0 &&
+                 (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "cast_f32_bf16: bad argument");
+  const int64_t total4 = static_cast<int64_t>(M) * (N >> 2);
+  int64_t blocks = (total4 + 255) / 256;
+  if (blocks > 16L * sm_count()) blocks = 16L * sm_count();
+  MOFO_CUDA(launch_pdl(cast_f32_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, lds,
+                       total4, N >> 2, reinterpret_cast<__nv_bfloat16*>(dst), ldd));
   return MOFO_OK;
 }
 

@@ -17,8 +17,9 @@ one ``autograd.Function`` whose backward is the manual kernel backward, so the r
 DropPath (the finetuning recipe's 0.1, modeling_finetune.py:20-31): the per-sample keep / scale factor of each residual
 branch rides in the residual GEMM's epilogue (``row_scale``) and, in backward, on the bf16 gradient copy the branch's
 GEMMs read (``bf16_row_scale`` of the LayerNorm backward / token-mean backward).
-Not implemented (raises): dropout, ``init_values`` > 0, learnable position embedding, ``use_mean_pooling=False``; the
-box-focused classifier ``VisionTransformer_BB_focused`` (:422-635) is out of scope of this round.
+``VisionTransformer_BB_focused`` (:422-635, ``forward(x, BB)``) pools the same encoder by the motion box, with every fusing
+method the reference runs ('org', 'weighted_mean', 'soft_attn', 'MCA' - see the class).
+Not implemented (raises): dropout, ``init_values`` > 0, learnable position embedding, ``use_mean_pooling=False``.
 """
 from __future__ import annotations
 
@@ -63,7 +64,7 @@ class _FtRunner(_Runner):
             for n in names:
                 if (n == prefix or n.startswith(prefix + ".")) and n not in stage_of:
                     order.append(n); stage_of[n] = stage
-        add("head", 0); add("fc_norm", 0)
+        add("head", 0); add("fc_norm", 0); add("local_MCA", 0)
         nb = len(m.blocks)
         for i in range(nb - 1, -1, -1):
             add(f"blocks.{i}", (nb - 1 - i) // self.blk_group)
@@ -105,6 +106,18 @@ class _FtRunner(_Runner):
             cast(pre + ".fc2", blk.mlp.fc2.weight)
             qb = self.buf(pre + ".qkvbias", (3 * blk.attn.q_bias.numel(),), torch.float32)
             _lib.pack_qkv_bias(blk.attn.q_bias.detach(), blk.attn.v_bias.detach(), qb)
+        if getattr(m, "fusing_method", None) == "MCA":          # cross-attention block of the box-focused classifier
+            mca = m.local_MCA[0]
+            D = m.embed_dim
+            # [q.weight; kv.weight] = the [3D, D] layout of a fused qkv projection (kv rows: K heads, then V heads, :140-143)
+            cast("mca.qkv", torch.cat((mca.attn.q.weight.detach(), mca.attn.kv.weight.detach()), 0))
+            cast("mca.proj", mca.attn.proj.weight)
+            cast("mca.fc1", mca.mlp.fc1.weight)
+            cast("mca.fc2", mca.mlp.fc2.weight)
+            qb = self.buf("mca.qkvbias", (3 * D,), torch.float32)   # q_bias on Q; v_bias is added once, after P @ V (rows of P sum to 1)
+            if not getattr(self, "_mca_bias_zeroed", False):
+                qb.zero_(); self._mca_bias_zeroed = True
+            qb[:D].copy_(mca.attn.q_bias.detach())
         C = m.num_classes
         self.c_pad = (C + 7) // 8 * 8
         cast("head", m.head.weight, pad_rows=self.c_pad - C)
@@ -113,12 +126,16 @@ class _FtRunner(_Runner):
         hb[:C].copy_(m.head.bias.detach())
 
     # ---- forward ------------------------------------------------------------------------------------------
-    def forward(self, x, pool_weights=None):
-        """``pool_weights``: None (mean over tokens, :400) or f32 [B, N] per-token weights of the box-focused pooling."""
+    def forward(self, x, pool_weights=None, mca=None):
+        """``pool_weights``: None (mean over tokens, :400) or f32 [B, N] per-token weights of the box-focused pooling.
+        ``mca``: None, or (key_allowed u8 [B, N], w_plain f32 [B, N]) for fusing 'MCA': the cross-attention block runs on the
+        encoder output, ``pool_weights`` (1 / n_in on the box tokens) pool ITS output and ``w_plain`` (1 / N on clips with no
+        token in the box, else 0) pools the encoder output itself (:560-562)."""
         m = self.m
         self._ensure_device(x.device)
         self.prepare_weights()
         self.pool_weights = pool_weights
+        self.mca_ctx = mca
         bf, f32 = torch.bfloat16, torch.float32
         B = x.shape[0]
         N = m.patch_embed.num_patches
@@ -149,7 +166,15 @@ class _FtRunner(_Runner):
         self.x_out = xe
         # norm = Identity, fc_norm(x.mean(1)), head  (:398-401, 405-406)
         pooled = self.buf("pooled", (B, D), f32)
-        _lib.token_mean_fwd(xe, B, N, D, pooled, weights=pool_weights)
+        if mca is not None:
+            allowed, w_plain = mca
+            xo = self._mca_fwd(m.local_MCA[0], xe, allowed, B, N, D)
+            plain = self.buf("pooled.plain", (B, D), f32)
+            _lib.token_mean_fwd(xo, B, N, D, pooled, weights=pool_weights)
+            _lib.token_mean_fwd(xe, B, N, D, plain, weights=w_plain)
+            pooled.add_(plain)
+        else:
+            _lib.token_mean_fwd(xe, B, N, D, pooled, weights=pool_weights)
         hn = self.buf("fc.hn", (B, D), bf); mean = self.buf("fc.mean", (B,), f32); rstd = self.buf("fc.rstd", (B,), f32)
         _lib.layernorm_fwd(pooled, m.fc_norm.weight, m.fc_norm.bias, hn, mean, rstd, B, D, m.fc_norm.eps)
         logits = self.buf("logits", (B, self.c_pad), f32)
@@ -159,6 +184,114 @@ class _FtRunner(_Runner):
         _lib.gemm_tn(hn, wc["head"][0], _lib.EPI_BIAS_RESID_F32, logits, bias=self.buf("head.bias_pad", (self.c_pad,), f32),
                      resid=zero)
         return logits
+
+    # ---- cross-attention block of fusing 'MCA' (modeling_finetune.py:162-191 over CrossAttention :100-160) ---------------
+    # The reference slices each clip into its in-box tokens x (queries) and out-of-box tokens y (keys / values) and runs
+    # x = x + attn(norm1(x), norm1(y)); x = x + mlp(norm2(x)) on the ragged pair, then averages x.  Here the block runs on ALL
+    # N tokens of every clip with the keys restricted by a mask: rows of tokens outside the box are computed and then get
+    # pooling weight 0, so their values never reach the logits and their gradient is exactly 0 - the same function of the
+    # parameters, on dense [B, N] shapes.  Heads are D / 3 = 256 wide, so scores, P @ V and their gradients are tcgen05 GEMM
+    # calls on per-clip, per-head views (K^T / V^T come from a second, operand-swapped GEMM; dK / dV from the MN-major
+    # weight-gradient kernel) with the masked softmax kernels between them.
+    def _mca_fwd(self, mca, x, allowed, B, N, D):
+        bf, f32 = torch.bfloat16, torch.float32
+        wc = self.wcache
+        M, H = B * N, mca.attn.num_heads
+        hd = D // H
+        scale = mca.attn.scale
+        h1 = self.buf("mca.h1", (M, D), bf); mean1 = self.buf("mca.mean1", (M,), f32); rstd1 = self.buf("mca.rstd1", (M,), f32)
+        _lib.layernorm_fwd(x, mca.norm1.weight, mca.norm1.bias, h1, mean1, rstd1, M, D, mca.norm1.eps)
+        qkv = self.buf("mca.qkv", (M, 3 * D), bf)
+        _lib.gemm_tn(h1, wc["mca.qkv"][0], _lib.EPI_BIAS_BF16, qkv, bias=self.buf("mca.qkvbias", (3 * D,), f32))
+        kvT = self.buf("mca.kvT", (B, 2 * D, N), bf)                 # K^T, V^T per clip: W_kv @ norm1(x_b)^T
+        w_kv = wc["mca.qkv"][0][D:]
+        for b in range(B):
+            _lib.gemm_tn(w_kv, h1[b * N:(b + 1) * N], _lib.EPI_PLAIN_BF16, kvT[b])
+        S = self.buf("mca.S", (B, H, N, N), f32)
+        zero = self.buf("mca.zero", (N, N), f32)
+        if not getattr(self, "_mca_zeroed", False):
+            zero.zero_(); self._mca_zeroed = True
+        for b in range(B):
+            rows = qkv[b * N:(b + 1) * N]
+            for h in range(H):
+                _lib.gemm_tn(rows[:, h * hd:(h + 1) * hd], rows[:, D + h * hd:D + (h + 1) * hd], _lib.EPI_BIAS_RESID_F32, S[b, h],
+                             resid=zero)
+        P = self.buf("mca.P", (B, H, N, N), bf)
+        _lib.masked_softmax_fwd(S, allowed, scale, P)
+        o = self.buf("mca.o", (M, D), bf)
+        v_bias = mca.attn.v_bias.detach()
+        for b in range(B):
+            for h in range(H):
+                _lib.gemm_tn(P[b, h], kvT[b, D + h * hd:D + (h + 1) * hd], _lib.EPI_BIAS_BF16, o[b * N:(b + 1) * N, h * hd:(h + 1) * hd],
+                             bias=v_bias[h * hd:(h + 1) * hd])
+        xm = self.buf("mca.xm", (M, D), f32)
+        _lib.gemm_tn(o, wc["mca.proj"][0], _lib.EPI_BIAS_RESID_F32, xm, bias=mca.attn.proj.bias, resid=x)
+        h2 = self.buf("mca.h2", (M, D), bf); mean2 = self.buf("mca.mean2", (M,), f32); rstd2 = self.buf("mca.rstd2", (M,), f32)
+        _lib.layernorm_fwd(xm, mca.norm2.weight, mca.norm2.bias, h2, mean2, rstd2, M, D, mca.norm2.eps)
+        Dh = mca.mlp.fc1.weight.shape[0]
+        u = self.buf("mca.u", (M, Dh), bf); a = self.buf("mca.a", (M, Dh), bf)
+        _lib.gemm_tn(h2, wc["mca.fc1"][0], _lib.EPI_BIAS_GELU_BF16, u, out1=a, bias=mca.mlp.fc1.bias)
+        xo = self.buf("mca.xo", (M, D), f32)
+        _lib.gemm_tn(a, wc["mca.fc2"][0], _lib.EPI_BIAS_RESID_F32, xo, bias=mca.mlp.fc2.bias, resid=xm)
+        return xo
+
+    def _mca_bwd(self, mca, g, x_in, dxA, dxA16, dxB, dxB16, dpooled, B, N, D, dp_prev_mlp):
+        """dxA / dxA16: gradient of the block's output on entry, of its input (the encoder output) on return."""
+        bf, f32 = torch.bfloat16, torch.float32
+        wc = self.wcache
+        M, H = B * N, mca.attn.num_heads
+        hd = D // H
+        scale = mca.attn.scale
+        Dh = mca.mlp.fc1.weight.shape[0]
+        name = "local_MCA.0"
+        h1 = self.buf("mca.h1", (M, D), bf); mean1 = self.buf("mca.mean1", (M,), f32); rstd1 = self.buf("mca.rstd1", (M,), f32)
+        qkv = self.buf("mca.qkv", (M, 3 * D), bf); kvT = self.buf("mca.kvT", (B, 2 * D, N), bf)
+        P = self.buf("mca.P", (B, H, N, N), bf); o = self.buf("mca.o", (M, D), bf); xm = self.buf("mca.xm", (M, D), f32)
+        h2 = self.buf("mca.h2", (M, D), bf); mean2 = self.buf("mca.mean2", (M,), f32); rstd2 = self.buf("mca.rstd2", (M,), f32)
+        u = self.buf("mca.u", (M, Dh), bf); a = self.buf("mca.a", (M, Dh), bf)
+        # mlp, norm2
+        _lib.gemm_wgrad(dxA16, a, g[name + ".mlp.fc2.weight"], dbias=g[name + ".mlp.fc2.bias"])
+        du = self.buf("mca.du", (M, Dh), bf)
+        _lib.gemm_tn(dxA16, wc["mca.fc2"][1], _lib.EPI_GELU_BWD_BF16, du, aux=u)
+        _lib.gemm_wgrad(du, h2, g[name + ".mlp.fc1.weight"], dbias=g[name + ".mlp.fc1.bias"])
+        dh = self.buf("mca.dh", (M, D), bf)
+        _lib.gemm_tn(du, wc["mca.fc1"][1], _lib.EPI_PLAIN_BF16, dh)
+        _lib.layernorm_bwd(dh, xm, mca.norm2.weight, mean2, rstd2, dxA, M, D, dxB, dxB16, g[name + ".norm2.weight"],
+                           g[name + ".norm2.bias"])
+        # proj
+        _lib.gemm_wgrad(dxB16, o, g[name + ".attn.proj.weight"], dbias=g[name + ".attn.proj.bias"])
+        do = self.buf("mca.do", (M, D), bf)
+        _lib.gemm_tn(dxB16, wc["mca.proj"][1], _lib.EPI_PLAIN_BF16, do)
+        _lib.colsum_bf16(do, M, D, g[name + ".attn.v_bias"])         # o = P @ V + v_bias
+        # attention: dP = dO V^T, dS = scale * P (dP - sum P dP), dQ = dS K, dK = dS^T Q, dV = P^T dO
+        dP = self.buf("mca.S", (B, H, N, N), f32)                    # the score buffer is free again
+        zero = self.buf("mca.zero", (N, N), f32)
+        for b in range(B):
+            for h in range(H):
+                _lib.gemm_tn(do[b * N:(b + 1) * N, h * hd:(h + 1) * hd], qkv[b * N:(b + 1) * N, 2 * D + h * hd:2 * D + (h + 1) * hd],
+                             _lib.EPI_BIAS_RESID_F32, dP[b, h], resid=zero)
+        dS = self.buf("mca.dS", (B, H, N, N), bf)
+        _lib.masked_softmax_bwd(P, dP, scale, dS)
+        dqkv = self.buf("mca.dqkv", (M, 3 * D), bf); dkv = self.buf("mca.dkv", (M, 2 * D), f32)
+        dkv.zero_()
+        for b in range(B):
+            r0, r1 = b * N, (b + 1) * N
+            for h in range(H):
+                c0, c1 = h * hd, (h + 1) * hd
+                _lib.gemm_tn(dS[b, h], kvT[b, c0:c1], _lib.EPI_PLAIN_BF16, dqkv[r0:r1, c0:c1])
+                _lib.gemm_wgrad(dS[b, h], qkv[r0:r1, c0:c1], dkv[r0:r1, c0:c1])
+                _lib.gemm_wgrad(P[b, h], do[r0:r1, c0:c1], dkv[r0:r1, D + c0:D + c1])
+        _lib.cast_f32_bf16(dkv, dqkv[:, D:])
+        # q / kv projections, norm1
+        _lib.colsum_bf16(dqkv[:, :D], M, D, g[name + ".attn.q_bias"])
+        _lib.gemm_wgrad(dqkv[:, :D], h1, g[name + ".attn.q.weight"])
+        _lib.gemm_wgrad(dqkv[:, D:], h1, g[name + ".attn.kv.weight"])
+        _lib.gemm_tn(dqkv, wc["mca.qkv"][1], _lib.EPI_PLAIN_BF16, dh)
+        # clips without a token in the box pool the encoder output directly: + w_plain[b, n] * dpooled[b]
+        dxB.view(B, N, D).addcmul_(self.mca_ctx[1][:, :, None], dpooled[:, None, :])
+        _lib.layernorm_bwd(dh, x_in, mca.norm1.weight, mean1, rstd1, dxB, M, D, dxA, dxA16, g[name + ".norm1.weight"],
+                           g[name + ".norm1.bias"], group_rows=N if dp_prev_mlp is not None else 0,
+                           in_group_rows=N if dp_prev_mlp is not None else 0, bf16_row_scale=dp_prev_mlp)
 
     # ---- backward -----------------------------------------------------------------------------------------
     def backward(self, dlogits, g):
@@ -186,8 +319,12 @@ class _FtRunner(_Runner):
         dxB = self.buf("bwd.dxB", (B * N, D), f32); dxB16 = self.buf("bwd.dxB16", (B * N, D), bf)
         nb = len(m.blocks)
         dp = self.dp
-        _lib.token_mean_bwd(dpooled, B, N, D, dxA, dxA16, bf16_row_scale=dp[2 * nb - 1] if dp is not None else None,
-                            weights=self.pool_weights)
+        last_scale = dp[2 * nb - 1] if dp is not None else None       # MLP-branch DropPath scale of the last block
+        if self.mca_ctx is not None:
+            _lib.token_mean_bwd(dpooled, B, N, D, dxA, dxA16, weights=self.pool_weights)
+            self._mca_bwd(m.local_MCA[0], g, self.x_out, dxA, dxA16, dxB, dxB16, dpooled, B, N, D, last_scale)
+        else:
+            _lib.token_mean_bwd(dpooled, B, N, D, dxA, dxA16, bf16_row_scale=last_scale, weights=self.pool_weights)
         for i in range(nb - 1, -1, -1):
             x_in = self.buf("x0", (B * N, D), f32) if i == 0 else self.buf(f"blk{i - 1}.xo", (B * N, D), f32)
             self._block_bwd(f"blk{i}", m.blocks[i], g, x_in, dxA, dxA16, dxB, dxB16, B * N, N, B, D,
@@ -200,8 +337,8 @@ class _FtRunner(_Runner):
 
 class _FtForwardFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner, x, pool_weights, *params):
-        logits = runner.forward(x, pool_weights)
+    def forward(ctx, runner, x, pool_weights, mca, *params):
+        logits = runner.forward(x, pool_weights, mca)
         ctx.runner = runner
         return logits[:, :runner.m.num_classes].clone()
 
@@ -213,7 +350,7 @@ class _FtForwardFn(torch.autograd.Function):
         arena, views = r.scratch_arena
         arena.zero_()
         r.backward(dlogits.float().contiguous(), views)
-        return (None, None, None) + tuple(views[n] for n, _ in r._named())
+        return (None, None, None, None) + tuple(views[n] for n, _ in r._named())
 
 
 class VisionTransformer(nn.Module):
@@ -289,16 +426,17 @@ class VisionTransformer(nn.Module):
         x = x.float().contiguous()
         return self._run(x, None)
 
-    def _run(self, x, pool_weights):
+    def _run(self, x, pool_weights, mca=None):
         r = self._runner
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return _FtForwardFn.apply(r, x, pool_weights, *[p for _, p in r._named()])
+            return _FtForwardFn.apply(r, x, pool_weights, mca, *[p for _, p in r._named()])
         with torch.no_grad():
-            return r.forward(x, pool_weights)[:, :self.num_classes].clone()
+            return r.forward(x, pool_weights, mca)[:, :self.num_classes].clone()
 
 
 # ---- parameter holders of the box-focused classifier's fusing modules (names / shapes / init of modeling_finetune.py:100-191,
-# 264-303): present so that state_dict round-trips with the reference; their forward paths ('soft_attn', 'MCA') are not built
+# 264-303), so that state_dict round-trips with the reference.  local_MCA[0] is run by _FtRunner._mca_fwd / _mca_bwd;
+# SoftAttention reduces to a plain mean (see VisionTransformer_BB_focused) and global_MCA is never called by the reference
 class _SoftAttention(nn.Module):
     def __init__(self, feature_dim, step_dim, bias=True):
         super().__init__()
@@ -312,6 +450,8 @@ class _SoftAttention(nn.Module):
 class _CrossAttention(nn.Module):
     def __init__(self, dim, num_heads, qkv_bias):
         super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
         self.q = nn.Linear(dim, dim, bias=False)
         self.kv = nn.Linear(dim, dim * 2, bias=False)
         if qkv_bias:
@@ -338,11 +478,12 @@ class VisionTransformer_BB_focused(VisionTransformer):
     ``'soft_attn'`` as a per-token weighted pooling inside the same kernel pipeline.  (``'soft_attn'`` as the reference WRITES
     it reduces to mean_in + mean_out: SoftAttention's [n,c] * [n,1,1] broadcast followed by sum(1).mean(0) leaves
     (sum_i a_i) * mean(x) with sum_i a_i = 1, so its own parameters get a mathematically zero gradient - none here.)
-    ``'MCA'`` (cross-attention with 256-wide heads over ragged per-clip token sets, the finetuning script's default) raises
-    ``NotImplementedError``; its parameters are held so that checkpoints round-trip."""
+    ``'MCA'`` (the finetuning script's default, :575-583): ``local_MCA[0]``, a pre-LN block whose attention takes its queries
+    from the tokens in the box and its keys / values from the tokens outside it (3 heads of embed_dim / 3), runs on the
+    encoder output as a key-masked dense block (``_FtRunner._mca_fwd``) and its box tokens are averaged; ``global_MCA`` is
+    commented out in the reference and stays unused.  Requires qkv_bias=True (what every registered model passes)."""
 
-    _unused_prefixes = ("soft_att_local", "soft_att_global", "local_MCA", "global_MCA", "patch_yab")
-    _FUSING = {"org": 0, "weighted_mean": 1, "soft_attn": 2}     # -> mofo_box_tokens mode
+    _FUSING = {"org": 0, "weighted_mean": 1, "soft_attn": 2, "MCA": 0}     # -> mofo_box_tokens mode
 
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
                  mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.,
@@ -353,7 +494,12 @@ class VisionTransformer_BB_focused(VisionTransformer):
         super().__init__(img_size, patch_size, in_chans, num_classes, embed_dim, depth, num_heads, mlp_ratio, qkv_bias, qk_scale,
                          drop_rate, attn_drop_rate, drop_path_rate, norm_layer, init_values, use_learnable_pos_emb, 1.0,
                          all_frames, tubelet_size, use_mean_pooling)
+        if fusing_method == "MCA" and (not qkv_bias or embed_dim % 3 != 0 or (embed_dim // 3) % 64 != 0):
+            raise NotImplementedError("fusing_method 'MCA' needs qkv_bias=True and embed_dim / 3 a multiple of 64")
         self.fusing_method = fusing_method
+        # parameters the forward never touches (no gradient in the reference either)
+        self._unused_prefixes = ("soft_att_local", "soft_att_global", "global_MCA", "patch_yab") + \
+            (() if fusing_method == "MCA" else ("local_MCA",))
         self.in_chans = in_chans
         self.soft_att_local = _SoftAttention(embed_dim, 1)
         self.soft_att_global = _SoftAttention(embed_dim, 1)
@@ -379,8 +525,17 @@ class VisionTransformer_BB_focused(VisionTransformer):
             raise RuntimeError("mofo_b200.VisionTransformer_BB_focused runs on CUDA (sm_100a) only; there is no CPU path")
         x = x.float().contiguous()
         bb = torch.as_tensor(BB).to(device=x.device, dtype=torch.int64).contiguous()
-        _, weights = _lib.box_tokens(bb, x.shape[2], x.shape[3], self._FUSING[self.fusing_method])
-        return self._run(x, weights)
+        if self.fusing_method != "MCA":
+            _, weights = _lib.box_tokens(bb, x.shape[2], x.shape[3], self._FUSING[self.fusing_method])
+            return self._run(x, weights)
+        inbox, _ = _lib.box_tokens(bb, x.shape[2], x.shape[3], 0, want_weights=False)
+        inb = inbox.bool()
+        N = inb.shape[1]
+        n_in = inb.sum(1, keepdim=True)
+        w_in = (inb.float() / n_in.clamp(min=1)).contiguous()                 # in_bbx.mean(0) of the block's output (:583)
+        w_plain = ((n_in == 0).float() / N).expand(-1, N).contiguous()         # no token in the box: x[i].mean(0) (:560-562)
+        key_allowed = (~inb | (n_in == N)).to(torch.uint8).contiguous()        # keys = tokens outside the box; none -> y = x (:131-133)
+        return self._run(x, w_in, (key_allowed, w_plain))
 
 
 _REGISTRY = {}

@@ -189,7 +189,7 @@ def test_reference_finetuning_engine_drives_the_b200_classifier():
     assert ((a - b).norm() / a.norm()).item() < 0.1
 
 
-@pytest.mark.parametrize("fusing", ["weighted_mean", "org", "soft_attn"])
+@pytest.mark.parametrize("fusing", ["weighted_mean", "org", "soft_attn", "MCA"])
 def test_box_focused_classifier_matches_reference(fusing):
     """VisionTransformer_BB_focused.forward(x, BB): the token-in-box predicate is bit-equal to the reference's patch_yab
     construction (all-ones Conv3d over a painted clip), logits and gradients follow the reference; parameters of the fusing
@@ -203,6 +203,11 @@ def test_box_focused_classifier_matches_reference(fusing):
     kw = dict(num_classes=classes, all_frames=16, tubelet_size=2, drop_rate=0.0, drop_path_rate=0.0, attn_drop_rate=0.0,
               use_mean_pooling=True, init_scale=1.0, fusing_method=fusing)
     ref_model = ref.modeling_finetune.vit_base_patch16_224_BB_focused(pretrained=False, **kw).to(dev).train()
+    if fusing == "MCA":              # away from the init point (std 0.02 weights, zero biases: a nearly uniform softmax)
+        with torch.no_grad():
+            att = ref_model.local_MCA[0].attn
+            att.q.weight.mul_(3.0); att.kv.weight.mul_(3.0)
+            att.q_bias.normal_(0, 0.5); att.v_bias.normal_(0, 0.5)
     ours = mf.create_model("vit_base_patch16_224_BB_focused", pretrained=False, drop_block_rate=None, **kw)
     ours.load_state_dict(ref_model.state_dict(), strict=True)
     ours = ours.to(dev).train()
@@ -213,6 +218,8 @@ def test_box_focused_classifier_matches_reference(fusing):
     BB = torch.cat([x1, y1, x1 + torch.randint(1, 74, (B, 16, 1), generator=g), y1 + torch.randint(1, 74, (B, 16, 1), generator=g)], 2)
     BB[1] = torch.tensor([10, 10, 10, 40])                       # empty box: no token inside -> plain mean (:560-562)
     BB[2, :, :] = torch.tensor([0, 0, 224, 100])
+    if fusing == "MCA":
+        BB[3, :, :] = torch.tensor([0, 0, 224, 224])             # every token in the box: keys fall back to the box tokens (:131-133)
     BB = BB.to(dev)
     # the reference's predicate, as modeling_finetune.py:589-630 builds it
     with torch.no_grad():
@@ -223,7 +230,7 @@ def test_box_focused_classifier_matches_reference(fusing):
         want = torch.clamp(ref_model.patch_yab(x_new).flatten(2).transpose(1, 2).mean(2), 0, 1).type(torch.bool)
     got = ours.tokens_in_box(BB, 16, 224)
     assert torch.equal(got, want)
-    assert int(want[1].sum()) == 0 and 0 < int(want[0].sum()) < 1568
+    assert int(want[1].sum()) == 0 and 0 < int(want[0].sum()) < 1568 and (fusing != "MCA" or int(want[3].sum()) == 1568)
 
     def ref_step(amp):
         ref_model.zero_grad(set_to_none=True)

@@ -146,3 +146,38 @@ def test_gemm_wgrad_grouped_matches_individual_calls(lib, M, D):
     w2 = torch.zeros(128, 128, device="cuda")
     lib.gemm_wgrad_grouped([(dY2, X2, w2, None, (0, 0))], 256)
     assert rel(w2, dY2.float().t() @ X2.float()) < 2e-5
+
+
+def test_gemm_on_per_head_views_with_ragged_n_and_k(lib):
+    """The products of the box-focused classifier's cross attention (3 heads of 256 over 1568 tokens): operands are column /
+    row slices of wider matrices, N = 1568 and K = 1568 are not multiples of the tile sizes."""
+    torch.manual_seed(9)
+    N, D, hd = 1568, 768, 256
+    qkv = torch.randn(2 * N, 3 * D, device="cuda").bfloat16()
+    rows = qkv[N:2 * N]
+    q, k = rows[:, hd:2 * hd], rows[:, D + hd:D + 2 * hd]
+    zero = torch.zeros(N, N, device="cuda")
+    S = torch.empty(N, N, device="cuda")
+    lib.gemm_tn(q, k, lib.EPI_BIAS_RESID_F32, S, resid=zero)                 # f32 scores, M = N = 1568, K = 256
+    ref = q.float() @ k.float().t()
+    assert rel(S, ref) < 1e-5
+    P = (torch.rand(N, N, device="cuda") / N).bfloat16()
+    kvT = (torch.randn(2 * D, N, device="cuda")).bfloat16()
+    o = torch.zeros(N, D, dtype=torch.bfloat16, device="cuda")
+    bias = torch.randn(D, device="cuda")
+    lib.gemm_tn(P, kvT[D + hd:D + 2 * hd], lib.EPI_BIAS_BF16, o[:, hd:2 * hd], bias=bias[hd:2 * hd])     # K = 1568
+    ref = P.float() @ kvT[D + hd:D + 2 * hd].float().t() + bias[hd:2 * hd]
+    assert rel(o[:, hd:2 * hd], ref) < 4e-3
+    assert o[:, :hd].abs().max().item() == 0 and o[:, 2 * hd:].abs().max().item() == 0
+    # operand-swapped projection: K^T, V^T [2D, N] = W_kv @ h^T  (N = 1568 output columns)
+    h = torch.randn(N, D, device="cuda").bfloat16(); w = (torch.randn(2 * D, D, device="cuda") / math.sqrt(D)).bfloat16()
+    out = torch.empty(2 * D, N, dtype=torch.bfloat16, device="cuda")
+    lib.gemm_tn(w, h, lib.EPI_PLAIN_BF16, out)
+    assert rel(out, w.float() @ h.float().t()) < 4e-3
+    # dK = dS^T Q into a column slice of an f32 [N, 2D] matrix (ldw > K), accumulated
+    dS = torch.randn(N, N, device="cuda").bfloat16()
+    dkv = torch.zeros(N, 2 * D, device="cuda")
+    lib.gemm_wgrad(dS, q, dkv[:, hd:2 * hd])
+    ref = dS.float().t() @ q.float()
+    assert rel(dkv[:, hd:2 * hd], ref) < 1e-4
+    assert dkv[:, :hd].abs().max().item() == 0 and dkv[:, 2 * hd:].abs().max().item() == 0

@@ -239,3 +239,39 @@ def test_normalize_u8_bit_exact_and_step_equivalence(lib):
     l_u8 = m.pretrain_step(u8.cuda(), mask).item()
     l_f32 = m.pretrain_step(ref.cuda(), mask).item()
     assert l_u8 == l_f32
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 3, 1568, 1568), (3, 1, 40, 2048), (1, 2, 7, 12)])
+def test_masked_softmax_fwd_bwd(B, H, Nq, Nk):
+    """Key-masked softmax pair of the box-focused classifier's cross attention vs torch fp32 (modeling_finetune.py:150-154)."""
+    from mofo_b200 import _lib
+    torch.manual_seed(B * 100 + Nk)
+    dev = "cuda"
+    S = torch.randn(B, H, Nq, Nk, device=dev) * 6
+    allowed = (torch.rand(B, Nk, device=dev) < 0.6)
+    allowed[:, 0] = True
+    allowed[0] = True
+    scale = 0.37
+    P = torch.empty(B, H, Nq, Nk, dtype=torch.bfloat16, device=dev)
+    _lib.masked_softmax_fwd(S, allowed.to(torch.uint8), scale, P)
+    want = (S * scale).masked_fill(~allowed[:, None, None, :], float("-inf")).softmax(-1)
+    assert torch.all(P.float()[~allowed[:, None, None, :].expand_as(P)] == 0)
+    assert (P.float() - want).abs().max().item() <= 2 ** -8 * want.max().item() + 1e-6      # bf16 rounding of values <= 1
+    assert (P.float().sum(-1) - 1).abs().max().item() < 5e-3
+    dP = torch.randn(B, H, Nq, Nk, device=dev)
+    dS = torch.empty_like(P)
+    _lib.masked_softmax_bwd(P, dP, scale, dS)
+    Pf = P.float()
+    want_dS = scale * Pf * (dP - (Pf * dP).sum(-1, keepdim=True))
+    err = (dS.float() - want_dS).abs().max().item()
+    assert err <= 2 ** -8 * want_dS.abs().max().item() + 1e-6, err
+
+
+def test_cast_f32_bf16_strided():
+    from mofo_b200 import _lib
+    torch.manual_seed(5)
+    src = torch.randn(777, 1536, device="cuda")
+    dst = torch.zeros(777, 2304, dtype=torch.bfloat16, device="cuda")
+    _lib.cast_f32_bf16(src[:, 256:1280], dst[:, 768:1792])
+    assert torch.equal(dst[:, 768:1792], src[:, 256:1280].bfloat16())
+    assert dst[:, :768].abs().max().item() == 0 and dst[:, 1792:].abs().max().item() == 0

@@ -128,6 +128,11 @@ def test_box_focused_classifier_schema_matches_reference():
     assert all(tuple(sd[k].shape) == tuple(v.shape) for k, v in om.state_dict().items())
     om.load_state_dict(sd, strict=True)
     assert torch.equal(om.patch_yab.weight, torch.ones_like(om.patch_yab.weight))
-    for bad in ("MCA",):
-        with pytest.raises(NotImplementedError):
-            mf.create_model("vit_base_patch16_224_BB_focused", num_classes=97, fusing_method=bad)
+    with pytest.raises(NotImplementedError):
+        mf.create_model("vit_base_patch16_224_BB_focused", num_classes=97, fusing_method="no_such_method")
+    # every fusing method of the reference constructs; 'MCA' keeps local_MCA among the trained parameters, the others do not
+    for fusing in ("org", "weighted_mean", "soft_attn", "MCA"):
+        mm = mf.create_model("vit_base_patch16_224_BB_focused", num_classes=97, fusing_method=fusing)
+        trained = [n for n, _ in mm._runner._named()]
+        assert any(n.startswith("local_MCA") for n in trained) == (fusing == "MCA")
+        assert not any(n.startswith(("global_MCA", "soft_att", "patch_yab")) for n in trained)
