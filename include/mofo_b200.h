@@ -274,6 +274,34 @@ int mofo_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
                     const int64_t* segs, const int32_t* tiles, int n_tiles, const float* hyper, const float* clip_coef,
                     const float* loss_guard, float* sq_norm_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * (10) Motion-box preprocessing, pixel stages.  The reference runs these once per dataset on the CPU with
+ * numpy / scipy.ndimage / cv2; both calls are bit-exact with that arithmetic (oracle/motion_oracle.py).
+ *
+ * mofo_motion_map: optical-flow video -> motion map.  Replaces the frame loop of create_lmdb_video_dataset_flow_mag
+ * (scripts/data/motion_map_creator.py:160-205) and compute_motion_boudary / zero_boundary (scripts/motion_sts.py:5-37).
+ * flows: uint8 [T,H,W,C] (C >= 2; channel 0 = u, 1 = v; the reference decodes C = 3).  For frame idx = 1..T the ws-frame
+ * window of :163-172, per channel the window sum of the 3x3 motion-boundary responses (ndimage.convolve, 'reflect'),
+ * float32 magnitude as cv2.cartToPolar computes it, (mag_u + mag_v) / 2, a `border`-pixel frame zeroed (the reference: 8;
+ * 0 = none), cast to uint8 as ndarray.astype does (trunc mod 256), written to out[T,H,W,out_channels] with the value
+ * replicated over the channels (the reference writes 3).
+ *
+ * mofo_motion_box_filter: the per-frame filtering in front of the contour search of json_creator
+ * (scripts/data/SSV2/bounding_box_creator_SSV.py:125-166; the Epic-Kitchens variant is the same code): for every frame of
+ * frames uint8 [T,H,W,3]: scipy gaussian_filter(sigma_before) over all three axes with uint8 storage after each 1-D pass,
+ * zero below remove_thrd * max, zero below std_k * (std + std_eps), gaussian_filter(sigma_after), cv2 BGR2GRAY.
+ * w_before[0..r_before] / w_after[0..r_after]: float64 gaussian weights by distance from the centre, as scipy's
+ * _gaussian_kernel1d(sigma, 0, int(4*sigma+0.5)) gives them (device pointers).  work: 2*T*H*W*3 bytes; stats: uint64 [T,4]
+ * (cleared by the call; afterwards [t] = {max, sum, sum of squares, -}).  Outputs: filtered uint8 [T,H,W,3] (the frame
+ * the reference hands to cvtColor) and gray uint8 [T,H,W] (what cv2.findContours receives).  frames is not modified.
+ * The contour search, ranking and temporal smoothing (:168-475) are sequential host code and stay on the host.
+ */
+int mofo_motion_map(const uint8_t* flows, int T, int H, int W, int C, int ws, int border, uint8_t* out, int out_channels,
+                    void* stream);
+int mofo_motion_box_filter(const uint8_t* frames, int T, int H, int W, const double* w_before, int r_before, const double* w_after,
+                           int r_after, double remove_thrd, double std_k, double std_eps, uint8_t* work, uint64_t* stats,
+                           uint8_t* filtered, uint8_t* gray, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

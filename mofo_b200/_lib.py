@@ -50,6 +50,8 @@ SIGNATURES = {
     "mofo_normalize_u8": ([_P, _I, _I, _I, _P, _P], C.c_int),
     "mofo_clip_preprocess": ([_P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P], C.c_int),
     "mofo_adamw_step": ([_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P], C.c_int),
+    "mofo_motion_map": ([_P, _I, _I, _I, _I, _I, _I, _P, _I, _P], C.c_int),
+    "mofo_motion_box_filter": ([_P, _I, _I, _I, _P, _I, _P, _I, _D, _D, _D, _P, _P, _P, _P, _P], C.c_int),
 }
 
 
@@ -78,7 +80,7 @@ def load() -> C.CDLL:
 
 
 # kernels launched per successful C-ABI call (bench.py reports the count it observed as "gpu_launches")
-_LAUNCHES = {"mofo_target_mse": 2, "mofo_attn_bwd": 3}
+_LAUNCHES = {"mofo_target_mse": 2, "mofo_attn_bwd": 3, "mofo_motion_box_filter": 8}
 launch_count = 0
 
 
@@ -393,3 +395,26 @@ def normalize_u8(clip_u8, out):
     assert Cc == 3 and clip_u8.dtype == torch.uint8 and clip_u8.is_contiguous() and out.dtype == torch.float32
     _check(load().mofo_normalize_u8(_ptr(clip_u8), B, frames, size, _ptr(out), _stream()), "mofo_normalize_u8")
     return out
+
+
+def motion_map(flows_u8, ws, border, out):
+    """flows_u8 uint8 [T,H,W,C>=2] -> out uint8 [T,H,W,OC] (motion-boundary magnitude map, value replicated over OC)."""
+    T, H, W, Cc = flows_u8.shape
+    assert flows_u8.dtype == torch.uint8 and flows_u8.is_contiguous() and flows_u8.is_cuda
+    assert out.dtype == torch.uint8 and out.is_contiguous() and out.shape[:3] == (T, H, W) and out.dim() == 4
+    _check(load().mofo_motion_map(_ptr(flows_u8), T, H, W, Cc, ws, border, _ptr(out), out.shape[3], _stream()), "mofo_motion_map")
+    return out
+
+
+def motion_box_filter(frames_u8, w_before, w_after, remove_thrd, std_k, std_eps, work, stats, filtered, gray):
+    """frames_u8 uint8 [T,H,W,3]; w_* f64 [r+1] weights by distance -> filtered uint8 [T,H,W,3], gray uint8 [T,H,W]."""
+    T, H, W, Cc = frames_u8.shape
+    assert Cc == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous() and frames_u8.is_cuda
+    assert w_before.dtype == torch.float64 and w_after.dtype == torch.float64 and w_before.is_cuda and w_after.is_cuda
+    assert work.dtype == torch.uint8 and work.numel() >= 2 * frames_u8.numel() and stats.dtype == torch.int64 and stats.numel() >= 4 * T
+    assert filtered.shape == frames_u8.shape and filtered.dtype == torch.uint8 and filtered.is_contiguous()
+    assert gray.shape == (T, H, W) and gray.dtype == torch.uint8 and gray.is_contiguous()
+    _check(load().mofo_motion_box_filter(_ptr(frames_u8), T, H, W, _ptr(w_before), w_before.numel() - 1, _ptr(w_after),
+                                         w_after.numel() - 1, remove_thrd, std_k, std_eps, _ptr(work), _ptr(stats), _ptr(filtered),
+                                         _ptr(gray), _stream()), "mofo_motion_box_filter")
+    return filtered, gray

@@ -12,14 +12,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmofo_sm100.so")
-SOURCES = ["runtime.cu", "simple_kernels.cu", "gemm.cu", "attention.cu", "attention_small.cu", "optimizer.cu"]
+SOURCES = ["runtime.cu", "simple_kernels.cu", "gemm.cu", "attention.cu", "attention_small.cu", "optimizer.cu", "motion_kernels.cu"]
 HEADERS = ["common.cuh", "attn_helpers.cuh", os.path.join("..", "..", "include", "mofo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # --use_fast_math (flush-to-zero, approximate division / sqrt) is for the GEMM / attention epilogues and the streaming
 # kernels whose results are rounded to bf16 anyway; the optimizer keeps IEEE division / sqrt and denormals so that
 # adamw_kernel really is torch.optim.AdamW's arithmetic (exp_avg_sq of tiny gradients must not flush to zero)
-FAST_MATH = {"runtime.cu": True, "simple_kernels.cu": True, "gemm.cu": True, "attention.cu": True, "attention_small.cu": True, "optimizer.cu": False}
+FAST_MATH = {"runtime.cu": True, "simple_kernels.cu": True, "gemm.cu": True, "attention.cu": True, "attention_small.cu": True, "optimizer.cu": False,
+             "motion_kernels.cu": False}
 
 
 def _nvcc() -> str:

@@ -129,6 +129,87 @@ __device__ __forceinline__ void coop_store(uint32_t stg, int lane, int row_base,
   }
 }
 
+// ---- bias + erf-GELU epilogue of one chunk (32 rows x 32 columns per warp), MOFO_GELU_V2 -------------------------------
+// Same arithmetic as erf_parts() with the constants folded (t = 1/(1 + p|u|/sqrt2), e = exp2(-log2e/2 * u^2),
+// Phi = 0.5 + copysign(0.5, u) * (1 - poly(t) e), gelu = u Phi, gelu' = Phi + u pdf(u)): 14 FMA-class + 2 MUFU per element.
+// What changed the kernel's speed is not the count but the SHAPE of the code: the round-2 ncu profile showed the epilogue
+// warps issuing 0.54 instructions per cycle and scheduler with ~4 warps each, and the SASS showed why - with the whole
+// chunk's bias slice (32 registers) held next to the 32 accumulators ptxas had serialised the elements (MUFU.RCP / MUFU.EX2
+// alternating one element at a time, a ~100-cycle dependent chain per element, two in flight).  Here eight elements go
+// through every stage together (eight independent chains per warp), the bias arrives eight columns at a time one batch
+// ahead, and each batch's gelu' words leave for the staging tile as soon as they exist.
+#ifndef MOFO_GELU_V2
+#define MOFO_GELU_V2 1
+#endif
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_chunk(const EpiParams& ep, uint32_t stg, int lane, int row_base, int M, int n0, int N,
+                                           uint32_t taddr) {
+  constexpr float kP = 0.47047f * 0.70710678118654752f;          // A-S 7.1.25's p, for z = |u| / sqrt(2)
+  constexpr float kE = -0.5f * 1.4426950408889634f;              // exp(-u^2 / 2) = exp2(kE * u^2)
+  constexpr float kD = 0.3989422804014327f;                      // 1 / sqrt(2 pi)
+  const int rem = N - n0;
+  const int valid_chunks = rem >= 32 ? 4 : rem / 8;
+  const bool has_bias = ep.bias != nullptr;
+  const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
+  auto bias4 = [&](int q) { return has_bias && n0 + q * 4 < N ? __ldg(bp + q) : make_float4(0.f, 0.f, 0.f, 0.f); };
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  float4 b0 = bias4(0), b1 = bias4(1);           // requested before the accumulator wait: the two latencies overlap
+  tc_wait_ld();
+  uint32_t packed[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float4 nb0 = b0, nb1 = b1;
+    if (c < 3) { nb0 = bias4(2 * c + 2); nb1 = bias4(2 * c + 3); }
+    float u[8], t[8], e[8];
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] = __uint_as_float(r[c * 8 + k]) + bb[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {          // GELU acts on the bf16-rounded pre-activation (what F.linear returns under autocast)
+      const uint32_t ub = pack_bf16(u[2 * k], u[2 * k + 1]);
+      u[2 * k] = bf16_lo(ub); u[2 * k + 1] = bf16_hi(ub);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = rcp_approx(fmaf(kP, fabsf(u[k]), 1.0f));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = ex2_approx(kE * (u[k] * u[k]));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float poly = t[k] * fmaf(t[k], fmaf(t[k], 0.7478556f, -0.0958798f), 0.3480242f);
+      t[k] = fmaf(copysignf(0.5f, u[k]), fmaf(-poly, e[k], 1.0f), 0.5f);            // Phi(u)
+    }
+    uint32_t dp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      packed[c * 4 + k] = pack_bf16(u[2 * k] * t[2 * k], u[2 * k + 1] * t[2 * k + 1]);
+      dp[k] = pack_bf16(fmaf(u[2 * k] * kD, e[2 * k], t[2 * k]), fmaf(u[2 * k + 1] * kD, e[2 * k + 1], t[2 * k + 1]));
+    }
+    sts128(stg64(stg, lane, c), make_uint4(dp[0], dp[1], dp[2], dp[3]));
+    b0 = nb0; b1 = nb1;
+  }
+  __syncwarp();
+  coop_store(stg, lane, row_base, M, valid_chunks,
+             [&](int g) { return reinterpret_cast<__nv_bfloat16*>(ep.out0) + static_cast<size_t>(g) * ep.ldo0 + n0; });
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    sts128(stg64(stg, lane, c), make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]));
+  __syncwarp();
+  coop_store(stg, lane, row_base, M, valid_chunks,
+             [&](int g) { return reinterpret_cast<__nv_bfloat16*>(ep.out1) + static_cast<size_t>(g) * ep.ldo1 + n0; });
+  __syncwarp();
+}
+
 template <int EPI>
 struct EpiTraits {
   static constexpr bool F32_OUT = (EPI == MOFO_EPI_BIAS_RESID_F32 || EPI == MOFO_EPI_BIAS_POS_F32);
@@ -159,6 +240,12 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, uint32_t stg
                                                int N, uint32_t taddr, const uint4 (&pre)[4]) {
   using T = EpiTraits<EPI>;
   constexpr int COLS = T::COLS;
+#if MOFO_GELU_V2
+  if constexpr (EPI == MOFO_EPI_BIAS_GELU_BF16) {
+    gelu_chunk(ep, stg, lane, row_base, M, n0, N, taddr);
+    return;
+  }
+#endif
   const int rem = N - n0;                                   // > 0
   const int valid_chunks = rem >= COLS ? 4 : (T::F32_OUT ? rem / 4 : rem / 8);
   float v[COLS];

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p mofo_b200/build/variant_$name tools/variants
-for s in runtime simple_kernels gemm attention attention_small optimizer; do
+for s in runtime simple_kernels gemm attention attention_small optimizer motion_kernels; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --use_fast_math "$@" \
     -c mofo_b200/csrc/$s.cu -o mofo_b200/build/variant_$name/$s.o &
 done
