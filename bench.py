@@ -495,10 +495,10 @@ def run_ours(args):
                          "frac": gemm_tflops / peaks["bf16_sustained"] if gemm_tflops else None,
                          "frac_of_burst_peak": gemm_tflops / peaks["bf16_burst"] if gemm_tflops else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the shipped kernel, `ncu --set full`
-                         # (profiles/r02_ncu_gemm_tn2_gelu_full.txt): decoder fc1 + GELU instance gemm_tn2_kernel<256,1>
-                         # [50176 x 1536, K = 384]: 40.1 MB read + 257.4 MB written vs 347.9 MB algorithmic (A 38.5 + W 1.2 +
+                         # (profiles/r02_ncu_gemm_epilogues_v3.txt): decoder fc1 + GELU instance gemm_tn2_kernel<256,1>
+                         # [50176 x 1536, K = 384]: 39.8 MB read + 254.1 MB written vs 347.9 MB algorithmic (A 38.5 + W 1.2 +
                          # two bf16 outputs 2 x 154.1; the tail of the outputs was still dirty in L2) -> no re-reads
-                         "traffic": 297.5e6, "traffic_instance": "gemm_tn2_kernel<256,BIAS_GELU_BF16> M=50176 N=1536 K=384 (algorithmic 347.9e6 B)",
+                         "traffic": 293.9e6, "traffic_instance": "gemm_tn2_kernel<256,BIAS_GELU_BF16> M=50176 N=1536 K=384 (algorithmic 347.9e6 B)",
                          "launches_timed": n_gemm, "kernel_ms_per_step": gemm_ms / args.steps if n_gemm else None,
                          "share_of_step": gemm_ms / ms_instrumented if n_gemm else None,
                          "instrumented_ms_per_step": ms_instrumented / args.steps if n_gemm else None,

@@ -141,6 +141,9 @@ __device__ __forceinline__ void coop_store(uint32_t stg, int lane, int row_base,
 #ifndef MOFO_GELU_V2
 #define MOFO_GELU_V2 1
 #endif
+#ifndef MOFO_EPI_PREFETCH
+#define MOFO_EPI_PREFETCH 1      // chunks of the epilogue's second input kept in flight per warp; 2 measured 2-4 % SLOWER (below)
+#endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // Pulls the bias slices of this warp's chunks of the coming tile into L1 while the tile's main loop is still running (lane i
 // takes the warp's i-th chunk): the epilogue's broadcast bias loads then hit L1 (~40 clk) instead of L2 (~700 clk).  ncu,
@@ -476,23 +479,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int row_base = m_blk * BM + quarter * 32;
-      uint4 pre[4];
-      if (T::HAS_OPERAND && n_blk * BN + grp * COLS < N)          // first chunk's operand: overlaps the tile's main loop
-        operand_fetch<EPI>(ep, pre, lane, row_base, M, n_blk * BN + grp * COLS, N);
+      // the epilogue's second input (residual / gelu' / pos rows) for this warp's first TWO chunks is requested here, while
+      // the tile's main loop still runs, and stays two chunks ahead afterwards: one chunk of work (~200 instructions) does
+      // not cover an HBM round trip (ncu, round 2: 50-60 % of these kernels' stall samples were long-scoreboard waits on
+      // exactly these registers, at 23-29 % issue utilisation)
+      constexpr int CSTEP = EPI_WARPS / 4;
+      uint4 pre[4], pre2[4];
+      if (T::HAS_OPERAND) {
+        if (n_blk * BN + grp * COLS < N) operand_fetch<EPI>(ep, pre, lane, row_base, M, n_blk * BN + grp * COLS, N);
+        if (MOFO_EPI_PREFETCH > 1 && grp + CSTEP < NCHUNK && n_blk * BN + (grp + CSTEP) * COLS < N)
+          operand_fetch<EPI>(ep, pre2, lane, row_base, M, n_blk * BN + (grp + CSTEP) * COLS, N);
+      }
       if (T::HAS_BIAS) prefetch_bias<COLS, NCHUNK>(ep.bias, lane, grp, n_blk * BN, N);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int ch = grp; ch < NCHUNK; ch += EPI_WARPS / 4) {
+      for (int ch = grp; ch < NCHUNK; ch += CSTEP) {
         const int n0 = n_blk * BN + ch * COLS;
         if (n0 >= N) break;
         uint4 cur[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) cur[i] = pre[i];
-        const int n_next = n0 + (EPI_WARPS / 4) * COLS;
-        if (T::HAS_OPERAND && ch + EPI_WARPS / 4 < NCHUNK && n_next < N)
-          operand_fetch<EPI>(ep, pre, lane, row_base, M, n_next, N);   // next chunk's operand in flight during this one
+        if (T::HAS_OPERAND) {
+          if (MOFO_EPI_PREFETCH > 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pre[i] = pre2[i];
+            const int n_fetch = n0 + 2 * CSTEP * COLS;
+            if (ch + 2 * CSTEP < NCHUNK && n_fetch < N) operand_fetch<EPI>(ep, pre2, lane, row_base, M, n_fetch, N);
+          } else {
+            const int n_next = n0 + CSTEP * COLS;
+            if (ch + CSTEP < NCHUNK && n_next < N) operand_fetch<EPI>(ep, pre, lane, row_base, M, n_next, N);
+          }
+        }
         epilogue_chunk<EPI>(ep, stg, lane, row_base, M, n0, N, taddr + ch * COLS, cur);
       }
       tc_fence_before();
@@ -656,23 +675,36 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = pair; tile < tiles; tile += n_pairs) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int row_base = m_blk * 2 * BM + static_cast<int>(rank) * BM + quarter * 32;
-      uint4 pre[4];
-      if (T::HAS_OPERAND && n_blk * BN + grp * COLS < N)
-        operand_fetch<EPI>(ep, pre, lane, row_base, M, n_blk * BN + grp * COLS, N);
+      // operand rows two chunks ahead, as in gemm_tn_kernel
+      constexpr int CSTEP = EPI_WARPS / 4;
+      uint4 pre[4], pre2[4];
+      if (T::HAS_OPERAND) {
+        if (n_blk * BN + grp * COLS < N) operand_fetch<EPI>(ep, pre, lane, row_base, M, n_blk * BN + grp * COLS, N);
+        if (MOFO_EPI_PREFETCH > 1 && grp + CSTEP < NCHUNK && n_blk * BN + (grp + CSTEP) * COLS < N)
+          operand_fetch<EPI>(ep, pre2, lane, row_base, M, n_blk * BN + (grp + CSTEP) * COLS, N);
+      }
       if (T::HAS_BIAS) prefetch_bias<COLS, NCHUNK>(ep.bias, lane, grp, n_blk * BN, N);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int ch = grp; ch < NCHUNK; ch += EPI_WARPS / 4) {
+      for (int ch = grp; ch < NCHUNK; ch += CSTEP) {
         const int n0 = n_blk * BN + ch * COLS;
         if (n0 >= N) break;
         uint4 cur[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) cur[i] = pre[i];
-        const int n_next = n0 + (EPI_WARPS / 4) * COLS;
-        if (T::HAS_OPERAND && ch + EPI_WARPS / 4 < NCHUNK && n_next < N)
-          operand_fetch<EPI>(ep, pre, lane, row_base, M, n_next, N);
+        if (T::HAS_OPERAND) {
+          if (MOFO_EPI_PREFETCH > 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pre[i] = pre2[i];
+            const int n_fetch = n0 + 2 * CSTEP * COLS;
+            if (ch + 2 * CSTEP < NCHUNK && n_fetch < N) operand_fetch<EPI>(ep, pre2, lane, row_base, M, n_fetch, N);
+          } else {
+            const int n_next = n0 + CSTEP * COLS;
+            if (ch + CSTEP < NCHUNK && n_next < N) operand_fetch<EPI>(ep, pre, lane, row_base, M, n_next, N);
+          }
+        }
         epilogue_chunk<EPI>(ep, stg, lane, row_base, M, n0, N, taddr + ch * COLS, cur);
       }
       tc_fence_before();
