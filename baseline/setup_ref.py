@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("MOFO_REFERENCE", "/root/reference")
 REF_DST = os.path.join(HERE, "_ref")
 FILES = ["masking_generator.py", "modeling_pretrain.py", "modeling_finetune.py", "engine_for_pretraining.py", "utils.py",
-         "optim_factory.py", "engine_for_finetuning.py", "mixup.py"]
+         "optim_factory.py", "engine_for_finetuning.py", "mixup.py", os.path.join("scripts", "motion_sts.py")]
 
 
 def stage(verbose=False):
@@ -23,7 +23,7 @@ def stage(verbose=False):
     os.makedirs(REF_DST, exist_ok=True)
     done = []
     for f in FILES:
-        s, d = os.path.join(REF_SRC, f), os.path.join(REF_DST, f)
+        s, d = os.path.join(REF_SRC, f), os.path.join(REF_DST, os.path.basename(f))
         if not os.path.exists(s):
             continue
         if not os.path.exists(d) or os.path.getmtime(d) < os.path.getmtime(s) or os.path.getsize(d) != os.path.getsize(s):

@@ -32,7 +32,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE configs[1]: 32)")
     ap.add_argument("--model", default="pretrain_videomae_base_patch16_224")
-    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune"],
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "finetune", "motion"],
                     help="finetune = BASELINE configs[4]: vit_base_patch16_224 classifier fwd+bwd on all 1568 tokens, batch 8 (not the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -596,9 +596,145 @@ def run_finetune(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# motion-box preprocessing, pixel stages (flow video -> motion map -> filtered gray map)
+# ------------------------------------------------------------------------------------------------------------------
+MOTION_METRIC = "MOFO motion-box preprocessing frames/s (240x320 flow video -> motion map -> gaussian/threshold/gaussian -> gray)"
+MOTION_T, MOTION_H, MOTION_W, MOTION_WS = 48, 240, 320, 8
+
+
+def motion_workload():
+    return (f"SURVEY 8f-4: one SSv2-shaped optical-flow video per step ({MOTION_T} frames of {MOTION_H}x{MOTION_W}x3 uint8, ws = {MOTION_WS}): "
+            "motion_map_creator.py:160-228 then bounding_box_creator_SSV.py:125-166 on every frame")
+
+
+def motion_cpu(frames, steps, warmup):
+    """The reference's own CPU path (baseline/motion_ref.py: its motion_sts functions + scipy + cv2) on the first `frames`
+    frames of a synthetic video, one host thread (scipy.ndimage and this cv2 path are single-threaded)."""
+    from baseline import motion_ref
+    flows = motion_ref.synthetic_flow_video(3, MOTION_T, MOTION_H, MOTION_W)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        mm = motion_ref.reference_motion_map(flows[:max(frames, MOTION_WS)], MOTION_WS)[:frames]
+        for f in mm:
+            motion_ref.reference_filter_frame(f.copy())
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return frames * len(ts) / sum(ts), 1e3 * sum(ts) / len(ts)
+
+
+def run_motion_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from baseline import motion_ref
+    if not motion_ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/motion_sts.py, scipy or cv2 missing"}), flush=True)
+        return
+    frames = 12
+    val, ms = motion_cpu(frames, args.steps, min(args.warmup, 1))
+    sample = (f"{frames} of the video's {MOTION_T} frames per step x {args.steps} steps: the reference's motion_sts.py (baseline/_ref) + "
+              "scipy.ndimage + cv2 replaying motion_map_creator.py:160-228 and bounding_box_creator_SSV.py:125-166")
+    print(json.dumps({"impl": "reference", "metric": MOTION_METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "u8 / f64", "data": "synthetic", "config": {"workload": motion_workload()},
+                      "cpu_baseline": {"value": val, "unit": "frames/s", "cores": 1, "kind": "reference", "sample": sample},
+                      "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+
+
+def run_motion(args):
+    """One step = one flow video through mofo_motion_map + mofo_motion_box_filter (9 kernel launches).  Inputs resident in HBM:
+    16 rotating videos (177 MB > L2).  e2e: pinned host flows in, gray maps back to pinned host memory, inside the timed region.
+    Independent videos: N GPUs would run N replicas (no exchange); measured on one."""
+    import torch
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    from mofo_b200 import _lib
+    from mofo_b200 import motion_boxes as mb
+    _lib.load()
+    peaks = measured_peaks()
+    T, H, W, ws = MOTION_T, MOTION_H, MOTION_W, MOTION_WS
+    g = torch.Generator(device="cpu").manual_seed(7)
+    host = [torch.randint(96, 160, (T, H, W, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(4)]
+    for hbuf in host:                                        # a moving patch with a different flow value
+        hbuf[:, 60:150, 80:200, :2] += 70
+    vids = [host[i % 4].to(dev) + (i // 4) for i in range(16)]
+    flt = mb.MotionMapFilter()
+    gray_host = torch.empty(T, H, W, dtype=torch.uint8).pin_memory()
+
+    def step(i):
+        return flt.filter(mb.motion_map(vids[i % 16], ws=ws))
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    n0 = _lib.launch_count
+    sampler.t0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.t1 = time.time()
+    launches = _lib.launch_count - n0
+    ms = e0.elapsed_time(e1) / args.steps
+    # per-stage device times (CUDA events on the launching stream, separate leg)
+    ea = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ta = tb = 0.0
+    for i in range(args.steps):
+        ea[0].record(); mm = mb.motion_map(vids[i % 16], ws=ws); ea[1].record(); flt.filter(mm); ea[2].record()
+        torch.cuda.synchronize()
+        ta += ea[0].elapsed_time(ea[1]); tb += ea[1].elapsed_time(ea[2])
+    ta /= args.steps; tb /= args.steps
+    # e2e through the module API with host buffers
+    for i in range(2):
+        d = host[i % 4].to(dev, non_blocking=True)
+        gray_host.copy_(flt.filter(mb.motion_map(d, ws=ws))[1], non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        d = host[i % 4].to(dev, non_blocking=True)
+        gray_host.copy_(flt.filter(mb.motion_map(d, ws=ws))[1], non_blocking=True)
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    px = T * H * W
+    bytes_a = px * 6                                          # stage A: 3 B read + 3 B written per pixel and frame
+    slots_b = px * 3 * 2 * ((4 + 1) + (120 + 1)) * 3          # stage B: DMUL + DADD per tap pair, 3 passes each for sigma 1 and 30
+    fp64_peak = 148 * 64 * (clocks["sm_mhz"] or 1900.0) * 1e6   # DP lanes x SMs x clock: one DMUL or DADD per lane and cycle
+    line = {"metric": MOTION_METRIC, "value": T / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 / f64", "data": "synthetic",
+            "config": {"workload": motion_workload(), "l2": "16 rotating videos (177 MB) > L2"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": T / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": T * H * W * 3, "d2h_bytes_per_step": T * H * W,
+                    "api": "mofo_b200.motion_boxes.motion_map + MotionMapFilter.filter on pinned host uint8 flows; gray maps copied back to pinned host memory"},
+            "roofline": {"bound": "hbm", "kernel": "motion_map_kernel (stage A; stage B is bound by the float64 pipe, see stage_b)",
+                         "achieved": bytes_a / (ta * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": bytes_a / (ta * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "algorithmic_bytes_per_launch": bytes_a, "kernel_ms": ta, "peak_source": peaks["source"]},
+            "stage_b": {"kernels": "3 x gauss_pass (sigma 1) + box_stats + 3 x gauss_pass (sigma 30, 241 taps in scipy's float64 order) + gray",
+                        "ms": tb, "share_of_step": tb / (ta + tb), "fp64_issue_slots": slots_b,
+                        "achieved_fp64_slots_per_s": slots_b / (tb * 1e-3), "frac_of_fp64_issue_peak": slots_b / (tb * 1e-3) / fp64_peak,
+                        "note": "bit-exactness with scipy forbids FMA contraction and reordering: one DMUL + one DADD per tap pair"}}
+    if not args.no_cpu_baseline:
+        from baseline import motion_ref
+        if motion_ref.available():
+            frames = 12
+            val, cms = motion_cpu(frames, 2, 1)
+            line["cpu_baseline"] = {"value": val, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                    "sample": f"2 steps (after 1 warm-up) of {frames} of the video's {T} frames: the reference's motion_sts.py + scipy.ndimage + cv2 "
+                                              "(baseline/motion_ref.py), single thread as in the reference's per-video worker"}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.workload == "finetune" and a.impl != "reference":
+    if a.workload == "motion":
+        run_motion_reference(a) if a.impl == "reference" else run_motion(a)
+    elif a.workload == "finetune" and a.impl != "reference":
         run_finetune(a)
     elif a.impl == "reference":
         run_reference(a)

@@ -173,6 +173,186 @@ __global__ void __launch_bounds__(256) gauss_pass_kernel(const uint8_t* __restri
   }
 }
 
+// ---- specialised passes: the generic kernel above spends ~12 instructions per tap pair (two table lookups, two global byte
+// loads, two threshold selects ...) for two float64 operations and ran at 13 % of the float64 issue rate (bench.py --workload
+// motion, round 2).  These stage the reflected, thresholded line segments in shared memory ONCE, so a tap pair costs two
+// shared byte loads, one integer add, one conversion, DMUL, DADD (+ the weight, a broadcast shared load); the channel pass
+// needs no loads at all.  Arithmetic and its order are unchanged.  The host falls back to the generic kernel when a frame is
+// too large for the staging buffers.
+__device__ __forceinline__ int frame_cut(int cut_mode, const unsigned long long* stats, int t, long long frame_n, double remove_thrd,
+                                         double std_k, double std_eps) {
+  if (!cut_mode) return 0;
+  const unsigned long long* st = stats + static_cast<size_t>(t) * BOX_STATS;
+  return max(cut_from_max(st[0], remove_thrd), cut_from_std(st[1], st[2], frame_n, std_k, std_eps));
+}
+// exact int -> double for 0 <= s < 2^32 without the conversion unit: the bits (0x43300000, s) are the double 2^52 + s, and the
+// subtraction is exact.  I2F.F64 issues at a quarter of the DADD rate and was the limiter of the staged passes.
+__device__ __forceinline__ double u32_to_double(unsigned int s) { return __dadd_rn(__hiloint2double(0x43300000, static_cast<int>(s)), -4503599627370496.0); }
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  int p = i % (2 * n);
+  if (p < 0) p += 2 * n;
+  return p >= n ? 2 * n - 1 - p : p;
+}
+
+// Four outputs per thread, taken from ALIGNED 32-bit shared-memory words (four neighbouring lines side by side): the first
+// staged version issued two byte loads and one weight load per tap pair and was bound by the shared-memory pipe (one
+// wavefront per instruction: 3 clk per warp and pair against 1.5 clk of float64 work).  Here a step costs two word loads and
+// one weight load for four pairs; the four byte sums are formed two at a time in 16-bit lanes (PRMT + IADD).
+__device__ __forceinline__ void tap_loop4(const uint8_t* base, int stride, const double* sw, int r, int (&res)[4]) {
+  auto w32 = [&](int off) { return *reinterpret_cast<const unsigned int*>(base + off); };
+  const unsigned int c0 = w32(0);
+  double tmp[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tmp[k] = __dmul_rn(u32_to_double((c0 >> (8 * k)) & 255u), sw[0]);
+#pragma unroll 4
+  for (int d = r; d >= 1; --d) {
+    const unsigned int a = w32(-d * stride), b = w32(d * stride);
+    const double w = sw[d];
+    const unsigned int se = __byte_perm(a, 0, 0x4240) + __byte_perm(b, 0, 0x4240);      // bytes 0 and 2 in 16-bit lanes
+    const unsigned int so = __byte_perm(a, 0, 0x4341) + __byte_perm(b, 0, 0x4341);      // bytes 1 and 3
+    tmp[0] = __dadd_rn(tmp[0], __dmul_rn(u32_to_double(se & 0xFFFFu), w));
+    tmp[1] = __dadd_rn(tmp[1], __dmul_rn(u32_to_double(so & 0xFFFFu), w));
+    tmp[2] = __dadd_rn(tmp[2], __dmul_rn(u32_to_double(se >> 16), w));
+    tmp[3] = __dadd_rn(tmp[3], __dmul_rn(u32_to_double(so >> 16), w));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) res[k] = static_cast<int>(tmp[k]) & 255;      // C cast double -> unsigned char
+}
+
+// AXIS 0 (H): one CTA = a strip of CW consecutive bytes of the (W*3)-byte rows over the full height of one frame; a thread
+// owns four neighbouring bytes of a row.
+constexpr int GS_CW = 64;
+__global__ void __launch_bounds__(256) gauss_strip_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int W3,
+                                                            const double* __restrict__ wd, int r, int cut_mode, double remove_thrd,
+                                                            double std_k, double std_eps, const unsigned long long* __restrict__ stats) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  double* sw = reinterpret_cast<double*>(smem_raw);                               // [r + 1]
+  uint8_t* s = smem_raw + static_cast<size_t>(r + 1) * 8;                         // [(H + 2r)][CW]
+  const int t = blockIdx.y, x0 = blockIdx.x * GS_CW;
+  const long long frame_n = static_cast<long long>(H) * W3;
+  const uint8_t* fin = in + static_cast<size_t>(t) * frame_n;
+  const int cut = frame_cut(cut_mode, stats, t, frame_n, remove_thrd, std_k, std_eps);
+  for (int k = threadIdx.x; k <= r; k += 256) sw[k] = wd[k];
+  for (int i = threadIdx.x; i < (H + 2 * r) * GS_CW; i += 256) {
+    const int row = i / GS_CW, x = i % GS_CW;
+    int v = 0;
+    if (x0 + x < W3) v = fin[static_cast<size_t>(reflect_idx(row - r, H)) * W3 + x0 + x];
+    s[i] = static_cast<uint8_t>(v < cut ? 0 : v);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < H * (GS_CW / 4); o += 256) {
+    const int y = o / (GS_CW / 4), x = (o % (GS_CW / 4)) * 4;
+    if (x0 + x >= W3) continue;
+    int res[4];
+    tap_loop4(s + (y + r) * GS_CW + x, GS_CW, sw, r, res);
+    uint8_t* dst = out + static_cast<size_t>(t) * frame_n + static_cast<size_t>(y) * W3 + x0 + x;
+    if (x0 + x + 3 < W3 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+      *reinterpret_cast<unsigned int*>(dst) = static_cast<unsigned int>(res[0]) | (res[1] << 8) | (res[2] << 16) | (static_cast<unsigned int>(res[3]) << 24);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (x0 + x + k < W3) dst[k] = static_cast<uint8_t>(res[k]);
+    }
+  }
+}
+
+// AXIS 1 (W): one CTA = RB (4, 8 or 16) full rows of one frame, de-interleaved per channel with the reflected halo and
+// TRANSPOSED so that the RB rows of one (channel, x) sit side by side: s[c][W + 2r][RB]; a thread owns four rows of one (c, x).
+__global__ void __launch_bounds__(256) gauss_rows_w_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int W,
+                                                           int RB, const double* __restrict__ wd, int r, int cut_mode,
+                                                           double remove_thrd, double std_k, double std_eps,
+                                                           const unsigned long long* __restrict__ stats) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  double* sw = reinterpret_cast<double*>(smem_raw);
+  uint8_t* s = smem_raw + static_cast<size_t>(r + 1) * 8;
+  const int t = blockIdx.y, y0 = blockIdx.x * RB, WE = W + 2 * r, W3 = W * 3;
+  const int rows = min(RB, H - y0);
+  const long long frame_n = static_cast<long long>(H) * W3;
+  const uint8_t* fin = in + static_cast<size_t>(t) * frame_n + static_cast<size_t>(y0) * W3;
+  const int cut = frame_cut(cut_mode, stats, t, frame_n, remove_thrd, std_k, std_eps);
+  for (int k = threadIdx.x; k <= r; k += 256) sw[k] = wd[k];
+  for (int i = threadIdx.x; i < 3 * WE * RB; i += 256) {
+    const int row = i % RB, rem = i / RB, xe = rem % WE, c = rem / WE;
+    int v = 0;
+    if (row < rows) v = fin[static_cast<size_t>(row) * W3 + reflect_idx(xe - r, W) * 3 + c];
+    s[i] = static_cast<uint8_t>(v < cut ? 0 : v);
+  }
+  __syncthreads();
+  const int quads = RB / 4;
+  for (int o = threadIdx.x; o < 3 * W * quads; o += 256) {
+    const int q = o % quads, rem = o / quads, x = rem % W, c = rem / W;
+    if (4 * q >= rows) continue;
+    int res[4];
+    tap_loop4(s + (c * WE + x + r) * RB + 4 * q, RB, sw, r, res);
+    uint8_t* dst = out + static_cast<size_t>(t) * frame_n + (static_cast<size_t>(y0 + 4 * q) * W + x) * 3 + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (4 * q + k < rows) dst[static_cast<size_t>(k) * W3] = static_cast<uint8_t>(res[k]);
+  }
+}
+
+// AXIS 2 (channel): thread = one pixel.  The reflected extension of a 3-sample line has period 6, so x[c-d] + x[c+d] takes
+// only six values per output channel: they are formed once (18 doubles in registers) and the tap loop is pure DMUL + DADD
+// with a broadcast weight load, in scipy's order d = r .. 1.
+__global__ void __launch_bounds__(256) gauss_chan_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long pixels,
+                                                         long long frame_n, const double* __restrict__ wd, int r, int cut_mode,
+                                                         double remove_thrd, double std_k, double std_eps,
+                                                         unsigned long long* __restrict__ stats, int want_max) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  double* sw = reinterpret_cast<double*>(smem_raw);
+  const int t = blockIdx.y;
+  const int cut = frame_cut(cut_mode, stats, t, frame_n, remove_thrd, std_k, std_eps);
+  for (int k = threadIdx.x; k <= r; k += 256) sw[k] = wd[k];
+  __syncthreads();
+  const long long px = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  int vmax = 0;
+  if (px < pixels) {
+    const uint8_t* src = in + static_cast<size_t>(t) * frame_n + px * 3;
+    int v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { v[c] = src[c]; v[c] = v[c] < cut ? 0 : v[c]; }
+    // ext(k) for k = -6 .. 8 via the period-6 pattern v0 v1 v2 v2 v1 v0
+    auto ext = [&](int k) { const int p = ((k % 6) + 6) % 6; return p == 0 || p == 5 ? v[0] : (p == 1 || p == 4 ? v[1] : v[2]); };
+    double ps[3][6], tmp[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int m = 0; m < 6; ++m) ps[c][m] = static_cast<double>(ext(c - m) + ext(c + m));      // d = m (mod 6)
+      tmp[c] = __dmul_rn(static_cast<double>(v[c]), sw[0]);
+    }
+    int d = r;
+    for (; d % 6 != 0; --d) {                     // head: distances down to the next multiple of 6 (at most five steps)
+      const int m = d % 6;
+      const double w = sw[d];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double q = m == 1 ? ps[c][1] : m == 2 ? ps[c][2] : m == 3 ? ps[c][3] : m == 4 ? ps[c][4] : ps[c][5];
+        tmp[c] = __dadd_rn(tmp[c], __dmul_rn(q, w));
+      }
+    }
+    for (; d >= 6; d -= 6) {                      // d, d-1, .. d-5  <->  m = 0, 5, 4, 3, 2, 1
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const double w = sw[d - j];
+        const int m = (6 - j) % 6;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tmp[c] = __dadd_rn(tmp[c], __dmul_rn(ps[c][m], w));
+      }
+    }
+    uint8_t* dst = out + static_cast<size_t>(t) * frame_n + px * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int o = static_cast<int>(tmp[c]);
+      dst[c] = static_cast<uint8_t>(o);
+      vmax = max(vmax, o & 255);
+    }
+  }
+  if (want_max) {
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if ((threadIdx.x & 31) == 0 && vmax > 0) atomicMax(stats + static_cast<size_t>(t) * BOX_STATS, static_cast<unsigned long long>(vmax));
+  }
+}
+
 __global__ void __launch_bounds__(256) box_stats_kernel(const uint8_t* __restrict__ in, long long frame_n, double remove_thrd,
                                                         unsigned long long* __restrict__ stats) {
   const int t = blockIdx.y;
@@ -239,22 +419,51 @@ int mofo_motion_box_filter(const uint8_t* frames, int T, int H, int W, const dou
   const dim3 grid(static_cast<unsigned>((frame_n + 255) / 256), T);
   auto smem = [&](int n, int r) { return ((static_cast<size_t>(n + 2 * r) * 4 + 7) & ~size_t(7)) + static_cast<size_t>(r + 1) * 8; };
   MOFO_CHECK_ARG(smem(max(H, W), max(r_before, r_after)) <= 48 * 1024, "motion_box_filter: lookup table does not fit shared memory");
+  const bool generic_only = getenv("MOFO_MOTION_GENERIC") != nullptr;      // tests: force the fallback kernels
+  // one 1-D pass: the staged kernel when its buffers fit the default 48 KB of shared memory, else the generic one
+  auto pass = [&](int axis, const uint8_t* src, uint8_t* dst, const double* w, int r, int cut_mode, int want_max) -> int {
+    const size_t wbytes = static_cast<size_t>(r + 1) * 8;
+    if (axis == 0) {
+      const size_t need = wbytes + static_cast<size_t>(H + 2 * r) * GS_CW;
+      if (!generic_only && need <= 48 * 1024) {
+        gauss_strip_h_kernel<<<dim3((W * 3 + GS_CW - 1) / GS_CW, T), 256, need, st>>>(src, dst, H, W * 3, w, r, cut_mode, remove_thrd, std_k,
+                                                                                      std_eps, stats_ull);
+      } else {
+        gauss_pass_kernel<0><<<grid, 256, smem(H, r), st>>>(src, dst, H, W, w, r, cut_mode, remove_thrd, std_k, std_eps, stats_ull, want_max);
+      }
+    } else if (axis == 1) {
+      const size_t per_row = static_cast<size_t>(3) * (W + 2 * r);
+      const size_t rb_fit = (48 * 1024 - wbytes) / per_row;
+      const int RB = rb_fit >= 16 ? 16 : rb_fit >= 8 ? 8 : rb_fit >= 4 ? 4 : 0;
+      if (!generic_only && RB >= 4) {
+        gauss_rows_w_kernel<<<dim3((H + RB - 1) / RB, T), 256, wbytes + RB * per_row, st>>>(src, dst, H, W, RB, w, r, cut_mode, remove_thrd,
+                                                                                            std_k, std_eps, stats_ull);
+      } else {
+        gauss_pass_kernel<1><<<grid, 256, smem(W, r), st>>>(src, dst, H, W, w, r, cut_mode, remove_thrd, std_k, std_eps, stats_ull, want_max);
+      }
+    } else {
+      if (!generic_only) {
+        const long long px = static_cast<long long>(H) * W;
+        gauss_chan_kernel<<<dim3(static_cast<unsigned>((px + 255) / 256), T), 256, wbytes, st>>>(src, dst, px, frame_n, w, r, cut_mode, remove_thrd,
+                                                                                               std_k, std_eps, stats_ull, want_max);
+      } else {
+        gauss_pass_kernel<2><<<grid, 256, smem(3, r), st>>>(src, dst, H, W, w, r, cut_mode, remove_thrd, std_k, std_eps, stats_ull, want_max);
+      }
+    }
+    MOFO_LAUNCH_CHECK("gauss pass");
+    return MOFO_OK;
+  };
+  int rc;
   // gaussian_filter(sigma = before): H, W, channel axis in turn; the last pass also reduces the frame maximum
-  gauss_pass_kernel<0><<<grid, 256, smem(H, r_before), st>>>(frames, bufA, H, W, w_before, r_before, 0, 0.0, 0.0, 0.0, stats_ull, 0);
-  MOFO_LAUNCH_CHECK("gauss_pass_kernel<0>");
-  gauss_pass_kernel<1><<<grid, 256, smem(W, r_before), st>>>(bufA, bufB, H, W, w_before, r_before, 0, 0.0, 0.0, 0.0, stats_ull, 0);
-  MOFO_LAUNCH_CHECK("gauss_pass_kernel<1>");
-  gauss_pass_kernel<2><<<grid, 256, smem(3, r_before), st>>>(bufB, bufA, H, W, w_before, r_before, 0, 0.0, 0.0, 0.0, stats_ull, 1);
-  MOFO_LAUNCH_CHECK("gauss_pass_kernel<2>");
+  if ((rc = pass(0, frames, bufA, w_before, r_before, 0, 0)) != MOFO_OK) return rc;
+  if ((rc = pass(1, bufA, bufB, w_before, r_before, 0, 0)) != MOFO_OK) return rc;
+  if ((rc = pass(2, bufB, bufA, w_before, r_before, 0, 1)) != MOFO_OK) return rc;
   box_stats_kernel<<<dim3(static_cast<unsigned>((frame_n + 4095) / 4096), T), 256, 0, st>>>(bufA, frame_n, remove_thrd, stats_ull);
   MOFO_LAUNCH_CHECK("box_stats_kernel");
   // gaussian_filter(sigma = after) of the doubly thresholded frame; the thresholds are applied as the bytes are read
-  gauss_pass_kernel<0><<<grid, 256, smem(H, r_after), st>>>(bufA, bufB, H, W, w_after, r_after, 1, remove_thrd, std_k, std_eps, stats_ull, 0);
-  MOFO_LAUNCH_CHECK("gauss_pass_kernel<0>");
-  gauss_pass_kernel<1><<<grid, 256, smem(W, r_after), st>>>(bufB, bufA, H, W, w_after, r_after, 0, 0.0, 0.0, 0.0, stats_ull, 0);
-  MOFO_LAUNCH_CHECK("gauss_pass_kernel<1>");
-  gauss_pass_kernel<2><<<grid, 256, smem(3, r_after), st>>>(bufA, filtered, H, W, w_after, r_after, 0, 0.0, 0.0, 0.0, stats_ull, 0);
-  MOFO_LAUNCH_CHECK("gauss_pass_kernel<2>");
+  if ((rc = pass(0, bufA, bufB, w_after, r_after, 1, 0)) != MOFO_OK) return rc;
+  if ((rc = pass(1, bufB, bufA, w_after, r_after, 0, 0)) != MOFO_OK) return rc;
+  if ((rc = pass(2, bufA, filtered, w_after, r_after, 0, 0)) != MOFO_OK) return rc;
   const long long pixels = static_cast<long long>(T) * H * W;
   gray_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, st>>>(filtered, pixels, gray);
   MOFO_LAUNCH_CHECK("gray_kernel");

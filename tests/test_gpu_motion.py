@@ -54,10 +54,17 @@ def test_box_filter_golden():
     assert np.array_equal(gray.cpu().numpy(), GOLD["box_gray"]), _diff(gray.cpu().numpy(), GOLD["box_gray"])
 
 
-@pytest.mark.parametrize("T,H,W", [(3, 240, 320), (2, 37, 53), (1, 130, 70)])
-def test_box_filter_vs_oracle(T, H, W):
+@pytest.mark.parametrize("T,H,W,generic", [(3, 240, 320, False), (2, 37, 53, False), (1, 130, 70, False), (1, 700, 24, False),
+                                             (2, 61, 95, True)])
+def test_box_filter_vs_oracle(T, H, W, generic, monkeypatch):
+    """generic=True forces the table-driven fallback kernels (what frames too large for the staged kernels' shared-memory
+    buffers get; H = 700 takes the fallback for the H pass on its own)."""
     from mofo_b200 import motion_boxes as mb
     from oracle import motion_oracle as mo
+    if generic:
+        monkeypatch.setenv("MOFO_MOTION_GENERIC", "1")
+    else:
+        monkeypatch.delenv("MOFO_MOTION_GENERIC", raising=False)
     rng = np.random.default_rng(H)
     yy, xx = np.mgrid[:H, :W]
     frames = np.zeros((T, H, W, 3), np.uint8)
