@@ -21,6 +21,9 @@
 
 namespace mofo {
 
+#ifndef MOFO_ATTN_PAIRBAR
+#define MOFO_ATTN_PAIRBAR 1
+#endif
 #ifndef MOFO_ATTN_PAD
 #define MOFO_ATTN_PAD 0          // tuning aid: extra dynamic smem per CTA to force lower occupancy in variant builds
 #endif
@@ -144,7 +147,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     xch[half * 128 + row] = __float2bfloat16_ru(mx);
     TRACE_AT(j, 3);
+#if MOFO_ATTN_PAIRBAR
+    // the row maximum is exchanged between the two warps that share these 32 rows only (named barrier, 64 threads): nothing
+    // else in the CTA depends on this point, and a CTA-wide barrier made every warp wait for the slowest pair (ncu, round 2:
+    // 7.7 % of the kernel's stall samples sat on the instruction behind it).  xch is rewritten only after the CTA-wide
+    // barrier below, so the partner's read of this iteration is always complete.
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+#else
     __syncthreads();
+#endif
     TRACE_AT(j, 4);
     mx = fmaxf(__bfloat162float(xch[row]), __bfloat162float(xch[128 + row])) * c;
     const bool bump = mx > m_ref + 8.0f;

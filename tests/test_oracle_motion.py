@@ -59,3 +59,13 @@ def test_magnitude_gray_and_cast_vs_cv2():
     big = (rng.random(4096) * 9000).astype(np.float32)
     with np.errstate(invalid="ignore"):
         assert np.array_equal(big.astype(np.uint8), mo.wrap_u8(big))
+
+
+def test_product_weight_table_matches_scipy_formula():
+    """Host logic of mofo_b200/motion_boxes.py (no GPU): the weight table handed to the kernels is scipy's kernel, by distance."""
+    from mofo_b200 import motion_boxes as mb
+    for sigma in (1, 30, 2.5):
+        w, r = mo.gaussian_weights(sigma)
+        got = mb.gaussian_weights(sigma).numpy()
+        assert got.dtype == np.float64 and got.shape == (r + 1,)
+        assert np.array_equal(got, w[r:]) and np.array_equal(got, w[:r + 1][::-1])
