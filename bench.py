@@ -713,7 +713,10 @@ def run_motion(args):
                     "api": "mofo_b200.motion_boxes.motion_map + MotionMapFilter.filter on pinned host uint8 flows; gray maps copied back to pinned host memory"},
             "roofline": {"bound": "hbm", "kernel": "motion_map_kernel (stage A; stage B is bound by the float64 pipe, see stage_b)",
                          "achieved": bytes_a / (ta * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": bytes_a / (ta * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "frac": bytes_a / (ta * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r02_ncu_motion_full.txt):
+                         # the 11.06 MB video is read once; the map (11.06 MB) was still in L2 when the next kernel consumed it
+                         "traffic": 11.08e6,
                          "algorithmic_bytes_per_launch": bytes_a, "kernel_ms": ta, "peak_source": peaks["source"]},
             "stage_b": {"kernels": "3 x gauss_pass (sigma 1) + box_stats + 3 x gauss_pass (sigma 30, 241 taps in scipy's float64 order) + gray",
                         "ms": tb, "share_of_step": tb / (ta + tb), "fp64_issue_slots": slots_b,
