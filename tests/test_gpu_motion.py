@@ -95,3 +95,32 @@ def test_motion_pipeline_properties_full_size():
     const = torch.full((48, 240, 320, 3), 93, dtype=torch.uint8, device="cuda")
     assert int(mb.motion_map(const).max()) == 0
     assert int(a[:, :8].max()) == 0 and int(a[:, :, -8:].max()) == 0 and int(a[:, 8:-8, 8:-8].max()) > 0
+
+
+def test_other_sigmas_and_thresholds_vs_oracle():
+    """Nothing in the kernels is tied to the reference's constants (sigma 1 / 30, 0.4, 1.5)."""
+    from mofo_b200 import motion_boxes as mb
+    from oracle import motion_oracle as mo
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (2, 45, 77, 3), dtype=np.uint8)
+    frames[:, 10:30, 20:50] = np.clip(frames[:, 10:30, 20:50].astype(np.int64) + 90, 0, 255)
+    kw = dict(before_sigma=2.5, remove_thrd=0.3, std_k=0.7, after_sigma=6)
+    filt, gray = mb.filter_motion_map(torch.from_numpy(frames).cuda(), **kw)
+    for t in range(2):
+        wf, wg = mo.filter_frame(frames[t], **kw)
+        assert np.array_equal(filt[t].cpu().numpy(), wf), _diff(filt[t].cpu().numpy(), wf)
+        assert np.array_equal(gray[t].cpu().numpy(), wg)
+
+
+def test_motion_calls_reject_bad_arguments():
+    from mofo_b200 import _lib
+    flows = torch.zeros(4, 16, 16, 3, dtype=torch.uint8, device="cuda")
+    out = torch.empty(4, 16, 16, 1, dtype=torch.uint8, device="cuda")
+    with pytest.raises(_lib.MofoError):
+        _lib.motion_map(flows, 0, 8, out)                                   # ws < 1
+    with pytest.raises(_lib.MofoError):
+        _lib.motion_map(flows[..., :1].contiguous(), 8, 8, out)             # needs the u and v channels
+    with pytest.raises(AssertionError):
+        _lib.motion_map(flows.cpu(), 8, 8, out)                             # host tensors never reach the library
+    _lib.motion_map(flows, 8, 8, out)                                       # and the library is still usable afterwards
+    assert int(out.max()) == 0
