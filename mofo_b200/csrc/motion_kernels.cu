@@ -34,7 +34,7 @@ __device__ __forceinline__ void flow_window(int idx /*1-based*/, int T, int ws, 
 }
 
 __global__ void __launch_bounds__(MM_TX * MM_TY) motion_map_kernel(const uint8_t* __restrict__ flows, int T, int H, int W, int C,
-                                                                   int ws, int border, uint8_t* __restrict__ out, int OC) {
+                                                                   int ws, int border, uint8_t* __restrict__ out, int OC, int chunk) {
   __shared__ int su[MM_HY][MM_HX], sv[MM_HY][MM_HX];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * MM_TX + tx;
   const int x0 = blockIdx.x * MM_TX, y0 = blockIdx.y * MM_TY;
@@ -51,8 +51,16 @@ __global__ void __launch_bounds__(MM_TX * MM_TY) motion_map_kernel(const uint8_t
     off[k] = (sy * W + sx) * C;
   }
   int au[2] = {0, 0}, av[2] = {0, 0};          // running window sums of the thread's halo positions
-  int cur_lo = 0, cur_hi = 0;                  // frames currently inside the sums
-  for (int t = 0; t < T; ++t) {
+  // blockIdx.z = chunk of `chunk` consecutive frames: a chunk rebuilds its first window from scratch (ws extra frame reads
+  // from L2) and then slides; 300 CTAs walking 48 frames one after the other were latency-bound (78 us per video)
+  const int t_begin = blockIdx.z * chunk, t_end = min(T, t_begin + chunk);
+  int cur_lo, cur_hi;                          // frames currently inside the sums
+  {
+    int lo0, hi0;
+    flow_window(t_begin + 1, T, ws, lo0, hi0);
+    cur_lo = cur_hi = lo0;
+  }
+  for (int t = t_begin; t < t_end; ++t) {
     int lo, hi;
     flow_window(t + 1, T, ws, lo, hi);
     if (lo < cur_lo || hi < cur_hi || lo > cur_hi) {      // never taken for the reference's windows; kept for safety
@@ -396,9 +404,15 @@ int mofo_motion_map(const uint8_t* flows, int T, int H, int W, int C, int ws, in
   MOFO_CHECK_ARG(T > 0 && H > 0 && W > 0 && C >= 2 && ws >= 1 && ws <= 4096 && border >= 0 && out_channels >= 1 &&
                      static_cast<int64_t>(H) * W * C < (int64_t(1) << 31),
                  "motion_map: bad shape T=%d H=%d W=%d C=%d ws=%d border=%d out_channels=%d", T, H, W, C, ws, border, out_channels);
-  const dim3 grid((W + MM_TX - 1) / MM_TX, (H + MM_TY - 1) / MM_TY);
-  MOFO_CHECK_ARG(grid.y <= 65535, "motion_map: H too large");
-  motion_map_kernel<<<grid, dim3(MM_TX, MM_TY), 0, static_cast<cudaStream_t>(stream)>>>(flows, T, H, W, C, ws, border, out, out_channels);
+  // frames per CTA: long enough that sliding beats rebuilding (>= 2 ws), short enough to fill the machine (~8 CTAs per SM)
+  const int tiles = ((W + MM_TX - 1) / MM_TX) * ((H + MM_TY - 1) / MM_TY);
+  int chunk = T;
+  if (getenv("MOFO_MOTION_CHUNK")) chunk = atoi(getenv("MOFO_MOTION_CHUNK"));
+  else while (chunk > 2 * ws && tiles * ((T + chunk - 1) / chunk) < 8 * sm_count()) chunk = (chunk + 1) / 2;
+  if (chunk < 1) chunk = 1;
+  const dim3 grid((W + MM_TX - 1) / MM_TX, (H + MM_TY - 1) / MM_TY, (T + chunk - 1) / chunk);
+  MOFO_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "motion_map: H or T too large");
+  motion_map_kernel<<<grid, dim3(MM_TX, MM_TY), 0, static_cast<cudaStream_t>(stream)>>>(flows, T, H, W, C, ws, border, out, out_channels, chunk);
   MOFO_LAUNCH_CHECK("motion_map_kernel");
   return MOFO_OK;
 }

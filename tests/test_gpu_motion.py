@@ -124,3 +124,16 @@ def test_motion_calls_reject_bad_arguments():
         _lib.motion_map(flows.cpu(), 8, 8, out)                             # host tensors never reach the library
     _lib.motion_map(flows, 8, 8, out)                                       # and the library is still usable afterwards
     assert int(out.max()) == 0
+
+
+@pytest.mark.parametrize("chunk", ["1", "3", "1000"])
+def test_motion_map_frame_chunking_is_invisible(chunk, monkeypatch):
+    """The kernel splits a video into chunks of frames (each rebuilds its first window): any chunk length gives the same map."""
+    from mofo_b200 import motion_boxes as mb
+    from oracle import motion_oracle as mo
+    rng = np.random.default_rng(9)
+    flows = rng.integers(0, 256, (19, 40, 36, 3), dtype=np.uint8)
+    monkeypatch.setenv("MOFO_MOTION_CHUNK", chunk)
+    got = mb.motion_map(torch.from_numpy(flows).cuda(), ws=8, channels=1).cpu().numpy()[..., 0]
+    want = mo.motion_map(flows, ws=8)
+    assert np.array_equal(got, want), _diff(got, want)
