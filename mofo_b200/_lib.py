@@ -225,7 +225,8 @@ def gemm_wgrad_grouped(problems, M):
     n = len(problems)
     if n == 0:
         return
-    if n > 4 or any(X.shape[1] % 192 != 0 for _, X, _, _, _ in problems):
+    ks = [X.shape[1] for _, X, _, _, _ in problems]
+    if n > 4 or not (all(k % 192 == 0 for k in ks) or all(k % 256 == 0 for k in ks)):
         for dY, X, dW, dbias, skip in problems:
             gemm_wgrad(dY, X, dW, M=M, dbias=dbias, skip=skip)
         return

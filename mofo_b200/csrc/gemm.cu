@@ -1068,6 +1068,47 @@ static int launch_wgrad(const CUtensorMap& tY, const CUtensorMap& tX, int M, int
 
 using namespace mofo;
 
+template <int BNW>
+static int launch_wgrad_grouped(int n, const mofo_bf16* const* dY, const int* ldy, const mofo_bf16* const* X, const int* ldx, int M,
+                                const int* N, const int* K, float* const* dW, const int* ldw, float* const* dbias,
+                                const int* dbias_skip_lo, const int* dbias_skip_hi, void* stream) {
+  static WgGroup g;                      // ~1.3 KB: filled on the host, passed by value as the kernel parameter
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    MOFO_CHECK_ARG(dY[i] && X[i] && dW[i] && N[i] > 0 && K[i] > 0 && N[i] % 8 == 0 && K[i] % BNW == 0,
+                   "gemm_wgrad_grouped: problem %d: N=%d K=%d (need N%%8==0, K%%%d==0)", i, N[i], K[i], BNW);
+    MOFO_CHECK_ARG(ldy[i] >= N[i] && ldx[i] >= K[i] && ldy[i] % 8 == 0 && ldx[i] % 8 == 0 && ldw[i] >= K[i] && ldw[i] % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(dW[i]) & 15) == 0, "gemm_wgrad_grouped: problem %d: bad leading dimension / alignment", i);
+    int rc = get_tmap(&g.p[i].tmY, dY[i], M, N[i], ldy[i], 64);
+    if (rc) return rc;
+    rc = get_tmap(&g.p[i].tmX, X[i], M, K[i], ldx[i], 64);
+    if (rc) return rc;
+    g.p[i].dW = dW[i]; g.p[i].dbias = dbias ? dbias[i] : nullptr;
+    g.p[i].N = N[i]; g.p[i].K = K[i]; g.p[i].ldw = ldw[i];
+    g.p[i].skip_lo = dbias_skip_lo ? dbias_skip_lo[i] : 0; g.p[i].skip_hi = dbias_skip_hi ? dbias_skip_hi[i] : 0;
+    g.p[i].tile0 = tiles;
+    tiles += ((N[i] + 127) / 128) * (K[i] / BNW);
+  }
+  g.n = n; g.M = M;
+  const int kblocks = (M + BK - 1) / BK;
+  int splits = (2 * sm_count()) / tiles;                    // ~2 waves of equal-sized work items
+  if (splits < 1) splits = 1;
+  if (splits > kblocks) splits = kblocks;
+  g.kb_per_split = (kblocks + splits - 1) / splits;
+  splits = (kblocks + g.kb_per_split - 1) / g.kb_per_split;
+  using Cfg = WgCfg<BNW, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MOFO_CUDA(cudaFuncSetAttribute(gemm_wgrad_grouped_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  MOFO_CUDA(launch_pdl(gemm_wgrad_grouped_kernel<BNW>, dim3(tiles, splits), dim3(WG_THREADS), Cfg::SMEM_BYTES,
+                       static_cast<cudaStream_t>(stream), g));
+  return MOFO_OK;
+}
+
 extern "C" {
 
 int mofo_gemm_tn(const mofo_bf16* A, int lda, const mofo_bf16* B, int ldb, int M, int N, int K, int epilogue,
@@ -1149,42 +1190,13 @@ int mofo_gemm_wgrad_grouped(int n, const mofo_bf16* const* dY, const int* ldy, c
                             const int* N, const int* K, float* const* dW, const int* ldw, float* const* dbias,
                             const int* dbias_skip_lo, const int* dbias_skip_hi, void* stream) {
   MOFO_CHECK_ARG(n >= 1 && n <= WG_MAX_GROUP && dY && X && N && K && dW && ldy && ldx && ldw && M > 0, "gemm_wgrad_grouped: bad argument (1..%d problems)", WG_MAX_GROUP);
-  constexpr int BNW = 192;
-  static WgGroup g;                      // ~1.3 KB: filled on the host, passed by value as the kernel parameter
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
-  int tiles = 0;
-  for (int i = 0; i < n; ++i) {
-    MOFO_CHECK_ARG(dY[i] && X[i] && dW[i] && N[i] > 0 && K[i] > 0 && N[i] % 8 == 0 && K[i] % BNW == 0,
-                   "gemm_wgrad_grouped: problem %d: N=%d K=%d (need N%%8==0, K%%192==0)", i, N[i], K[i]);
-    MOFO_CHECK_ARG(ldy[i] >= N[i] && ldx[i] >= K[i] && ldy[i] % 8 == 0 && ldx[i] % 8 == 0 && ldw[i] >= K[i] && ldw[i] % 4 == 0 &&
-                   (reinterpret_cast<uintptr_t>(dW[i]) & 15) == 0, "gemm_wgrad_grouped: problem %d: bad leading dimension / alignment", i);
-    int rc = get_tmap(&g.p[i].tmY, dY[i], M, N[i], ldy[i], 64);
-    if (rc) return rc;
-    rc = get_tmap(&g.p[i].tmX, X[i], M, K[i], ldx[i], 64);
-    if (rc) return rc;
-    g.p[i].dW = dW[i]; g.p[i].dbias = dbias ? dbias[i] : nullptr;
-    g.p[i].N = N[i]; g.p[i].K = K[i]; g.p[i].ldw = ldw[i];
-    g.p[i].skip_lo = dbias_skip_lo ? dbias_skip_lo[i] : 0; g.p[i].skip_hi = dbias_skip_hi ? dbias_skip_hi[i] : 0;
-    g.p[i].tile0 = tiles;
-    tiles += ((N[i] + 127) / 128) * (K[i] / BNW);
-  }
-  g.n = n; g.M = M;
-  const int kblocks = (M + BK - 1) / BK;
-  int splits = (2 * sm_count()) / tiles;                    // ~2 waves of equal-sized work items
-  if (splits < 1) splits = 1;
-  if (splits > kblocks) splits = kblocks;
-  g.kb_per_split = (kblocks + splits - 1) / splits;
-  splits = (kblocks + g.kb_per_split - 1) / g.kb_per_split;
-  using Cfg = WgCfg<BNW, 1>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MOFO_CUDA(cudaFuncSetAttribute(gemm_wgrad_grouped_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
-  MOFO_CUDA(launch_pdl(gemm_wgrad_grouped_kernel<BNW>, dim3(tiles, splits), dim3(WG_THREADS), Cfg::SMEM_BYTES,
-                       static_cast<cudaStream_t>(stream), g));
-  return MOFO_OK;
+  // one k-tile width for the whole group: 192 when every K divides by it (ViT-S / ViT-B: 384, 768, 1536, 3072), else 256
+  // (ViT-L: 1024, 4096; decoder width 512)
+  bool all192 = true, all256 = true;
+  for (int i = 0; i < n; ++i) { all192 = all192 && K[i] > 0 && K[i] % 192 == 0; all256 = all256 && K[i] > 0 && K[i] % 256 == 0; }
+  MOFO_CHECK_ARG(all192 || all256, "gemm_wgrad_grouped: every K must be a multiple of 192, or every K a multiple of 256");
+  if (all192) return launch_wgrad_grouped<192>(n, dY, ldy, X, ldx, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, stream);
+  return launch_wgrad_grouped<256>(n, dY, ldy, X, ldx, M, N, K, dW, ldw, dbias, dbias_skip_lo, dbias_skip_hi, stream);
 }
 
 }  // extern "C"

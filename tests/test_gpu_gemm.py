@@ -121,7 +121,7 @@ def test_gemm_rejects_bad_args(lib):
         lib.gemm_tn(A, B, lib.EPI_PLAIN_BF16, out)      # K % 8 != 0
 
 
-@pytest.mark.parametrize("M,D", [(5120, 768), (6272, 384), (320, 192)])
+@pytest.mark.parametrize("M,D", [(5120, 768), (6272, 384), (320, 192), (2560, 1024), (300, 512)])      # D = 1024 / 512: the 256-wide k-tile group
 def test_gemm_wgrad_grouped_matches_individual_calls(lib, M, D):
     """The four weight gradients of a transformer block in one grouped launch (fc2, fc1, proj, qkv with its skipped bias window)."""
     torch.manual_seed(M + D)
@@ -141,7 +141,7 @@ def test_gemm_wgrad_grouped_matches_individual_calls(lib, M, D):
         ref = pairs[i][0].float().t() @ pairs[i][1].float()
         assert rel(got_w[i], ref) < 2e-5
     assert got_b[3][D:2 * D].abs().max().item() == 0
-    # a shape the grouped kernel does not take (K % 192 != 0) falls back to individual launches
+    # a shape the grouped kernel does not take (K % 192 != 0 and K % 256 != 0) falls back to individual launches
     dY2, X2 = t(256, 128), t(256, 128)
     w2 = torch.zeros(128, 128, device="cuda")
     lib.gemm_wgrad_grouped([(dY2, X2, w2, None, (0, 0))], 256)
