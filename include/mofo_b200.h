@@ -118,7 +118,8 @@ int mofo_gemm_wgrad(const mofo_bf16* dY, int ldy, const mofo_bf16* X, int ldx, i
 
 /* mofo_gemm_wgrad_grouped: n (1..4) independent mofo_gemm_wgrad problems that share the reduction length M, in ONE launch
  * (HOST arrays of n device pointers / sizes; dbias, dbias_skip_lo, dbias_skip_hi may be NULL).  The four weight gradients of
- * a transformer block (fc2, fc1, proj, qkv) are independent and off the backward critical path.  Needs K[i] % 192 == 0. */
+ * a transformer block (fc2, fc1, proj, qkv) are independent and off the backward critical path.  One k-tile width serves the
+ * whole group: every K[i] % 192 == 0 (ViT-S / ViT-B widths), or every K[i] % 256 == 0 (ViT-L: 1024 / 4096, decoder 512). */
 int mofo_gemm_wgrad_grouped(int n, const mofo_bf16* const* dY, const int* ldy, const mofo_bf16* const* X, const int* ldx, int M,
                             const int* N, const int* K, float* const* dW, const int* ldw, float* const* dbias,
                             const int* dbias_skip_lo, const int* dbias_skip_hi, void* stream);
