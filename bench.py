@@ -646,6 +646,8 @@ def run_motion(args):
     """One step = one flow video through mofo_motion_map + mofo_motion_box_filter (9 kernel launches).  Inputs resident in HBM:
     16 rotating videos (177 MB > L2).  e2e: pinned host flows in, gray maps back to pinned host memory, inside the timed region.
     Independent videos: N GPUs would run N replicas (no exchange); measured on one."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return                      # replicas only: videos are independent, no exchange step; one replica is measured (rank 0)
     import torch
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
@@ -707,7 +709,8 @@ def run_motion(args):
     fp64_peak = 148 * 64 * (clocks["sm_mhz"] or 1900.0) * 1e6   # DP lanes x SMs x clock: one DMUL or DADD per lane and cycle
     line = {"metric": MOTION_METRIC, "value": T / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 / f64", "data": "synthetic",
-            "config": {"workload": motion_workload(), "l2": "16 rotating videos (177 MB) > L2"},
+            "config": {"workload": motion_workload(), "l2": "16 rotating videos (177 MB) > L2",
+                       "parallelism": "replicas only (independent videos, no collective); one replica measured"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": T / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": T * H * W * 3, "d2h_bytes_per_step": T * H * W,
                     "api": "mofo_b200.motion_boxes.motion_map + MotionMapFilter.filter on pinned host uint8 flows; gray maps copied back to pinned host memory"},
